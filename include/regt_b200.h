@@ -1,0 +1,169 @@
+/*
+ * regt_b200.h -- C-ABI of the B200-native RegT-GCN hot path (libregt_b200.so).
+ *
+ * The reference (raynbowy23/RegT-GCN) has no FFI layer: its boundary for this path is the
+ * Python nn.Module surface.  Every entry point below therefore names the reference
+ * interface whose arithmetic it replaces (file:line under the reference tree); the
+ * Python binding a maintainer adds on the reference side is shown in INTEGRATION.md and
+ * implemented in regt-gcn_b200/regt_b200/_lib.py + models/*.py.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless the comment says "host";
+ *  - no ownership transfer and no hidden allocation: the caller passes a workspace of at
+ *    least regt_workspace_bytes() bytes (256-byte aligned);
+ *  - every function returns 0 on success, <0 on error; regt_last_error() returns a
+ *    thread-local message for the last failure on the calling thread;
+ *  - work is enqueued on `stream`; nothing synchronises the device except the two
+ *    regt_*_plan_build calls (they return counts to the host);
+ *  - thread-compatible: no global state except the thread-local error string.
+ */
+#ifndef REGT_B200_H
+#define REGT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGT_VERSION 100 /* 0.1.0 */
+#define REGT_F 8         /* node features; fixed by the reference (run.py:116) */
+
+/* precision of the H x H contractions */
+#define REGT_PREC_FP32 0  /* FFMA, fp32 everywhere (parity mode, all shapes)            */
+#define REGT_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-pass split: fp32-equivalent accuracy  */
+#define REGT_PREC_BF16 2  /* tcgen05 kind::f16 bf16 operands, fp32 accumulate            */
+
+typedef void* regt_stream_t; /* cudaStream_t */
+
+/* ---- K1: static-graph plan ---------------------------------------------------------- */
+/* CSR by destination of the normalised operators, built once per static graph.
+ * Canonical order (bit-exact contract): PyG's post-normalisation edge list, stable-sorted
+ * by destination; duplicates kept. */
+typedef struct regt_graph_plan {
+  int32_t N;        /* nodes */
+  int32_t nnz_gcn;  /* E' + N  (E' = non-loop edges of edge_index)                       */
+  int32_t nnz_cheb; /* non-loop edges of all regional lists                              */
+  int32_t nseg;     /* number of (node, region) segments with at least one in-edge       */
+  int32_t R;        /* number of regional edge lists (1 for A3TGCN)                      */
+  int32_t _pad;
+  const int32_t* g_rowptr; /* [N+1]                                                      */
+  const int32_t* g_col;    /* [nnz_gcn] sources                                          */
+  const float* g_val;      /* [nnz_gcn] D~^-1/2 (A+I) D~^-1/2 entries (gcn_norm)          */
+  const int32_t* c_rowptr; /* [N+1]                                                      */
+  const int32_t* c_col;    /* [nnz_cheb]                                                 */
+  const float* c_val;      /* [nnz_cheb] -D^-1/2 A D^-1/2 entries (ChebConv, K=2, sym)    */
+  const int32_t* c_reg;    /* [nnz_cheb] regional list id of every entry                  */
+  const int32_t* seg_ptr;  /* [N+1]   segments of node n are seg_ptr[n]..seg_ptr[n+1]     */
+  const int32_t* seg_eptr; /* [nseg+1] entry range of each segment inside the cheb CSR    */
+  const int32_t* seg_reg;  /* [nseg]                                                     */
+  const int32_t* seg_node; /* [nseg]                                                     */
+  const int32_t* rseg_ptr; /* [R+1]   segments grouped by region: rseg_list[rseg_ptr[r]..]    */
+  const int32_t* rseg_list;/* [nseg]  segment ids, ascending inside a region                  */
+} regt_graph_plan;
+
+/* replaces torch_geometric gcn_norm + scatter index of GCNConv.propagate, which the
+ * reference re-runs 3*T times per sample (models/utils.py:169,175,181; cached=False :81).
+ * edge_index int64 [2,E] (row 0 = source, row 1 = target), edge_weight f32 [E] or NULL.
+ * Outputs: rowptr [N+1], col/val [E+N] (upper bound), eid [E+N] = position of every CSR
+ * entry in PyG's post-normalisation edge list (for tests).  *nnz_out (host) = E'+N.   */
+size_t regt_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int regt_gcn_plan_build(const int64_t* edge_index, const float* edge_weight, int64_t E, int64_t N,
+                        int32_t* rowptr, int32_t* col, float* val, int32_t* eid, int32_t* nnz_out /*host*/,
+                        void* workspace, size_t workspace_bytes, regt_stream_t stream);
+
+/* replaces torch_geometric get_laplacian('sym') + Chebyshev rescale inside ChebConv.forward,
+ * which the reference re-runs R*T times per sample (models/RegionalTemporalGCN.py:136-140,
+ * models/TemporalGCN.py:88).  The R regional lists are passed concatenated:
+ * edge_index int64 [2,E_tot], edge_weight f32 [E_tot] or NULL, list_ptr (host) int64 [R+1].
+ * Each list is normalised on its own (source degree inside that list).
+ * Outputs (upper bounds): rowptr [N+1], col/val/reg/eid [E_tot], seg_ptr [N+1],
+ * seg_eptr [E_tot+1], seg_reg/seg_node/rseg_list [E_tot], rseg_ptr [R+1],
+ * region_of [N] (-1 untouched, -2 in >1 list).  counts_out (host) int32[2] = {nnz, nseg}. */
+int regt_cheb_plan_build(const int64_t* edge_index, const float* edge_weight, const int64_t* list_ptr /*host*/,
+                         int32_t R, int64_t E_tot, int64_t N, int32_t* rowptr, int32_t* col, float* val,
+                         int32_t* reg, int32_t* eid, int32_t* seg_ptr, int32_t* seg_eptr, int32_t* seg_reg,
+                         int32_t* seg_node, int32_t* rseg_ptr, int32_t* rseg_list, int32_t* region_of,
+                         int32_t* counts_out /*host*/, void* workspace, size_t workspace_bytes,
+                         regt_stream_t stream);
+
+/* ---- stand-alone F-wide SpMM (BASELINE metric "SpMM HBM GB/s") ----------------------- */
+/* y[b,n,:] = sum_{e in row n} val[e] * x[b,col[e],:]  for rows of `width` floats
+ * (width = F*T = 96 for the x[B,N,F,T] layout of load_dataset.py:456; width % 4 == 0).
+ * Replaces GCNConv.propagate's index_select/mul/scatter_add (models/utils.py:169).      */
+int regt_spmm_f8(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
+                 int32_t B, int32_t N, int32_t width, regt_stream_t stream);
+
+/* ---- the cell + head ---------------------------------------------------------------- */
+typedef struct regt_params {            /* reference state_dict layouts      */
+  float* attention;                     /* tgnn._attention [T]                             */
+  float* conv_w[3];                     /* tgnn._base_tgcn.conv_{z,r,h}.lin.weight [H,F]    */
+  float* conv_b[3];                     /* tgnn._base_tgcn.conv_{z,r,h}.bias [H]            */
+  float* lin_w[3];                      /* tgnn._base_tgcn.linear_{z,r,h}.weight [H,2H]     */
+  float* lin_b[3];                      /* tgnn._base_tgcn.linear_{z,r,h}.bias [H]          */
+  float* cheb_w0;                       /* tgnn.conv.lins.0.weight [H,F]                   */
+  float* cheb_w1;                       /* tgnn.conv.lins.1.weight [H,F]                   */
+  float* cheb_b;                        /* tgnn.conv.bias [H]                              */
+  float* comb_w;                        /* tgnn.linear.weight [H,R*H]   (regional only)     */
+  float* comb_b;                        /* tgnn.linear.bias [H]         (regional only)     */
+  float* head_w1;                       /* linear1.weight [128,H]                          */
+  float* head_b1;                       /* linear1.bias [128]                              */
+  float* head_w2;                       /* linear2.weight [O,128]                          */
+  float* head_b2;                       /* linear2.bias [O]                                */
+} regt_params;
+
+#define REGT_MODE_REGIONAL 1 /* RegionalA3TGCN: R ChebConvs -> Linear(R*H,H) -> leaky_relu  */
+#define REGT_MODE_A3TGCN 0   /* A3TGCN: h = ChebConv(X_t) on the full graph                */
+#define REGT_MODE_TGCN 2     /* bare TGCN cell: h supplied by the caller (or zeros)         */
+
+typedef struct regt_args {
+  int32_t B, N, T, H, O;  /* x is [B,N,F,T]; T = periods; O = output_dim                  */
+  int32_t mode;           /* REGT_MODE_*                                                  */
+  int32_t precision;      /* REGT_PREC_*                                                  */
+  int32_t accumulate;     /* backward: 0 overwrite param grads, 1 add into them           */
+  regt_graph_plan plan;
+  const float* x;         /* [B,N,F,T] f32, T innermost (load_dataset.py:456)             */
+  const float* y;         /* [B,N,O] or NULL: if set head_forward also writes loss, d_out  */
+  const float* h_ext;     /* REGT_MODE_TGCN: [B,N,T,H] state or NULL (= zeros)            */
+  regt_params p;          /* parameters                                                   */
+  regt_params g;          /* parameter gradients (same layouts; any may be NULL)          */
+  float* out_hidden;      /* [B,N,H]  cell output (pre-ReLU), models/RegionalTemporalGCN.py:34 */
+  float* out;             /* [B,N,O]                                                      */
+  float* loss;            /* [1]  sum_b mean_{n,o} (out-y)^2   (run.py:180)                */
+  float* d_out;           /* [B,N,O]  gradient of loss wrt out (in/out)                   */
+  float* d_hidden;        /* [B,N,H]  extra gradient flowing into out_hidden, or NULL     */
+  float* d_h_ext;         /* REGT_MODE_TGCN: [B,N,T,H] gradient wrt h_ext, or NULL        */
+  void* workspace;        /* regt_workspace_bytes(args) bytes, preserved fwd -> bwd       */
+  size_t workspace_bytes;
+  regt_stream_t stream;
+} regt_args;
+
+size_t regt_workspace_bytes(const regt_args* a);
+
+/* replaces RegionalA3TGCN.forward (models/RegionalTemporalGCN.py:114-149) /
+ * A3TGCN.forward (models/TemporalGCN.py:75-91) / TGCN.forward (models/utils.py:190-203):
+ * weight collapse, F-wide SpMM, regional combine, GRU gates, period attention.
+ * Writes out_hidden and the saved activations inside the workspace.                    */
+int regt_cell_forward(const regt_args* a);
+/* replaces the head of RegionalTemporalGCN.forward / TemporalGCN.forward
+ * (models/RegionalTemporalGCN.py:35-38, models/TemporalGCN.py:28-31) and, when y is
+ * given, the loss of the call site (run.py:180).                                        */
+int regt_head_forward(const regt_args* a);
+/* autograd of the head (run.py:190): consumes d_out, writes g.head_* and the gradient
+ * wrt out_hidden (kept in the workspace for regt_cell_backward).                        */
+int regt_head_backward(const regt_args* a);
+/* autograd of the cell (run.py:190): all parameter gradients of the cell.  No gradient
+ * wrt x is produced (x is data in the reference: batch.x never requires grad).          */
+int regt_cell_backward(const regt_args* a);
+
+int regt_version(void);
+const char* regt_last_error(void);
+/* number of kernel launches issued by this library on the calling thread since the last
+ * call with reset != 0 (bench.py's "gpu_launches").                                     */
+int64_t regt_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGT_B200_H */

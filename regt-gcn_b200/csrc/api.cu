@@ -1,0 +1,111 @@
+// C-ABI entry points of the cell + head (include/regt_b200.h) and the workspace layout.
+#include "common.cuh"
+
+namespace regt {
+
+constexpr int F = REGT_F;
+
+int cell_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st);
+int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st);
+int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st);
+
+Layout make_layout(const regt_args* a, void* base) {
+  Layout L{};
+  Carver c(base);
+  const size_t H = a->H, T = a->T, R = a->plan.R > 0 ? a->plan.R : 1, O = a->O;
+  const size_t BN = (size_t)a->B * a->N, rows = BN * T;
+  const size_t nseg = a->plan.nseg;
+  L.Wzr = c.take<float>((F + H) * 2 * H);
+  L.Wc = c.take<float>((F + H) * H);
+  L.czr = c.take<float>(2 * H);
+  L.cc = c.take<float>(H);
+  L.M0t = c.take<float>(F * H);
+  L.M1t = c.take<float>(R * F * H);
+  L.c0 = c.take<float>(H);
+  L.Lsum = c.take<float>(H * H);
+  L.probs = c.take<float>(T);
+  L.S = c.take<float>(BN * F * T);
+  L.U = c.take<float>((size_t)a->B * (nseg ? nseg : 1) * F * T);
+  L.h = c.take<float>(rows * H);
+  L.Z = c.take<float>(rows * H);
+  L.Rg = c.take<float>(rows * H);
+  L.Hc = c.take<float>(rows * H);
+  L.hR = c.take<float>(rows * H);
+  L.Hn = c.take<float>(rows * H);
+  L.a1 = c.take<float>(BN * HEAD_HID);
+  L.G = c.take<float>(BN * H);
+  L.d_a1 = c.take<float>(BN * HEAD_HID);
+  L.D = c.take<float>(rows * 4 * H);
+  L.dB = c.take<float>(3 * H * H);
+  L.dP = c.take<float>(3 * H * F);
+  L.dcg = c.take<float>(3 * H);
+  L.dM0 = c.take<float>(H * F);
+  L.dM1 = c.take<float>(R * H * F);
+  L.dc0 = c.take<float>(H);
+  L.dprobs = c.take<float>(T);
+  size_t pf = (size_t)3 * WGRAD_SPLITS * H * H;                    // H x H split-K partials
+  pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * (F + 1));             // F-wide partials
+  pf = max(pf, (size_t)8 * R * H * F);                              // per-region partials
+  pf = max(pf, (size_t)128 * T);                                    // attention partials
+  pf = max(pf, (size_t)32 * (O * HEAD_HID + HEAD_HID * H));         // head split-K partials
+  pf = max(pf, BN / 64 + 2);                                        // loss partials
+  pf += H * HEAD_HID + HEAD_HID * O + 64;                           // transposed head weights (tail)
+  L.part = c.take<float>(pf);
+  L.part_floats = pf;
+  L.total = align_up(c.off, 256);
+  return L;
+}
+
+static int validate(const regt_args* a, const char* who) {
+  REGT_CHECK(a != nullptr, "%s: args is NULL", who);
+  REGT_CHECK(a->B > 0 && a->N > 0 && a->T > 0 && a->O > 0, "%s: bad dims B=%d N=%d T=%d O=%d", who, a->B, a->N, a->T, a->O);
+  REGT_CHECK(a->H >= 8 && a->H % 8 == 0 && a->H <= 1024, "%s: H=%d must be a multiple of 8 in [8,1024]", who, a->H);
+  REGT_CHECK(a->mode >= 0 && a->mode <= 2, "%s: bad mode %d", who, a->mode);
+  REGT_CHECK(a->plan.N == a->N, "%s: plan built for %d nodes, args say %d", who, a->plan.N, a->N);
+  REGT_CHECK((long long)a->B * a->N * a->T < (1ll << 31), "%s: B*N*T overflows int32 rows", who);
+  REGT_CHECK(a->workspace && a->workspace_bytes >= regt_workspace_bytes(a), "%s: workspace missing or too small", who);
+  REGT_CHECK(a->precision >= 0 && a->precision <= 2, "%s: bad precision %d", who, a->precision);
+  return 0;
+}
+
+}  // namespace regt
+
+using namespace regt;
+
+extern "C" size_t regt_workspace_bytes(const regt_args* a) {
+  if (!a) return 0;
+  return make_layout(a, nullptr).total;
+}
+
+extern "C" int regt_cell_forward(const regt_args* a) {
+  if (validate(a, "regt_cell_forward")) return -1;
+  REGT_CHECK(a->x && a->out_hidden, "regt_cell_forward: x / out_hidden is NULL");
+  Layout L = make_layout(a, a->workspace);
+  cudaStream_t st = (cudaStream_t)a->stream;
+  if (a->precision == REGT_PREC_FP32) return cell_forward_fp32(a, L, st);
+  return cell_forward_tc(a, L, st);
+}
+
+extern "C" int regt_cell_backward(const regt_args* a) {
+  if (validate(a, "regt_cell_backward")) return -1;
+  Layout L = make_layout(a, a->workspace);
+  cudaStream_t st = (cudaStream_t)a->stream;
+  if (a->precision == REGT_PREC_FP32) return cell_backward_fp32(a, L, st);
+  return cell_backward_tc(a, L, st);
+}
+
+extern "C" int regt_head_forward(const regt_args* a) {
+  if (validate(a, "regt_head_forward")) return -1;
+  REGT_CHECK(a->out_hidden && a->out, "regt_head_forward: out_hidden / out is NULL");
+  Layout L = make_layout(a, a->workspace);
+  return head_forward_fp32(a, L, (cudaStream_t)a->stream);
+}
+
+extern "C" int regt_head_backward(const regt_args* a) {
+  if (validate(a, "regt_head_backward")) return -1;
+  Layout L = make_layout(a, a->workspace);
+  return head_backward_fp32(a, L, (cudaStream_t)a->stream);
+}

@@ -1,0 +1,106 @@
+// Shared helpers for libregt_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "regt_b200.h"
+
+namespace regt {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define REGT_CHECK(cond, ...)         \
+  do {                                \
+    if (!(cond)) {                    \
+      regt::set_error(__VA_ARGS__);   \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+#define REGT_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      regt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                         \
+    }                                                                                    \
+  } while (0)
+
+#define REGT_LAUNCH_CHECK()                                                              \
+  do {                                                                                   \
+    regt::count_launch();                                                                \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      regt::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -3;                                                                         \
+    }                                                                                    \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// bump allocator over the caller's workspace
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base((char*)p), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = base ? (T*)(base + off) : (T*)nullptr;
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ---- workspace layout shared by forward / backward (cell.cu, head.cu, api.cu) -------
+struct Layout {
+  // collapsed weights (rebuilt every forward: parameters change between steps)
+  float* Wzr;    // [F+H][2H]   rows 0..F-1: (A_g W_g)^T, rows F..: B_g^T ; cols 0..H-1 z, H..2H-1 r
+  float* Wc;     // [F+H][H]
+  float* czr;    // [2H]        A_g b_g + linear_g.bias
+  float* cc;     // [H]
+  float* M0t;    // [F][H]      (sum_r L_r W0)^T          (A3TGCN: W0^T)
+  float* M1t;    // [R][F][H]   (L_r W1)^T                (A3TGCN: W1^T)
+  float* c0;     // [H]         (sum_r L_r) b + b_lin     (A3TGCN: b)
+  float* Lsum;   // [H][H]      sum_r L_r                 (regional only)
+  float* probs;  // [T]
+  // F-wide features
+  float* S;      // [B*N][F][T]      A_hat X
+  float* U;      // [B][nseg][F][T]  L_hat_r X per (node, region) segment
+  // saved planes, row = (b*N+n)*T + t
+  float* h;      // [rows][H]
+  float* Z;
+  float* Rg;
+  float* Hc;     // candidate H~
+  float* hR;     // h * R
+  float* Hn;     // H' (cell output per period)
+  // head
+  float* a1;     // [B*N][128]  relu(linear1(relu(hid)))
+  float* G;      // [B*N][H]    gradient wrt out_hidden
+  float* d_a1;   // [B*N][128]
+  // backward planes
+  float* D;      // [rows][4H]  d_pre_z | d_pre_r | d_pre_h | d_hpre
+  // collapsed-weight gradients
+  float* dB;     // [3][H][H]   dB_z, dB_r, dB_h
+  float* dP;     // [3][H][F]
+  float* dcg;    // [3][H]
+  float* dM0;    // [H][F]
+  float* dM1;    // [R][H][F]
+  float* dc0;    // [H]
+  float* dprobs; // [T]
+  float* part;   // split-K partials
+  size_t part_floats;
+  size_t total;
+};
+
+Layout make_layout(const regt_args* a, void* base);
+
+constexpr int HEAD_HID = 128;  // hidden_dim of the decoder MLP (models/RegionalTemporalGCN.py:19)
+constexpr int WGRAD_SPLITS = 64;
+
+}  // namespace regt

@@ -1,0 +1,98 @@
+"""ctypes binding of libregt_b200.so (include/regt_b200.h).  No torch types cross the ABI:
+only raw device pointers, sizes and the CUDA stream handle.
+
+The library is required: there is no CPU or eager-PyTorch fallback.  If it is missing it is
+built in-tree with nvcc (csrc/build.py); if that fails the error is raised as is."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+vp = C.c_void_p
+
+
+class GraphPlan(C.Structure):
+    _fields_ = [("N", C.c_int32), ("nnz_gcn", C.c_int32), ("nnz_cheb", C.c_int32), ("nseg", C.c_int32),
+                ("R", C.c_int32), ("_pad", C.c_int32),
+                ("g_rowptr", vp), ("g_col", vp), ("g_val", vp),
+                ("c_rowptr", vp), ("c_col", vp), ("c_val", vp), ("c_reg", vp),
+                ("seg_ptr", vp), ("seg_eptr", vp), ("seg_reg", vp), ("seg_node", vp),
+                ("rseg_ptr", vp), ("rseg_list", vp)]
+
+
+class Params(C.Structure):
+    _fields_ = [("attention", vp), ("conv_w", vp * 3), ("conv_b", vp * 3), ("lin_w", vp * 3), ("lin_b", vp * 3),
+                ("cheb_w0", vp), ("cheb_w1", vp), ("cheb_b", vp), ("comb_w", vp), ("comb_b", vp),
+                ("head_w1", vp), ("head_b1", vp), ("head_w2", vp), ("head_b2", vp)]
+
+
+class Args(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("O", C.c_int32),
+                ("mode", C.c_int32), ("precision", C.c_int32), ("accumulate", C.c_int32),
+                ("plan", GraphPlan),
+                ("x", vp), ("y", vp), ("h_ext", vp),
+                ("p", Params), ("g", Params),
+                ("out_hidden", vp), ("out", vp), ("loss", vp), ("d_out", vp), ("d_hidden", vp), ("d_h_ext", vp),
+                ("workspace", vp), ("workspace_bytes", C.c_size_t), ("stream", vp)]
+
+
+MODE_A3TGCN, MODE_REGIONAL, MODE_TGCN = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
+
+EXPORTS = ["regt_version", "regt_last_error", "regt_launch_count", "regt_plan_workspace_bytes",
+           "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_workspace_bytes",
+           "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward"]
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.path.normpath(os.path.join(_HERE, "..", "lib", "libregt_b200.so"))
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        sys.path.insert(0, _CSRC)
+        try:
+            import build as _build  # csrc/build.py
+            _build.build()
+        finally:
+            sys.path.remove(_CSRC)
+    lib = C.CDLL(path)
+    lib.regt_version.restype = C.c_int
+    lib.regt_last_error.restype = C.c_char_p
+    lib.regt_launch_count.restype = C.c_int64
+    lib.regt_launch_count.argtypes = [C.c_int]
+    lib.regt_plan_workspace_bytes.restype = C.c_size_t
+    lib.regt_plan_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.regt_gcn_plan_build.restype = C.c_int
+    lib.regt_gcn_plan_build.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, c_i32p, vp, C.c_size_t, vp]
+    lib.regt_cheb_plan_build.restype = C.c_int
+    lib.regt_cheb_plan_build.argtypes = [vp, vp, c_i64p, C.c_int32, C.c_int64, C.c_int64] + [vp] * 12 + \
+                                        [c_i32p, vp, C.c_size_t, vp]
+    lib.regt_spmm_f8.restype = C.c_int
+    lib.regt_spmm_f8.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.regt_workspace_bytes.restype = C.c_size_t
+    lib.regt_workspace_bytes.argtypes = [C.POINTER(Args)]
+    for name in ("regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(Args)]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {load().regt_last_error().decode()}")
