@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- RegT-GCN hot path: fwd + loss + bwd samples/s on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+One "step" = one pass of the hot path (forward + MSE loss + backward, all parameter gradients)
+over one batch of B synthetic snapshots.  Workload at N=1: BASELINE.json configs[1]
+(A3TGCN/TemporalGCN, METR-LA shape: 207 nodes, 12 periods, batch 64, hidden 64).  For N>1 every
+rank runs the same per-GPU batch on its own synthetic snapshots (weak scaling over the batch
+dimension -- the snapshots are independent units) and the shared-weight gradients are
+all-reduced over NCCL inside the step.
+
+Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset)
+between timed steps, barrier + synchronize on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "regt-gcn_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "regt_gcn_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="2", help="SURVEY 8(d) config id (default 2 = BASELINE configs[1])")
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch B")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--micro-batch", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(w, seconds: float, min_samples: int = 4, warm: int = 1):
+    """times the reference's CPU path (the pure-torch fp32 oracle port: per-call re-normalisation,
+    per-sample and per-period Python loops) on this box's host cores."""
+    from oracle import regt_oracle as O
+    from regt_b200 import workloads as W
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    if w.model == "TemporalGCN":
+        m = O.TemporalGCN(8, w.T, w.O, hidden=w.H)
+    else:
+        m = O.RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R)
+    W.init_params_synthetic(m, 1234)
+    x, y = w.inputs(max(min_samples, 8))
+    g = w.graph_args()
+
+    def one(b):
+        out, _ = m(x[b % x.shape[0]], *g)
+        loss = torch.mean((out - y[b % x.shape[0]]) ** 2)
+        loss.backward()
+
+    for b in range(warm):
+        one(b)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one(n); n += 1
+        el = time.perf_counter() - t0
+        if (el >= seconds and n >= min_samples) or n >= 4096:
+            break
+    return n / el, n, el, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation cannot be imported (torch_geometric is
+    absent and not installable offline), so this arm times the oracle port of it."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from regt_b200 import workloads as W
+    w = W.make_workload(args.workload, args.batch)
+    per_step = 4  # snapshots per "step": a bounded sample of the workload's batch
+    from oracle import regt_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = (O.TemporalGCN(8, w.T, w.O, hidden=w.H) if w.model == "TemporalGCN"
+         else O.RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R))
+    W.init_params_synthetic(m, 1234)
+    x, y = w.inputs(per_step)
+    g = w.graph_args()
+
+    def step():
+        for b in range(per_step):
+            out, _ = m(x[b], *g)
+            torch.mean((out - y[b]) ** 2).backward()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    ts = []
+    budget_t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - budget_t0 > 150:
+            break
+    ms = 1e3 * sum(ts) / len(ts)
+    val = per_step / (ms / 1e3)
+    sample = f"{per_step} of {w.B} snapshots per step, {len(ts)} steps, oracle fp32 port on host cores"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": dict(w.describe(), samples_per_step=per_step),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def kernel_alg_bytes(w, B: int) -> dict:
+    """algorithmic bytes per launch of the two dominant kernels under SURVEY 8(d)'s save-4-planes
+    accounting: per (b,n,t) row the forward cell reads X_t,S_t (2*F*4 B) and
+    writes 4 planes (4*H*4 B); the backward cell reads the 4 planes; weights once per launch."""
+    rows = B * w.N * w.T
+    F, H = 8, w.H
+    wts = (F + H) * 3 * H * 4
+    fwd = rows * (2 * F * 4 + 4 * H * 4) + B * w.N * H * 4 + wts
+    bwd = rows * (4 * H * 4) + B * w.N * H * 4 + wts
+    return {"k_cell_fwd": fwd, "k_cell_bwd": bwd, "k_cell_fwd_tc": fwd, "k_cell_bwd_tc": bwd}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    from models import RegionalTemporalGCN, TemporalGCN
+    from regt_b200 import _lib, workloads as W
+    lib = _lib.load()
+
+    w = W.make_workload(args.workload, args.batch)
+    B = w.B
+    if w.model == "TemporalGCN":
+        model = TemporalGCN(8, w.T, w.O, hidden=w.H, precision=args.precision)
+    else:
+        model = RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R, precision=args.precision)
+    W.init_params_synthetic(model, 1234)
+    model = model.to(dev)
+    graph_args = tuple(None if a is None else a.to(dev) for a in w.graph_args())
+
+    # one flat gradient buffer so that a single NCCL all-reduce covers every shared weight
+    live = [p for n, p in model.named_parameters() if p.requires_grad]
+    offs, tot = [], 0
+    for p in live:
+        offs.append(tot); tot += (p.numel() + 3) // 4 * 4
+    flat = torch.zeros(tot, device=dev)
+    for p, o in zip(live, offs):
+        p.grad = flat[o:o + p.numel()].view_as(p)
+
+    # host (pinned) and device-resident inputs; every rank gets its own snapshots
+    xh, yh = w.inputs(B, seed_offset=rank)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    xd, yd = xh.to(dev), yh.to(dev)
+    loss_h = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def raw_step():
+        return model.fused_step(xd, yd, *graph_args, micro_batch=args.micro_batch)[0]
+
+    # warm-up (eager) -- also builds and caches the static-graph plan (K1), excluded from timing
+    lib.regt_launch_count(1)
+    loss_d = None
+    for _ in range(max(3, args.warmup)):
+        loss_d = raw_step()
+    torch.cuda.synchronize()
+    launches_per_step = lib.regt_launch_count(1) // max(3, args.warmup)
+
+    graph = None
+    if not args.no_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            raw_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_d = raw_step()
+        torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            nonlocal loss_d
+            loss_d = raw_step()
+        if dist is not None:
+            dist.all_reduce(flat)  # shared-weight gradients, NCCL over NVLink
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value") ----------------
+    K = args.steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    for a, b in evs:
+        flush.zero_()                      # evict L2 between timed iterations (outside the event pair)
+        a.record(); step(); b.record()
+    barrier()
+    per = [a.elapsed_time(b) for a, b in evs]
+    tot_ms = torch.tensor([sum(per)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot_ms) / K
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------- end to end: host buffers in, loss out, every step ----------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        xd.copy_(xh, non_blocking=True)
+        yd.copy_(yh, non_blocking=True)
+        step()
+        loss_h.copy_(loss_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the loss every step (run.py:180)
+        _ = float(loss_h)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms)
+
+    # ---------------- per-kernel breakdown for the roofline (rank 0, eager, events per launch) -----
+    roofline, breakdown = None, None
+    if rank == 0:
+        st_ptr = torch.cuda.current_stream().cuda_stream
+        nprof = 5
+        agg = {}
+        for i in range(nprof):
+            flush.zero_()
+            torch.cuda.synchronize()
+            lib.regt_profile(1, st_ptr)
+            raw_step()
+            torch.cuda.synchronize()
+            for name, ms in _lib.profile_read():
+                agg.setdefault(name, []).append(ms)
+            lib.regt_profile(0, None)
+        # launches of one kernel name within a step are summed per step
+        per_kernel = {k: sum(v) / nprof for k, v in agg.items()}
+        counts = {k: len(v) // nprof for k, v in agg.items()}
+        step_sum = sum(per_kernel.values())
+        breakdown = {k: {"ms_per_step": round(v, 5), "launches": counts[k], "share": round(v / step_sum, 4)}
+                     for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+        pk = peaks()
+        ab = kernel_alg_bytes(w, B if not args.micro_batch else min(B, args.micro_batch))
+        dom = max((k for k in per_kernel if k in ab), key=lambda k: per_kernel[k], default=None)
+        if dom is not None:
+            t_launch = per_kernel[dom] / counts[dom] * 1e-3
+            ach = ab[dom] / t_launch / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                        "alg_bytes_per_launch": ab[dom], "launch_ms": t_launch * 1e3,
+                        "share_of_step": per_kernel[dom] / step_sum}
+        step_bytes = W.alg_bytes_per_step(w, B)
+        step_roof = {"alg_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "fwd_bwd_flops_per_step": 3 * W.fwd_flops_per_step(w, B)}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, n, el, thr = cpu_oracle_rate(w, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": f"{n} snapshots of the same workload in {el:.1f}s (oracle fp32 port, one snapshot at a time)"}
+
+    if rank == 0:
+        h2d = xh.numel() * 4 + yh.numel() * 4
+        out = {
+            "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor cores)", "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, l2="flushed between timed steps (256 MiB memset)",
+                           cuda_graph=graph is not None, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
+                           parallelism=f"batch-sharded x{world}, NCCL all-reduce of the flat gradient buffer" if world > 1 else "single GPU"),
+            "clocks": clocks,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches_per_step * K),
+            "launches_per_step": int(launches_per_step),
+            "roofline": roofline, "roofline_step": step_roof, "kernels": breakdown, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

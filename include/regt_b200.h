@@ -163,6 +163,15 @@ const char* regt_last_error(void);
  * call with reset != 0 (bench.py's "gpu_launches").                                     */
 int64_t regt_launch_count(int reset);
 
+/* per-kernel timing for bench.py's roofline: while enabled, every kernel launch of this
+ * library is followed by a cudaEventRecord on the launching stream.  regt_profile_begin()
+ * re-arms the interval origin; regt_profile_read() synchronises and returns, for each launch,
+ * the time since the previous mark ('\n'-separated names; ms[i]).  Not for use under graph
+ * capture.  No reference counterpart (the reference has no profiling).     */
+int regt_profile(int enable, regt_stream_t stream);
+int regt_profile_begin(regt_stream_t stream);
+int regt_profile_read(char* names, size_t names_len, float* ms, int max_n);
+
 #ifdef __cplusplus
 }
 #endif

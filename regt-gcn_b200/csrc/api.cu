@@ -48,7 +48,7 @@ Layout make_layout(const regt_args* a, void* base) {
   L.dprobs = c.take<float>(T);
   size_t pf = (size_t)3 * WGRAD_SPLITS * H * H;                    // H x H split-K partials
   pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * (F + 1));             // F-wide partials
-  pf = max(pf, (size_t)8 * R * H * F);                              // per-region partials
+  pf = max(pf, (size_t)64 * R * H * F);                             // per-region partials (<= 64 z-splits)
   pf = max(pf, (size_t)128 * T);                                    // attention partials
   pf = max(pf, (size_t)32 * (O * HEAD_HID + HEAD_HID * H));         // head split-K partials
   pf = max(pf, BN / 64 + 2);                                        // loss partials
@@ -85,6 +85,7 @@ extern "C" int regt_cell_forward(const regt_args* a) {
   REGT_CHECK(a->x && a->out_hidden, "regt_cell_forward: x / out_hidden is NULL");
   Layout L = make_layout(a, a->workspace);
   cudaStream_t st = (cudaStream_t)a->stream;
+  prof_mark("<begin>", st);
   if (a->precision == REGT_PREC_FP32) return cell_forward_fp32(a, L, st);
   return cell_forward_tc(a, L, st);
 }
@@ -93,6 +94,7 @@ extern "C" int regt_cell_backward(const regt_args* a) {
   if (validate(a, "regt_cell_backward")) return -1;
   Layout L = make_layout(a, a->workspace);
   cudaStream_t st = (cudaStream_t)a->stream;
+  prof_mark("<begin>", st);
   if (a->precision == REGT_PREC_FP32) return cell_backward_fp32(a, L, st);
   return cell_backward_tc(a, L, st);
 }
@@ -101,11 +103,13 @@ extern "C" int regt_head_forward(const regt_args* a) {
   if (validate(a, "regt_head_forward")) return -1;
   REGT_CHECK(a->out_hidden && a->out, "regt_head_forward: out_hidden / out is NULL");
   Layout L = make_layout(a, a->workspace);
+  prof_mark("<begin>", (cudaStream_t)a->stream);
   return head_forward_fp32(a, L, (cudaStream_t)a->stream);
 }
 
 extern "C" int regt_head_backward(const regt_args* a) {
   if (validate(a, "regt_head_backward")) return -1;
   Layout L = make_layout(a, a->workspace);
+  prof_mark("<begin>", (cudaStream_t)a->stream);
   return head_backward_fp32(a, L, (cudaStream_t)a->stream);
 }

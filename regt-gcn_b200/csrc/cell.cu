@@ -326,30 +326,33 @@ __global__ void k_skinny_reduce(const float* __restrict__ part, int splits, int 
   }
 }
 
-// dM1[r] = sum over the (node, region r) segments of D_3^T U ; part[bsplit][r][n][F]
+// dM1[r] = sum over the (node, region r) segments of D_3^T U ; part[zsplit][r][n][F]
+// work items of region r = (segment of r, snapshot b), split evenly over gridDim.z
 __global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ D, const float* __restrict__ U,
                                                   const int32_t* __restrict__ rseg_ptr,
                                                   const int32_t* __restrict__ rseg_list,
                                                   const int32_t* __restrict__ seg_node, int B, int N, int T, int H,
-                                                  int R, int nseg, int bchunk, float* __restrict__ part) {
+                                                  int R, int nseg, float* __restrict__ part) {
   const int r = blockIdx.x;
   const int n = blockIdx.y * 128 + threadIdx.x;
-  const int b0 = blockIdx.z * bchunk, b1 = min(B, b0 + bchunk);
   if (n >= H) return;
+  const int s0 = rseg_ptr[r];
+  const long long items = (long long)(rseg_ptr[r + 1] - s0) * B;
+  const long long per = (items + gridDim.z - 1) / gridDim.z;
+  const long long i0 = blockIdx.z * per, i1 = min(items, i0 + per);
   float acc[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) acc[f] = 0.f;
-  for (int si = rseg_ptr[r]; si < rseg_ptr[r + 1]; ++si) {
-    const int s = rseg_list[si];
+  for (long long i = i0; i < i1; ++i) {
+    const int s = rseg_list[s0 + (int)(i / B)];
+    const int b = (int)(i % B);
     const int node = seg_node[s];
-    for (int b = b0; b < b1; ++b) {
-      const float* ur = U + ((size_t)b * nseg + s) * F * T;
-      const float* dr = D + (((size_t)b * N + node) * T) * 4 * H + 3 * H + n;
-      for (int t = 0; t < T; ++t) {
-        const float d = __ldg(dr + (size_t)t * 4 * H);
+    const float* ur = U + ((size_t)b * nseg + s) * F * T;
+    const float* dr = D + (((size_t)b * N + node) * T) * 4 * H + 3 * H + n;
+    for (int t = 0; t < T; ++t) {
+      const float d = __ldg(dr + (size_t)t * 4 * H);
 #pragma unroll
-        for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(ur + f * T + t), acc[f]);
-      }
+      for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(ur + f * T + t), acc[f]);
     }
   }
   float* o = part + (((size_t)blockIdx.z * R + r) * H + n) * F;
@@ -425,7 +428,7 @@ int launch_wgrad_tn(const TNBatch& batch, long long rows, int splits, cudaStream
   chunk = (chunk + KT - 1) / KT * KT;
   dim3 grid(cdiv(maxN, TN), cdiv(maxM, TN), batch.nprob * splits);
   k_wgrad_tn<<<grid, 256, 0, st>>>(batch, rows, splits, chunk);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_wgrad_tn", st);
   return 0;
 }
 
@@ -440,7 +443,7 @@ __global__ void k_reduce_splits(const float* __restrict__ part, float* __restric
 int launch_reduce_splits(const float* part, float* out, long long count, int splits, int accumulate, cudaStream_t st) {
   if (!out || count == 0) return 0;
   k_reduce_splits<<<cdiv(count, 256), 256, 0, st>>>(part, out, count, splits, accumulate);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_reduce_splits", st);
   return 0;
 }
 
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(128) k_colsum(const float* __restrict__ A, int
 int launch_colsum(const float* A, int lda, int C, long long rows, int splits, float* part, cudaStream_t st) {
   long long chunk = (rows + splits - 1) / splits;
   k_colsum<<<dim3(cdiv(C, 128), splits), 128, 0, st>>>(A, lda, C, rows, chunk, part);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_colsum", st);
   return 0;
 }
 
@@ -486,7 +489,7 @@ static int run_fwd(const CellK& k, cudaStream_t st) {
   const size_t smem = ((size_t)2 * TM * (F + k.H + 1) + KT * TN) * sizeof(float);
   REGT_CUDA(cudaFuncSetAttribute(k_cell_fwd<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_cell_fwd<TM><<<cdiv(k.rows, TM), TM * 4, smem, st>>>(k);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_cell_fwd", st);
   return 0;
 }
 template <int TM>
@@ -494,7 +497,7 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
   const size_t smem = ((size_t)4 * TM * (k.H + 1) + 4 + KT * TN) * sizeof(float);
   REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_cell_bwd<TM><<<cdiv(k.rows, TM), TM * 4, smem, st>>>(k);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_cell_bwd", st);
   return 0;
 }
 
@@ -513,7 +516,7 @@ int cell_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   int rc = (smem64 <= 200 * 1024) ? run_fwd<64>(k, st) : run_fwd<32>(k, st);
   if (rc) return rc;
   k_attn_accum<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(L.Hn, L.probs, T, H, BN, a->out_hidden);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_attn_accum", st);
   return 0;
 }
 
@@ -528,7 +531,7 @@ int cell_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   // attention gradient
   const int nblk = 128;
   k_dprobs<<<nblk, 256, 0, st>>>(L.G, L.Hn, T, H, BN, part);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_dprobs", st);
   if (launch_reduce_splits(part, L.dprobs, T, nblk, 0, st)) return -1;
   // H x H weight gradients: dB_z = Dz^T h, dB_r = Dr^T h, dB_h = Dh^T (h*R)
   const int splits = (int)max(1ll, min((long long)WGRAD_SPLITS, rows / 256));
@@ -551,18 +554,15 @@ int cell_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int ncol = (a->mode == REGT_MODE_TGCN) ? 3 * H : 4 * H;
   long long chunk = (rows + splits - 1) / splits;
   k_wgrad_skinny<<<dim3(cdiv(ncol, 128), splits), 128, 0, st>>>(L.D, L.S, a->x, H, T, rows, ncol, chunk, part);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_wgrad_skinny", st);
   k_skinny_reduce<<<cdiv((long long)ncol * (F + 1), 256), 256, 0, st>>>(part, splits, H, ncol, L.dP, L.dcg, L.dM0, L.dc0);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_skinny_reduce", st);
   if (a->mode != REGT_MODE_TGCN) {
-    const int bs = min(a->B, 8);
-    const int bchunk = (a->B + bs - 1) / bs;
-    const int bsplits = (a->B + bchunk - 1) / bchunk;
-    k_wgrad_m1<<<dim3(R, cdiv(H, 128), bsplits), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
-                                                             a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg,
-                                                             bchunk, part);
-    REGT_LAUNCH_CHECK();
-    if (launch_reduce_splits(part, L.dM1, (long long)R * H * F, bsplits, 0, st)) return -1;
+    const int zs = (int)max(1ll, min(64ll, 1024ll / ((long long)R * cdiv(H, 128))));
+    k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
+                                                        a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
+    REGT_LAUNCHED("k_wgrad_m1", st);
+    if (launch_reduce_splits(part, L.dM1, (long long)R * H * F, zs, 0, st)) return -1;
   }
   return launch_chain(a, L, st);
 }

@@ -10,6 +10,7 @@ namespace regt {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void prof_mark(const char* name, cudaStream_t st);
 
 #define REGT_CHECK(cond, ...)         \
   do {                                \
@@ -36,6 +37,14 @@ void count_launch(int n = 1);
       regt::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return -3;                                                                         \
     }                                                                                    \
+  } while (0)
+
+// like REGT_LAUNCH_CHECK, and (when regt_profile(1) is active) records a CUDA event on the
+// launching stream so that consecutive marks bracket every kernel of the step
+#define REGT_LAUNCHED(name, st)       \
+  do {                                \
+    REGT_LAUNCH_CHECK();              \
+    regt::prof_mark(name, st);        \
   } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -171,13 +171,13 @@ int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   float* W2t = W1t + (size_t)H * HEAD_HID;
   k_head_transpose<<<cdiv((long long)H * HEAD_HID + HEAD_HID * O, 256), 256, 0, st>>>(a->p.head_w1, a->p.head_w2, H, O,
                                                                                   W1t, W2t);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_head_transpose", st);
   HeadK k = make_headk(a, L, W1t, W2t);
   const int nblk = cdiv(k.BN, TMH);
   const size_t smem = ((size_t)TMH * (H + 1) + TMH * (HEAD_HID + 1) + KT * TN) * sizeof(float);
   REGT_CUDA(cudaFuncSetAttribute(k_head_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_head_fwd<<<nblk, TMH * 4, smem, st>>>(k);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_head_fwd", st);
   if (a->y) {
     REGT_CHECK(a->loss && a->d_out, "head_forward: y given but loss/d_out is NULL");
     if (launch_reduce_splits(L.part, a->loss, 1, nblk, 0, st)) return -1;
@@ -190,7 +190,7 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const long long BN = (long long)a->B * a->N;
   if (!a->d_out) {  // only out_hidden carries gradient
     k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H);
-    REGT_LAUNCH_CHECK();
+    REGT_LAUNCHED("k_copy_or_zero", st);
     return 0;
   }
   HeadK k = make_headk(a, L, nullptr, nullptr);
@@ -198,7 +198,7 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const size_t smem = ((size_t)TMH * (O + 1) + TMH * (HEAD_HID + 1) + KT * TN + 4) * sizeof(float);
   REGT_CUDA(cudaFuncSetAttribute(k_head_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_head_bwd<<<nblk, TMH * 4, smem, st>>>(k);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_head_bwd", st);
   // weight gradients: dW2 = d_out^T a1, dW1 = d_a1^T relu(hid); biases = column sums
   const int splits = (int)max(1ll, min(32ll, BN / 128));
   float* part = L.part;

@@ -63,7 +63,7 @@ int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val
   long long warps = (long long)B * n_out;
   k_spmm_rows<4><<<cdiv(warps * 32, 256), 256, 0, st>>>(rowptr, col, val, (const float4*)x, (float4*)y, B, n_out, n_in,
                                                        width / 4);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_spmm_rows", st);
   return 0;
 }
 

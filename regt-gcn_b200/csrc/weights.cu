@@ -123,12 +123,12 @@ int launch_prep(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, R = a->plan.R;
   if (a->mode == REGT_MODE_REGIONAL) {
     k_lsum<<<cdiv((long long)H * H, 256), 256, 0, st>>>(a->p.comb_w, H, R, L.Lsum);
-    REGT_LAUNCH_CHECK();
+    REGT_LAUNCHED("k_lsum", st);
   }
   long long n = (long long)3 * (F + H) * H + 3 * H + (long long)F * H + (long long)R * F * H + H + 1;
   k_prep<<<cdiv(n, 256), 256, 0, st>>>(a->p, H, R, a->T, a->mode, L.Lsum, L.Wzr, L.Wc, L.czr, L.cc, L.M0t, L.M1t, L.c0,
                                       L.probs);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_prep", st);
   return 0;
 }
 
@@ -255,7 +255,7 @@ int launch_chain(const regt_args* a, const Layout& L, cudaStream_t st) {
                 (long long)H * R * H;
   k_chain<<<cdiv(n, 256), 256, 0, st>>>(a->p, a->g, H, R, a->T, a->mode, a->accumulate, L.Lsum, L.probs, L.dB, L.dP,
                                        L.dcg, L.dM0, L.dM1, L.dc0, L.dprobs);
-  REGT_LAUNCH_CHECK();
+  REGT_LAUNCHED("k_chain", st);
   return 0;
 }
 

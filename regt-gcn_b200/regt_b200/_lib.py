@@ -48,7 +48,8 @@ PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
 
 EXPORTS = ["regt_version", "regt_last_error", "regt_launch_count", "regt_plan_workspace_bytes",
            "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_workspace_bytes",
-           "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward"]
+           "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward",
+           "regt_profile", "regt_profile_begin", "regt_profile_read"]
 
 _lib = None
 
@@ -89,8 +90,25 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(Args)]
+    lib.regt_profile.restype = C.c_int
+    lib.regt_profile.argtypes = [C.c_int, vp]
+    lib.regt_profile_begin.restype = C.c_int
+    lib.regt_profile_begin.argtypes = [vp]
+    lib.regt_profile_read.restype = C.c_int
+    lib.regt_profile_read.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
     _lib = lib
     return lib
+
+
+def profile_read(max_n: int = 4096):
+    """-> list of (kernel name, ms) recorded since regt_profile(1, stream)."""
+    lib = load()
+    names = C.create_string_buffer(max_n * 24)
+    ms = (C.c_float * max_n)()
+    n = lib.regt_profile_read(names, len(names), ms, max_n)
+    if n < 0:
+        raise RuntimeError("regt_profile_read failed")
+    return list(zip(names.value.decode().split("\n")[:n], [ms[i] for i in range(n)]))
 
 
 def check(rc: int, what: str) -> None:
