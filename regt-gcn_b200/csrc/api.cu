@@ -29,16 +29,30 @@ Layout make_layout(const regt_args* a, void* base) {
   L.probs = c.take<float>(T);
   L.S = c.take<float>(BN * F * T);
   L.U = c.take<float>((size_t)a->B * (nseg ? nseg : 1) * F * T);
-  L.h = c.take<float>(rows * H);
-  L.Z = c.take<float>(rows * H);
-  L.Rg = c.take<float>(rows * H);
-  L.Hc = c.take<float>(rows * H);
-  L.hR = c.take<float>(rows * H);
-  L.Hn = c.take<float>(rows * H);
+  const bool tcp = a->precision != REGT_PREC_FP32;
+  if (!tcp) {
+    L.h = c.take<float>(rows * H);
+    L.Z = c.take<float>(rows * H);
+    L.Rg = c.take<float>(rows * H);
+    L.Hc = c.take<float>(rows * H);
+    L.hR = c.take<float>(rows * H);
+    L.Hn = c.take<float>(rows * H);
+    L.D = c.take<float>(rows * 4 * H);
+  } else {
+    const size_t nqt = (BN + 127) / 128, plane = T * nqt * 128 * H;
+    L.tc_img_f = c.take<unsigned char>(TC_IMG_BYTES);
+    L.tc_img_b = c.take<unsigned char>(TC_IMG_BYTES);
+    L.Zp = c.take<float>(plane);
+    L.Rp = c.take<float>(plane);
+    L.Hcp = c.take<float>(plane);
+    L.dhp_p = c.take<float>(a->mode == REGT_MODE_REGIONAL ? plane : 4);
+    L.hid_part = c.take<float>(T * BN * H);
+    L.tc_wpart = c.take<float>((size_t)TC_MAX_CTAS * 128 * 192);
+    L.tc_dpp = c.take<float>(T * nqt + 64);
+  }
   L.a1 = c.take<float>(BN * HEAD_HID);
   L.G = c.take<float>(BN * H);
   L.d_a1 = c.take<float>(BN * HEAD_HID);
-  L.D = c.take<float>(rows * 4 * H);
   L.dB = c.take<float>(3 * H * H);
   L.dP = c.take<float>(3 * H * F);
   L.dcg = c.take<float>(3 * H);

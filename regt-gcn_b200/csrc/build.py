@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 OUT = os.path.join(HERE, "..", "lib")
-SOURCES = ["api_core.cu", "plan.cu", "spmm.cu", "weights.cu", "cell.cu", "head.cu", "api.cu", "cell_tc.cu"]
+SOURCES = ["api_core.cu", "plan.cu", "spmm.cu", "weights.cu", "cell.cu", "head.cu", "api.cu", "cell_tc.cu", "umma_selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
 
@@ -39,7 +39,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
         if verbose:
             print(out)
-    subprocess.check_call([nvcc, "-shared", "-o", target, *objs, "-lcudart", "-lcuda"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs, "-lcudart", "-lcuda"])
     return target
 
 

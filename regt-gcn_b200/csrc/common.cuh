@@ -104,8 +104,17 @@ struct Layout {
   float* dprobs; // [T]
   float* part;   // split-K partials
   size_t part_floats;
+  // tensor-core path (precision != FP32): weight images, tile-layout planes, per-CTA partials
+  unsigned char* tc_img_f;   // forward weight image
+  unsigned char* tc_img_b;   // backward weight image
+  float *Zp, *Rp, *Hcp, *dhp_p;  // [T][nqt][H/4][128][4]
+  float* hid_part;           // [T (max t-chunks)][BN][H]
+  float* tc_wpart;           // [TC_MAX_CTAS][TC_WPART_FLOATS]
+  float* tc_dpp;             // [T * nqt] attention-gradient partials
   size_t total;
 };
+constexpr int TC_MAX_CTAS = 160;
+constexpr int TC_IMG_BYTES = 160 * 1024;
 
 Layout make_layout(const regt_args* a, void* base);
 

@@ -96,6 +96,8 @@ def load() -> C.CDLL:
     lib.regt_profile_begin.argtypes = [vp]
     lib.regt_profile_read.restype = C.c_int
     lib.regt_profile_read.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
+    lib.regt_debug_umma_selftest.restype = C.c_int
+    lib.regt_debug_umma_selftest.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = lib
     return lib
 

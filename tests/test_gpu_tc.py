@@ -1,0 +1,33 @@
+"""Tensor-core (tcgen05) precision modes of the cell against the fp64 oracle.
+tf32x3: fp32-equivalent accuracy (1e-5 normwise); bf16: stated tolerance 2e-2 activations / loss,
+5e-2 gradients (bf16 operands have an 8-bit mantissa; accumulation is fp32)."""
+import pytest
+import torch
+
+from parity_util import W, build_cuda, is_dead, oracle_step, relerr, to_dev
+
+pytestmark = pytest.mark.gpu
+TOL = {"tf32x3": (1e-5, 1e-5), "bf16": (2e-2, 5e-2)}
+
+
+def _cases():
+    return [
+        (W.tiny_workload("TemporalGCN", N=150, T=12, H=64, O=12, R=0, B=1, seed=24, k_intra=5), 1),
+        (W.tiny_workload("TemporalGCN", N=19, T=3, H=64, O=2, R=0, B=2, seed=21, adversarial=True), 2),
+        (W.tiny_workload("RegionalTemporalGCN", N=70, T=5, H=64, O=1, R=5, B=3, seed=23, k_intra=4), 3),
+        (W.tiny_workload("RegionalTemporalGCN", N=23, T=4, H=64, O=3, R=3, B=2, seed=22, adversarial=True), 2),
+        (W.make_workload(2), 3),
+    ]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("w,B", _cases(), ids=lambda v: v.name if hasattr(v, "name") else str(v))
+def test_tc_forward_matches_oracle(w, B, precision):
+    ref = oracle_step(w, B)
+    m = build_cuda(w, ref["state"], precision=precision)
+    x, _ = w.inputs(B)
+    with torch.no_grad():
+        out, hid = m(x.cuda(), *to_dev(w.graph_args(), "cuda"))
+    tol = TOL[precision][0]
+    assert relerr(hid, ref["hid"]) <= tol, f"out_hidden {relerr(hid, ref['hid']):.3e}"
+    assert relerr(out, ref["out"]) <= tol, f"out {relerr(out, ref['out']):.3e}"
