@@ -250,11 +250,60 @@ __device__ __forceinline__ void compute_h32(const TcArgs& a, const float* consts
   }
 }
 
-// saved-plane tile layout [T][nqt][HH/4][128][4]: thread r stores its 32 columns as 8 float4
-template <int HH>
-__device__ __forceinline__ float* plane_ptr(float* plane, int nqt, int t, int qt, int c4, int r) {
-  return plane + ((((size_t)t * nqt + qt) * (HH / 4) + c4) * TC_ROWS + r) * 4;
-}
+// Saved-plane tile layout: one (t, q-tile) tile is contiguous so the backward can bulk-copy it.
+//   tf32x3 mode: fp32  [T][nqt][HH/4][128][4]      bf16 mode: bf16  [T][nqt][HH/8][128][8]
+// Thread r writes 16-byte pieces; a warp instruction covers 512 contiguous bytes.
+template <int FMT, int HH>
+struct PlaneIO {
+  static constexpr bool BF = (FMT == FMT_BF16);
+  static constexpr int TILE_BYTES = TC_ROWS * HH * (BF ? 2 : 4);
+  __device__ static __forceinline__ uint8_t* tile(void* plane, int nqt, int t, int qt) {
+    return reinterpret_cast<uint8_t*>(plane) + ((size_t)t * nqt + qt) * TILE_BYTES;
+  }
+  // 16-byte piece index of column c for row r inside a tile
+  __device__ static __forceinline__ uint32_t piece_off(int r, int c) {
+    return (uint32_t)(((c / (BF ? 8 : 4)) * TC_ROWS + r) * 16);
+  }
+  __device__ static __forceinline__ void store32(void* plane, int nqt, int t, int qt, int r, int c0, const float (&v)[32]) {
+    uint8_t* tb = tile(plane, nqt, t, qt);
+    if constexpr (BF) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 p;
+        p.x = pack_bf16(v[j], v[j + 1]);
+        p.y = pack_bf16(v[j + 2], v[j + 3]);
+        p.z = pack_bf16(v[j + 4], v[j + 5]);
+        p.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(tb + piece_off(r, c0 + j)) = p;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(tb + piece_off(r, c0 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  // read 32 columns of row r from a tile image (global or shared)
+  __device__ static __forceinline__ void load32(const uint8_t* tb, int r, int c0, float (&v)[32]) {
+    if constexpr (BF) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 p = *reinterpret_cast<const uint4*>(tb + piece_off(r, c0 + j));
+        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[j + 2 * e] = __uint_as_float(w[e] << 16);
+          v[j + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 p = *reinterpret_cast<const float4*>(tb + piece_off(r, c0 + j));
+        v[j] = p.x; v[j + 1] = p.y; v[j + 2] = p.z; v[j + 3] = p.w;
+      }
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // forward
@@ -330,10 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
           tmem_ld32(tlane + c0, raw);
 #pragma unroll
           for (int j = 0; j < 32; ++j) z[j] = fast_sigmoid(raw[j] + consts[Cfg::C_CZR + c0 + j]);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(plane_ptr<HH>(a.Zp, a.nqt, t, qt, (c0 + j) / 4, r)) =
-                make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+          PlaneIO<FMT, HH>::store32(a.Zp, a.nqt, t, qt, r, c0, z);
           tmem_ld32(tlane + HH + c0, raw);
           float hr[32];
 #pragma unroll
@@ -342,10 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
             raw[j] = rg;
             hr[j] = h[j] * rg;
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(plane_ptr<HH>(a.Rp, a.nqt, t, qt, (c0 + j) / 4, r)) =
-                make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+          PlaneIO<FMT, HH>::store32(a.Rp, a.nqt, t, qt, r, c0, raw);
           store_operand32<FMT, HH>(Ah, r, c0, hr);
         }
         fence_proxy_async();
@@ -365,10 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
             raw[j] = hc;
             acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(plane_ptr<HH>(a.Hcp, a.nqt, t, qt, (c0 + j) / 4, r)) =
-                make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+          PlaneIO<FMT, HH>::store32(a.Hcp, a.nqt, t, qt, r, c0, raw);
         }
         ph ^= 1;
       }
@@ -507,9 +547,383 @@ int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   return run_fwd_tc<FMT_BF16, 64>(a, L, st);
 }
 
-int cell_backward_tc(const regt_args*, const Layout&, cudaStream_t) {
-  set_error("tensor-core backward is not built yet; use precision fp32 for training");
-  return -10;
+// ------------------------------------------------------------------------------------------
+// backward (bf16 operands): data gradients and ALL weight gradients on the tensor cores
+// ------------------------------------------------------------------------------------------
+// Per period and 128-row tile (same work items / thread ownership as the forward):
+//   E0  recompute h; read saved Z,R,H~ (bulk-prefetched tile); dH' = probs[t] G;
+//       Dh = dH~ (1-H~^2), Dz = dZ Z(1-Z); operand tiles Dh, Dz, h, h*R -> smem
+//   M1  dHR = Dh . B_h                                  (TMEM cols   0.. 63)
+//   E1  dh += dHR R ; Dr = dHR h R(1-R) -> smem
+//   M2  dhg = Dz . B_z + Dr . B_r                       (TMEM cols  64..127)
+//   W1  [Dz|Dr]^T . h        -> dB_z, dB_r              (TMEM cols 128..191, persistent)
+//   W1s [Dz|Dr]^T . [S|X|U|1] -> dP_z, dP_r, dc_z, dc_r (TMEM cols 192..223, persistent)
+//   E2  d h_pre = act'(h) (dh + dhg) -> smem
+//   W2  [Dh|dhp]^T . (h*R)   -> dB_h                    (TMEM cols 224..287, persistent)
+//   W2s [Dh|dhp]^T . [S|X|U|1] -> dP_h, dc_h, dM0, dM1, dc0 (TMEM cols 288..319, persistent)
+// The weight-gradient MMAs read the SAME shared-memory tiles as MN-major operands (contraction over
+// the 128 rows); their accumulators live in TMEM for the whole kernel and are flushed once per CTA.
+constexpr int WP_COLS = 192;  // per-CTA partial: [128][192] = accW1 | accW1s | accW2 | accW2s
+
+template <int HH>
+__global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
+  constexpr int FMT = FMT_BF16;
+  using Cfg = TcCfg<FMT, HH>;
+  using PIO = PlaneIO<FMT, HH>;
+  constexpr int TILE = Cfg::A_TILE;          // 16 KB
+  constexpr int PT = PIO::TILE_BYTES;        // 16 KB
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* W = smem;                                     // Bt_z | Bt_r | Bt_h | consts
+  uint8_t* T_DH = W + ((Cfg::BWD_IMG + 1023) & ~1023);
+  uint8_t* T_DHP = T_DH + TILE;
+  uint8_t* T_DZ = T_DHP + TILE;
+  uint8_t* T_DR = T_DZ + TILE;
+  uint8_t* T_H = T_DR + TILE;
+  uint8_t* T_HR = T_H + TILE;
+  uint8_t* SM = T_HR + TILE;                             // chunk tile: S | X | U | ones  (4 chunks)
+  uint8_t* STG = SM + 4 * TC_ROWS * 16;                  // staged Z | R | H~ tiles
+  __shared__ uint64_t bar_stage, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[2][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < Cfg::BWD_IMG / 16; i += NTHREADS)
+    reinterpret_cast<uint4*>(W)[i] = __ldg(reinterpret_cast<const uint4*>(a.img) + i);
+  if (tid == 0) {
+    mbar_init(&bar_stage, 1);
+    mbar_init(&bar_e0, NEPI);
+    mbar_init(&bar_m1, 1);
+    mbar_init(&bar_e1, NEPI);
+    mbar_init(&bar_m2, 1);
+    mbar_init(&bar_e2, NEPI);
+    mbar_init(&bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const float* consts = reinterpret_cast<const float*>(W + Cfg::BWD_W);
+  uint32_t ph = 0;
+  int gstep = 0;
+
+  if (warp < 8) {
+    const int r = (warp & 3) * 32 + lane;
+    const int ch = warp >> 2;
+    const int c0 = ch * 32;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+      const int qt = item / a.ntc, tc_i = item % a.ntc;
+      const long long q = (long long)qt * TC_ROWS + r;
+      const bool valid = q < a.BN;
+      const int b = valid ? (int)(q / a.N) : 0, n = valid ? (int)(q % a.N) : 0;
+      int s0 = 0, s1 = 0;
+      if (valid) {
+        s0 = a.seg_ptr[n];
+        s1 = a.seg_ptr[n + 1];
+      }
+      for (int t = tc_i * a.tp; t < (tc_i + 1) * a.tp; ++t) {
+        float h[32], dh[32], rr[32], sv[8];
+        compute_h32<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
+        const float pt = consts[Cfg::C_PROBS + t];
+        float dp = 0.f;
+        mbar_wait(&bar_stage, ph);
+        {
+          float z[32], hc[32];
+          PIO::load32(STG, r, c0, z);
+          PIO::load32(STG + PT, r, c0, rr);
+          PIO::load32(STG + 2 * PT, r, c0, hc);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) g4 = __ldg(reinterpret_cast<const float4*>(a.G + q * HH + c0 + j));
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int jj = j + e;
+              const float zz = z[jj], hcc = hc[jj], hv = h[jj];
+              dp = fmaf(gv[e], zz * hv + (1.0f - zz) * hcc, dp);
+              const float gs = pt * gv[e];
+              dh[jj] = gs * zz;
+              z[jj] = gs * (hv - hcc) * zz * (1.0f - zz);          // Dz
+              hc[jj] = gs * (1.0f - zz) * (1.0f - hcc * hcc);      // Dh
+            }
+          }
+          if (gstep > 0) mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));  // previous step's MMAs released the tiles
+          store_operand32<FMT, HH>(T_DZ, r, c0, z);
+          store_operand32<FMT, HH>(T_DH, r, c0, hc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = h[j] * rr[j];
+          store_operand32<FMT, HH>(T_HR, r, c0, z);
+          store_operand32<FMT, HH>(T_H, r, c0, h);
+        }
+        if (ch == 0) {
+          float xv[8], uv[8];
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            xv[f] = valid ? __ldg(a.x + q * F * a.T + f * a.T + t) : 0.f;
+            uv[f] = (s1 > s0) ? __ldg(a.U + ((size_t)b * a.nseg + s0) * F * a.T + f * a.T + t) : 0.f;
+          }
+          store_small8<FMT, HH>(SM, 0, r, 0, sv);
+          store_small8<FMT, HH>(SM, 0, r, 8, xv);
+          store_small8<FMT, HH>(SM, 0, r, 16, uv);
+          *reinterpret_cast<uint4*>(SM + chunk_off(r, 3, TC_ROWS)) = make_uint4(0x00003F80u, 0, 0, 0);  // bf16 1.0
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bar_e0);
+
+        // ---- E1 ----
+        mbar_wait(&bar_m1, ph);
+        tc_fence_after();
+        {
+          float raw[32];
+          tmem_ld32(tlane + c0, raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dHR = raw[j];
+            dh[j] = fmaf(dHR, rr[j], dh[j]);
+            raw[j] = dHR * h[j] * rr[j] * (1.0f - rr[j]);   // Dr
+          }
+          store_operand32<FMT, HH>(T_DR, r, c0, raw);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bar_e1);
+
+        // ---- E2 ----
+        mbar_wait(&bar_m2, ph);
+        tc_fence_after();
+        {
+          float raw[32];
+          tmem_ld32(tlane + 64 + c0, raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = dh[j] + raw[j];
+            if (a.mode == REGT_MODE_REGIONAL) v *= (h[j] > 0.f ? 1.0f : 0.01f);
+            raw[j] = v;
+          }
+          store_operand32<FMT, HH>(T_DHP, r, c0, raw);
+          if (a.mode == REGT_MODE_REGIONAL) PlaneIO<FMT_TF32, HH>::store32(a.dhp, a.nqt, t, qt, r, c0, raw);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bar_e2);
+
+        // ---- attention gradient partial: fixed-order block reduction ----
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) dp += __shfl_down_sync(0xffffffffu, dp, d);
+        if (lane == 0) red[gstep & 1][warp] = dp;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) sacc += red[gstep & 1][w8];
+          a.dprobs_part[(size_t)qt * a.T + t] = sacc;
+        }
+        ph ^= 1;
+        ++gstep;
+      }
+    }
+    // ---- flush the persistent weight-gradient accumulators ----
+    mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));
+    tc_fence_after();
+    float* wp = a.wpart + ((size_t)blockIdx.x * TC_ROWS + r) * WP_COLS;
+    {
+      float v[32];
+      tmem_ld32(tlane + 128 + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      tmem_ld32(tlane + 224 + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wp + 96 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      float u[16];
+      tmem_ld16(tlane + 192 + ch * 16, u);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(wp + 64 + ch * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+      tmem_ld16(tlane + 288 + ch * 16, u);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(wp + 160 + ch * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+    }
+    tc_fence_before();
+  } else {
+    // ================= MMA issuer + plane prefetch (warp 8, one elected lane) =================
+    const uint32_t id_dg = make_idesc(FMT, 128, HH, 0, 0);        // data gradients (K-major)
+    const uint32_t id_w = make_idesc(FMT, 128, HH, 1, 1);         // weight gradients (MN-major)
+    const uint32_t id_ws = make_idesc(FMT, 128, 32, 1, 1);
+    const uint32_t w = smem_u32(W), tdh = smem_u32(T_DH), tdz = smem_u32(T_DZ), tdr = smem_u32(T_DR), th = smem_u32(T_H),
+                   thr = smem_u32(T_HR), sm = smem_u32(SM);
+    auto prefetch = [&](int item, int t) {
+      const int qt = item / a.ntc;
+      mbar_arrive_expect_tx(&bar_stage, 3 * PT);
+      bulk_g2s(STG, PIO::tile(a.Zp, a.nqt, t, qt), PT, &bar_stage);
+      bulk_g2s(STG + PT, PIO::tile(a.Rp, a.nqt, t, qt), PT, &bar_stage);
+      bulk_g2s(STG + 2 * PT, PIO::tile(a.Hcp, a.nqt, t, qt), PT, &bar_stage);
+    };
+    if (lane == 0 && blockIdx.x < a.items) prefetch(blockIdx.x, (blockIdx.x % a.ntc) * a.tp);
+    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
+      const int tc_i = item % a.ntc;
+      for (int ti = 0; ti < a.tp; ++ti) {
+        const uint32_t accw = gstep > 0 ? 1u : 0u;
+        mbar_wait(&bar_e0, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          // the staged planes of this step are consumed: fetch the next step's
+          int nitem = item, nt = tc_i * a.tp + ti + 1;
+          if (ti + 1 == a.tp) {
+            nitem = item + gridDim.x;
+            nt = (nitem % a.ntc) * a.tp;
+          }
+          if (nitem < a.items) prefetch(nitem, nt);
+          // M1: dHR = Dh . B_h
+#pragma unroll
+          for (int s = 0; s < HH / 16; ++s)
+            umma<FMT>(tmem, make_desc(tdh + s * 32, 16, 1024, LAYOUT_SW128),
+                      make_desc(w + 2 * Cfg::BT + s * 32, 16, 1024, LAYOUT_SW128), id_dg, s > 0 ? 1u : 0u);
+          umma_commit(&bar_m1);
+        }
+        __syncwarp();
+        mbar_wait(&bar_e1, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          // M2: dhg = Dz . B_z + Dr . B_r
+#pragma unroll
+          for (int s = 0; s < HH / 16; ++s)
+            umma<FMT>(tmem + 64, make_desc(tdz + s * 32, 16, 1024, LAYOUT_SW128),
+                      make_desc(w + s * 32, 16, 1024, LAYOUT_SW128), id_dg, s > 0 ? 1u : 0u);
+#pragma unroll
+          for (int s = 0; s < HH / 16; ++s)
+            umma<FMT>(tmem + 64, make_desc(tdr + s * 32, 16, 1024, LAYOUT_SW128),
+                      make_desc(w + Cfg::BT + s * 32, 16, 1024, LAYOUT_SW128), id_dg, 1u);
+          umma_commit(&bar_m2);
+          // W1 / W1s: [Dz|Dr]^T . h , [Dz|Dr]^T . [S|X|U|1]   (contraction over the 128 rows)
+#pragma unroll
+          for (int s = 0; s < TC_ROWS / 16; ++s) {
+            const uint64_t da = make_desc(tdz + s * 2048, TILE, 1024, LAYOUT_SW128);
+            umma<FMT>(tmem + 128, da, make_desc(th + s * 2048, TILE, 1024, LAYOUT_SW128), id_w, (s > 0) ? 1u : accw);
+            umma<FMT>(tmem + 192, da, make_desc(sm + s * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (s > 0) ? 1u : accw);
+          }
+        }
+        __syncwarp();
+        mbar_wait(&bar_e2, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          // W2 / W2s: [Dh|dhp]^T . (h*R) , [Dh|dhp]^T . [S|X|U|1]
+#pragma unroll
+          for (int s = 0; s < TC_ROWS / 16; ++s) {
+            const uint64_t da = make_desc(tdh + s * 2048, TILE, 1024, LAYOUT_SW128);
+            umma<FMT>(tmem + 224, da, make_desc(thr + s * 2048, TILE, 1024, LAYOUT_SW128), id_w, (s > 0) ? 1u : accw);
+            umma<FMT>(tmem + 288, da, make_desc(sm + s * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (s > 0) ? 1u : accw);
+          }
+          umma_commit(&bar_w);
+        }
+        __syncwarp();
+        ph ^= 1;
+        ++gstep;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// sum the per-CTA partials and scatter them into the collapsed-weight gradient buffers
+__global__ void k_tc_wreduce(const float* __restrict__ wpart, int ncta, int HH, int R, float* __restrict__ dB,
+                             float* __restrict__ dP, float* __restrict__ dcg, float* __restrict__ dM0,
+                             float* __restrict__ dM1, float* __restrict__ dc0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= TC_ROWS * WP_COLS) return;
+  const int m = i / WP_COLS, c = i % WP_COLS;
+  float s = 0.f;
+  for (int k = 0; k < ncta; ++k) s += wpart[(size_t)k * TC_ROWS * WP_COLS + i];
+  const int g = m / HH, n = m % HH;
+  if (c < 64) {
+    dB[((size_t)g * HH + n) * HH + c] = s;                     // dB_z / dB_r
+  } else if (c < 96) {
+    const int cc = c - 64;
+    if (cc < F) dP[((size_t)g * HH + n) * F + cc] = s;
+    else if (cc == 24) dcg[g * HH + n] = s;
+  } else if (c < 160) {
+    if (m < HH) dB[((size_t)2 * HH + m) * HH + (c - 96)] = s;  // dB_h
+  } else {
+    const int cc = c - 160;
+    if (m < HH) {
+      if (cc < F) dP[((size_t)2 * HH + m) * F + cc] = s;
+      else if (cc == 24) dcg[2 * HH + m] = s;
+    } else {
+      if (cc >= 8 && cc < 16) dM0[(size_t)n * F + cc - 8] = s;
+      else if (cc >= 16 && cc < 24) { if (R == 1) dM1[(size_t)n * F + cc - 16] = s; }
+      else if (cc == 24) dc0[n] = s;
+    }
+  }
+}
+
+// regional decomposition (R > 1): dM1[r] from the saved d h_pre plane, one CTA per (region, z-split)
+template <int HH>
+__global__ void __launch_bounds__(HH) k_wgrad_m1_tc(const float* __restrict__ dhp, const float* __restrict__ U,
+                                                    const int32_t* __restrict__ rseg_ptr,
+                                                    const int32_t* __restrict__ rseg_list,
+                                                    const int32_t* __restrict__ seg_node, int B, int N, int T, int R,
+                                                    int nseg, int nqt, float* __restrict__ part) {
+  const int r = blockIdx.x, n = threadIdx.x;
+  const int s0 = rseg_ptr[r];
+  const long long items = (long long)(rseg_ptr[r + 1] - s0) * B;
+  const long long per = (items + gridDim.z - 1) / gridDim.z;
+  const long long i0 = blockIdx.z * per, i1 = min(items, i0 + per);
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.f;
+  for (long long i = i0; i < i1; ++i) {
+    const int s = rseg_list[s0 + (int)(i / B)];
+    const int b = (int)(i % B);
+    const long long q = (long long)b * N + seg_node[s];
+    const int qt = (int)(q / TC_ROWS), row = (int)(q % TC_ROWS);
+    const float* ur = U + ((size_t)b * nseg + s) * F * T;
+    for (int t = 0; t < T; ++t) {
+      const float d = __ldg(dhp + ((((size_t)t * nqt + qt) * (HH / 4) + n / 4) * TC_ROWS + row) * 4 + (n & 3));
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(ur + f * T + t), acc[f]);
+    }
+  }
+  float* o = part + (((size_t)blockIdx.z * R + r) * HH + n) * F;
+#pragma unroll
+  for (int f = 0; f < F; ++f) o[f] = acc[f];
+}
+
+int launch_chain(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_reduce_splits(const float* part, float* out, long long count, int splits, int accumulate, cudaStream_t st);
+
+int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
+  REGT_CHECK(a->precision == REGT_PREC_BF16,
+             "the tensor-core backward is built for precision bf16 only (tf32x3 is forward-only); use fp32 or bf16 to train");
+  REGT_CHECK(a->H == 64 && a->mode != REGT_MODE_TGCN, "tensor-core backward: hidden=64, TemporalGCN / RegionalTemporalGCN only");
+  constexpr int HH = 64;
+  using Cfg = TcCfg<FMT_BF16, HH>;
+  const int slots = num_sms();
+  TcArgs k = make_tcargs(a, L, slots);
+  k.img = L.tc_img_b;
+  const int grid = min(min(slots, k.items), TC_MAX_CTAS);
+  const size_t smem = 1024 + ((Cfg::BWD_IMG + 1023) & ~1023) + 6 * Cfg::A_TILE + 4 * TC_ROWS * 16 +
+                      3 * PlaneIO<FMT_BF16, HH>::TILE_BYTES;
+  REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd_tc<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cell_bwd_tc<HH><<<grid, NTHREADS, smem, st>>>(k);
+  REGT_LAUNCHED("k_cell_bwd_tc", st);
+  const int R = a->plan.R;
+  k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS, 256), 256, 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1, L.dc0);
+  REGT_LAUNCHED("k_tc_wreduce", st);
+  if (launch_reduce_splits(L.tc_dpp, L.dprobs, a->T, k.nqt, 0, st)) return -1;
+  if (a->mode == REGT_MODE_REGIONAL && R > 1) {
+    const int zs = (int)max(1ll, min(64ll, 1024ll / R));
+    k_wgrad_m1_tc<HH><<<dim3(R, 1, zs), HH, 0, st>>>(L.dhp_p, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
+                                                    a->B, a->N, a->T, R, a->plan.nseg, k.nqt, L.part);
+    REGT_LAUNCHED("k_wgrad_m1_tc", st);
+    if (launch_reduce_splits(L.part, L.dM1, (long long)R * HH * F, zs, 0, st)) return -1;
+  }
+  return launch_chain(a, L, st);
 }
 
 }  // namespace regt

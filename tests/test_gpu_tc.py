@@ -31,3 +31,33 @@ def test_tc_forward_matches_oracle(w, B, precision):
     tol = TOL[precision][0]
     assert relerr(hid, ref["hid"]) <= tol, f"out_hidden {relerr(hid, ref['hid']):.3e}"
     assert relerr(out, ref["out"]) <= tol, f"out {relerr(out, ref['out']):.3e}"
+
+
+@pytest.mark.parametrize("w,B", _cases(), ids=lambda v: v.name if hasattr(v, "name") else str(v))
+def test_bf16_fused_step_matches_oracle(w, B):
+    """forward + loss + backward with the tcgen05 bf16 kernels (all weight gradients on tensor cores)."""
+    ref = oracle_step(w, B)
+    m = build_cuda(w, ref["state"], precision="bf16")
+    x, y = w.inputs(B)
+    loss, out, hid = m.fused_step(x.cuda(), y.cuda(), *to_dev(w.graph_args(), "cuda"))
+    atol, gtol = TOL["bf16"]
+    assert relerr(hid, ref["hid"]) <= atol and relerr(out, ref["out"]) <= atol
+    assert abs(float(loss) - ref["loss"]) <= atol * abs(ref["loss"])
+    worst = {}
+    for k, g in ref["grads"].items():
+        if is_dead(w.model, k):
+            continue
+        worst[k] = relerr(m.get_parameter(k).grad, g)
+    # the attention gradient is a difference of nearly equal dot products <G, H'_t>: cancellation
+    # amplifies the bf16 rounding of the saved planes, so it gets a looser (stated) bound
+    bad = {k: v for k, v in worst.items() if v > (0.15 if k.endswith("_attention") else gtol)}
+    assert not bad, f"gradient errors above {gtol}: {bad}"
+
+
+def test_tf32x3_backward_is_rejected_loudly():
+    w = _cases()[0][0]
+    ref = oracle_step(w, 1)
+    m = build_cuda(w, ref["state"], precision="tf32x3")
+    x, y = w.inputs(1)
+    with pytest.raises(RuntimeError, match="bf16 only"):
+        m.fused_step(x.cuda(), y.cuda(), *to_dev(w.graph_args(), "cuda"))
