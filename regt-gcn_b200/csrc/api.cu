@@ -46,6 +46,7 @@ Layout make_layout(const regt_args* a, void* base) {
     L.Rp = c.take<float>(plane);
     L.Hcp = c.take<float>(plane);
     L.dhp_p = c.take<float>(a->mode == REGT_MODE_REGIONAL ? plane : 4);
+    L.Xt = c.take<float>(BN * F * T);
     L.hid_part = c.take<float>(T * BN * H);
     L.tc_wpart = c.take<float>((size_t)TC_MAX_CTAS * 128 * 192);
     L.tc_dpp = c.take<float>(T * nqt + 64);

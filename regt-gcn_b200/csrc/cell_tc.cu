@@ -12,12 +12,16 @@
 // Precision: REGT_PREC_BF16 = bf16 operands, fp32 accumulate; REGT_PREC_TF32X3 = three tf32 products
 // (hi*hi + lo*hi + hi*lo) per contraction, fp32-equivalent accuracy.
 // Reference arithmetic replaced: models/utils.py:168-188 + models/RegionalTemporalGCN.py:134-148.
+#include <stdlib.h>
+
 #include "cell_tc.cuh"
 
 namespace regt {
 using namespace tc;
 constexpr int F = REGT_F;
-constexpr int NEPI = 256;       // epilogue threads (8 warps); warp 8 issues the MMAs
+constexpr int CW = 32;                    // columns owned by one epilogue thread
+constexpr int NEPI_WARPS = 4 * (64 / CW);  // 4 lane quarters x column groups (hidden = 64)
+constexpr int NEPI = NEPI_WARPS * 32;      // epilogue threads; the next warp issues the MMAs
 constexpr int NTHREADS = NEPI + 32;
 
 __device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
@@ -99,20 +103,28 @@ __global__ void k_pack_tc(const float* __restrict__ Wzr, const float* __restrict
     const int g = j / (HH * HH), rem = j % (HH * HH);
     const int k = rem / HH, n = rem % HH;
     const float* lw = g == 0 ? lw0 : (g == 1 ? lw1 : lw2);
-    put_w<FMT, HH>(img_b + g * Cfg::BT, 3 * Cfg::BT, false, HH, k, n, lw[(size_t)n * 2 * HH + HH + k]);
+    put_w<FMT, HH>(img_b + g * Cfg::BT, Cfg::BWD_SPLIT, false, HH, k, n, lw[(size_t)n * 2 * HH + HH + k]);
+    return;
+  }
+  j -= 3 * HH * HH;
+  if (j < HH * 16) {  // B0[n][k]: k < 8 -> M0[n][k], k >= 8 -> M1[0][n][k-8]   (forward and backward images)
+    const int n = j / 16, k = j % 16;
+    const float v = k < F ? (M0t ? M0t[k * HH + n] : 0.f) : (M1t ? M1t[(k - F) * HH + n] : 0.f);
+    put_w<FMT, HH>(img_f + Cfg::OFF_W0, Cfg::FWD_SPLIT, true, HH, n, k, v);
+    put_w<FMT, HH>(img_b + 3 * Cfg::BT, Cfg::BWD_SPLIT, true, HH, n, k, v);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // shared device helpers
 // ------------------------------------------------------------------------------------------
-// write 32 consecutive columns [c0, c0+32) of row r into the [128 x HH] SW128 operand tile(s)
+// write CW consecutive columns [c0, c0+CW) of row r into the [128 x HH] SW128 operand tile(s)
 template <int FMT, int HH>
-__device__ __forceinline__ void store_operand32(uint8_t* tile, int r, int c0, const float (&v)[32]) {
+__device__ __forceinline__ void store_operand(uint8_t* tile, int r, int c0, const float (&v)[CW]) {
   using Cfg = TcCfg<FMT, HH>;
   if constexpr (FMT == FMT_TF32) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < CW; j += 4) {
       float hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -125,7 +137,7 @@ __device__ __forceinline__ void store_operand32(uint8_t* tile, int r, int c0, co
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < CW; j += 8) {
       uint4 p;
       p.x = pack_bf16(v[j], v[j + 1]);
       p.y = pack_bf16(v[j + 2], v[j + 3]);
@@ -171,7 +183,7 @@ __device__ __forceinline__ void issue_gate_mma(uint32_t tmem_d, uint32_t a_h, ui
 #pragma unroll
   for (int p = 0; p < NPROD; ++p) {
     const int pa = (p == 1) ? 1 : 0, pb = (p == 2) ? 1 : 0;  // hi*hi, lo*hi, hi*lo
-    const uint32_t ah = a_h + pa * Cfg::A_TILE, as = a_s + pa * Cfg::AS_TILE;
+    const uint32_t ah = a_h + pa * Cfg::A_TILE, as = a_s + pa * Cfg::SMF_TILE;
     const uint32_t wh = w_h + pb * Cfg::FWD_SPLIT, ws = w_s + pb * Cfg::FWD_SPLIT;
 #pragma unroll
     for (int s = 0; s < HH / Cfg::UK; ++s) {
@@ -187,23 +199,28 @@ __device__ __forceinline__ void issue_gate_mma(uint32_t tmem_d, uint32_t a_h, ui
   }
 }
 
-// h[32] for columns [c0, c0+32) of row q at period t (regional combine on F-wide features)
+// h[CW] for columns [c0, c0+CW) of row q at period t (regional combine on F-wide features)
 template <int HH>
-__device__ __forceinline__ void compute_h32(const TcArgs& a, const float* consts_s, bool valid, long long q, int b, int s0,
-                                            int s1, int t, int c0, float (&h)[32], float (&sv)[8]) {
+__device__ __forceinline__ void compute_h(const TcArgs& a, const float* consts_s, bool valid, long long q, int b, int s0,
+                                          int s1, int t, int c0, float (&h)[CW], float (&sv)[8]) {
   using C = TcCfg<FMT_BF16, HH>;  // constant offsets do not depend on FMT
   float xv[8];
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    xv[f] = valid ? __ldg(a.x + q * F * a.T + f * a.T + t) : 0.f;
-    sv[f] = valid ? __ldg(a.S + q * F * a.T + f * a.T + t) : 0.f;
+  {
+    const size_t ro = ((size_t)t * a.BN + (valid ? q : 0)) * F;
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(a.Xt + ro)), x1 = __ldg(reinterpret_cast<const float4*>(a.Xt + ro) + 1);
+    const float4 s0v = __ldg(reinterpret_cast<const float4*>(a.St + ro)), s1v = __ldg(reinterpret_cast<const float4*>(a.St + ro) + 1);
+    const float m = valid ? 1.f : 0.f;
+    xv[0] = m * x0.x; xv[1] = m * x0.y; xv[2] = m * x0.z; xv[3] = m * x0.w;
+    xv[4] = m * x1.x; xv[5] = m * x1.y; xv[6] = m * x1.z; xv[7] = m * x1.w;
+    sv[0] = m * s0v.x; sv[1] = m * s0v.y; sv[2] = m * s0v.z; sv[3] = m * s0v.w;
+    sv[4] = m * s1v.x; sv[5] = m * s1v.y; sv[6] = m * s1v.z; sv[7] = m * s1v.w;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) h[j] = consts_s[C::C_C0 + c0 + j];
+  for (int j = 0; j < CW; ++j) h[j] = consts_s[C::C_C0 + c0 + j];
 #pragma unroll
   for (int f = 0; f < F; ++f) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < CW; j += 4) {
       const float4 w = *reinterpret_cast<const float4*>(consts_s + C::C_M0 + f * HH + c0 + j);
       h[j] = fmaf(xv[f], w.x, h[j]);
       h[j + 1] = fmaf(xv[f], w.y, h[j + 1]);
@@ -213,15 +230,14 @@ __device__ __forceinline__ void compute_h32(const TcArgs& a, const float* consts
   }
   for (int s = s0; s < s1; ++s) {
     const int reg = a.seg_reg[s];
-    const float* ur = a.U + ((size_t)b * a.nseg + s) * F * a.T + t;
-    float uv[8];
-#pragma unroll
-    for (int f = 0; f < F; ++f) uv[f] = __ldg(ur + f * a.T);
+    const float4* up = reinterpret_cast<const float4*>(a.Ut + (((size_t)t * a.Bsz + b) * a.nseg + s) * F);
+    const float4 u0 = __ldg(up), u1 = __ldg(up + 1);
+    const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
     if (reg == 0) {
 #pragma unroll
       for (int f = 0; f < F; ++f) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < CW; j += 4) {
           const float4 w = *reinterpret_cast<const float4*>(consts_s + C::C_M1 + f * HH + c0 + j);
           h[j] = fmaf(uv[f], w.x, h[j]);
           h[j + 1] = fmaf(uv[f], w.y, h[j + 1]);
@@ -234,7 +250,7 @@ __device__ __forceinline__ void compute_h32(const TcArgs& a, const float* consts
 #pragma unroll
       for (int f = 0; f < F; ++f) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < CW; j += 4) {
           const float4 w = __ldg(reinterpret_cast<const float4*>(m + f * HH + j));
           h[j] = fmaf(uv[f], w.x, h[j]);
           h[j + 1] = fmaf(uv[f], w.y, h[j + 1]);
@@ -246,7 +262,7 @@ __device__ __forceinline__ void compute_h32(const TcArgs& a, const float* consts
   }
   if (a.mode == REGT_MODE_REGIONAL) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = h[j] > 0.f ? h[j] : 0.01f * h[j];
+    for (int j = 0; j < CW; ++j) h[j] = h[j] > 0.f ? h[j] : 0.01f * h[j];
   }
 }
 
@@ -264,11 +280,11 @@ struct PlaneIO {
   __device__ static __forceinline__ uint32_t piece_off(int r, int c) {
     return (uint32_t)(((c / (BF ? 8 : 4)) * TC_ROWS + r) * 16);
   }
-  __device__ static __forceinline__ void store32(void* plane, int nqt, int t, int qt, int r, int c0, const float (&v)[32]) {
+  __device__ static __forceinline__ void store(void* plane, int nqt, int t, int qt, int r, int c0, const float (&v)[CW]) {
     uint8_t* tb = tile(plane, nqt, t, qt);
     if constexpr (BF) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < CW; j += 8) {
         uint4 p;
         p.x = pack_bf16(v[j], v[j + 1]);
         p.y = pack_bf16(v[j + 2], v[j + 3]);
@@ -278,15 +294,15 @@ struct PlaneIO {
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < CW; j += 4)
         *reinterpret_cast<float4*>(tb + piece_off(r, c0 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  // read 32 columns of row r from a tile image (global or shared)
-  __device__ static __forceinline__ void load32(const uint8_t* tb, int r, int c0, float (&v)[32]) {
+  // read CW columns of row r from a tile image (global or shared)
+  __device__ static __forceinline__ void load(const uint8_t* tb, int r, int c0, float (&v)[CW]) {
     if constexpr (BF) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < CW; j += 8) {
         const uint4 p = *reinterpret_cast<const uint4*>(tb + piece_off(r, c0 + j));
         const uint32_t w[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
@@ -297,7 +313,7 @@ struct PlaneIO {
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < CW; j += 4) {
         const float4 p = *reinterpret_cast<const float4*>(tb + piece_off(r, c0 + j));
         v[j] = p.x; v[j + 1] = p.y; v[j + 2] = p.z; v[j + 3] = p.w;
       }
@@ -306,43 +322,110 @@ struct PlaneIO {
 };
 
 // ------------------------------------------------------------------------------------------
+// per-row F-wide features of one period (period-major arrays written by k_feat_tc)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_feats(const TcArgs& a, bool valid, long long q, int b, int s0, int s1, int t,
+                                           float (&sv)[8], float (&xv)[8], float (&uv)[8]) {
+  const size_t ro = ((size_t)t * a.BN + (valid ? q : 0)) * F;
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(a.Xt + ro)), x1 = __ldg(reinterpret_cast<const float4*>(a.Xt + ro) + 1);
+  const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.St + ro)), q1 = __ldg(reinterpret_cast<const float4*>(a.St + ro) + 1);
+  float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+  if (s1 > s0) {
+    const float4* up = reinterpret_cast<const float4*>(a.Ut + (((size_t)t * a.Bsz + b) * a.nseg + s0) * F);
+    u0 = __ldg(up);
+    u1 = __ldg(up + 1);
+  }
+  const float m = valid ? 1.f : 0.f;
+  xv[0] = m * x0.x; xv[1] = m * x0.y; xv[2] = m * x0.z; xv[3] = m * x0.w;
+  xv[4] = m * x1.x; xv[5] = m * x1.y; xv[6] = m * x1.z; xv[7] = m * x1.w;
+  sv[0] = m * q0.x; sv[1] = m * q0.y; sv[2] = m * q0.z; sv[3] = m * q0.w;
+  sv[4] = m * q1.x; sv[5] = m * q1.y; sv[6] = m * q1.z; sv[7] = m * q1.w;
+  uv[0] = u0.x; uv[1] = u0.y; uv[2] = u0.z; uv[3] = u0.w; uv[4] = u1.x; uv[5] = u1.y; uv[6] = u1.z; uv[7] = u1.w;
+}
+
+// forward small tile: S (+ zero pad in bf16) | X | U
+template <int FMT, int HH>
+__device__ __forceinline__ void write_small_fwd(uint8_t* sm, int r, const float (&sv)[8], const float (&xv)[8],
+                                                const float (&uv)[8]) {
+  using Cfg = TcCfg<FMT, HH>;
+  constexpr int EPC = 16 / Cfg::ES;  // elements per chunk
+  store_small8<FMT, HH>(sm, Cfg::SMF_TILE, r, 0, sv);
+  if constexpr (FMT == FMT_BF16) *reinterpret_cast<uint4*>(sm + chunk_off(r, 1, TC_ROWS)) = make_uint4(0, 0, 0, 0);
+  store_small8<FMT, HH>(sm, Cfg::SMF_TILE, r, Cfg::SMF_XU_CHUNK * EPC, xv);
+  store_small8<FMT, HH>(sm, Cfg::SMF_TILE, r, Cfg::SMF_XU_CHUNK * EPC + 8, uv);
+}
+
+// h_pre[128 x HH] = [X | U] x [M0 ; M1]   (K = 16), all precision products
+template <int FMT, int HH>
+__device__ __forceinline__ void issue_h_mma(uint32_t tmem_d, uint32_t sm_xu, int sm_split, uint32_t w0, int w_split) {
+  using Cfg = TcCfg<FMT, HH>;
+  const uint32_t idesc = make_idesc(FMT, 128, HH, 0, 0);
+  constexpr int NPROD = (FMT == FMT_TF32) ? 3 : 1;
+  constexpr int KSTEPS = 16 / Cfg::UK;
+  uint32_t acc = 0;
+#pragma unroll
+  for (int p = 0; p < NPROD; ++p) {
+    const int pa = (p == 1) ? 1 : 0, pb = (p == 2) ? 1 : 0;
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s) {
+      umma<FMT>(tmem_d, make_desc(sm_xu + pa * sm_split + s * 2 * TC_ROWS * 16, TC_ROWS * 16, 128, LAYOUT_NONE),
+                make_desc(w0 + pb * w_split + s * 2 * HH * 16, HH * 16, 128, LAYOUT_NONE), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+#define REGT_TS(i) \
+  if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 24) a.dbg[dbg_n * 8 + (i)] = clock64();
+
+// ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
 template <int FMT, int HH>
 __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   using Cfg = TcCfg<FMT, HH>;
+  constexpr int NBUF = Cfg::PIPE ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // align inside the shared window with pointer arithmetic only (an integer round trip would make
+  // every later access a generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* W = smem;                                   // weight image (tiles + consts)
   uint8_t* Ah = W + ((Cfg::FWD_IMG + 1023) & ~1023);   // [NSPLIT][128 x HH]
-  uint8_t* As = Ah + Cfg::NSPLIT * Cfg::A_TILE;        // [NSPLIT] chunk tiles
-  __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c;
+  uint8_t* SMf = Ah + Cfg::NSPLIT * Cfg::A_TILE;       // [NBUF][NSPLIT] small tiles
+  __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c, bar_img, bar_x, bar_h;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < Cfg::FWD_IMG / 16; i += NTHREADS)
-    reinterpret_cast<uint4*>(W)[i] = __ldg(reinterpret_cast<const uint4*>(a.img) + i);
   if (tid == 0) {
     mbar_init(&bar_a, NEPI);
     mbar_init(&bar_zr, 1);
     mbar_init(&bar_a2, NEPI);
     mbar_init(&bar_c, 1);
+    mbar_init(&bar_img, 1);
+    mbar_init(&bar_x, NEPI);
+    mbar_init(&bar_h, 1);
     fence_barrier_init();
+    // weight image -> shared memory with the bulk-copy engine (16 KB pieces)
+    mbar_arrive_expect_tx(&bar_img, Cfg::FWD_IMG);
+    for (int o = 0; o < Cfg::FWD_IMG; o += 16384)
+      bulk_g2s(W + o, a.img + o, min(16384, Cfg::FWD_IMG - o), &bar_img);
   }
-  if (warp == 8) tmem_alloc(&tmem_base_s, 256);
-  fence_proxy_async();
+  if (warp == NEPI_WARPS) tmem_alloc(&tmem_base_s, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(&bar_img, 0);
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(W + Cfg::FWD_W);
   uint32_t ph = 0;
+  int dbg_n = 0;
+  const bool hmma = a.hmma != 0;
 
-  if (warp < 8) {
+  if (warp < NEPI_WARPS) {
     // ================= epilogue / prologue threads =================
     const int r = (warp & 3) * 32 + lane;  // row = TMEM lane
-    const int ch = warp >> 2;              // column half
-    const int c0 = ch * 32;
+    const int ch = warp >> 2;              // column group
+    const int c0 = ch * CW;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
       const int qt = item / a.ntc, tc_i = item % a.ntc;
@@ -350,81 +433,146 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
       const bool valid = q < a.BN;
       const int b = valid ? (int)(q / a.N) : 0, n = valid ? (int)(q % a.N) : 0;
       int s0 = 0, s1 = 0;
-      if (valid && a.mode != REGT_MODE_TGCN) {
+      if (valid) {
         s0 = a.seg_ptr[n];
         s1 = a.seg_ptr[n + 1];
       }
-      float acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      for (int t = tc_i * a.tp; t < (tc_i + 1) * a.tp; ++t) {
-        float h[32], sv[8];
-        compute_h32<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
-        store_operand32<FMT, HH>(Ah, r, c0, h);
+      const int t_begin = tc_i * a.tp, t_end = t_begin + a.tp;
+      int buf = 0;
+      if (hmma) {  // first period of the item: features -> small tile -> h_pre MMA
         if (ch == 0) {
-          store_small8<FMT, HH>(As, Cfg::AS_TILE, r, 0, sv);
-          if constexpr (FMT == FMT_BF16)  // zero padding chunk of the 16-wide k-step
-            *reinterpret_cast<uint4*>(As + chunk_off(r, 1, TC_ROWS)) = make_uint4(0, 0, 0, 0);
+          float sv[8], xv[8], uv[8];
+          load_feats(a, valid, q, b, s0, s1, t_begin, sv, xv, uv);
+          write_small_fwd<FMT, HH>(SMf, r, sv, xv, uv);
         }
         fence_proxy_async();
         tc_fence_before();
+        mbar_arrive(&bar_x);
+      }
+      float acc[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+      for (int t = t_begin; t < t_end; ++t) {
+        const bool last = (t + 1 == t_end);
+        uint8_t* sm_cur = SMf + buf * Cfg::NSPLIT * Cfg::SMF_TILE;
+        float h[CW];
+        REGT_TS(0)
+        if (hmma) {
+          mbar_wait(&bar_h, ph);
+          tc_fence_after();
+          tmem_ld<CW>(tlane + 3 * HH + c0, h);
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
+            h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
+          }
+        } else {
+          float sv[8];
+          compute_h<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
+          if (ch == 0) {
+            store_small8<FMT, HH>(sm_cur, Cfg::SMF_TILE, r, 0, sv);
+            if constexpr (FMT == FMT_BF16) *reinterpret_cast<uint4*>(sm_cur + chunk_off(r, 1, TC_ROWS)) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        REGT_TS(1)
+        store_operand<FMT, HH>(Ah, r, c0, h);
+        fence_proxy_async();
+        tc_fence_before();
         mbar_arrive(&bar_a);
+        if (hmma && Cfg::PIPE && !last && ch == 0) {  // next period's features while the gate MMA runs
+          float sv[8], xv[8], uv[8];
+          load_feats(a, valid, q, b, s0, s1, t + 1, sv, xv, uv);
+          write_small_fwd<FMT, HH>(SMf + (buf ^ 1) * Cfg::NSPLIT * Cfg::SMF_TILE, r, sv, xv, uv);
+        }
 
         // ---- E1: gates ----
+        REGT_TS(2)
         mbar_wait(&bar_zr, ph);
         tc_fence_after();
-        float z[32];
+        REGT_TS(3)
+        float z[CW];
         {
-          float raw[32];
-          tmem_ld32(tlane + c0, raw);
+          float raw[CW];
+          tmem_ld<CW>(tlane + c0, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] = fast_sigmoid(raw[j] + consts[Cfg::C_CZR + c0 + j]);
-          PlaneIO<FMT, HH>::store32(a.Zp, a.nqt, t, qt, r, c0, z);
-          tmem_ld32(tlane + HH + c0, raw);
-          float hr[32];
+          for (int j = 0; j < CW; ++j) z[j] = fast_sigmoid(raw[j] + consts[Cfg::C_CZR + c0 + j]);
+          PlaneIO<FMT, HH>::store(a.Zp, a.nqt, t, qt, r, c0, z);
+          tmem_ld<CW>(tlane + HH + c0, raw);
+          float hr[CW];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CW; ++j) {
             const float rg = fast_sigmoid(raw[j] + consts[Cfg::C_CZR + HH + c0 + j]);
             raw[j] = rg;
             hr[j] = h[j] * rg;
           }
-          PlaneIO<FMT, HH>::store32(a.Rp, a.nqt, t, qt, r, c0, raw);
-          store_operand32<FMT, HH>(Ah, r, c0, hr);
+          PlaneIO<FMT, HH>::store(a.Rp, a.nqt, t, qt, r, c0, raw);
+          store_operand<FMT, HH>(Ah, r, c0, hr);
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bar_a2);
 
         // ---- E2: candidate, blend, attention accumulation ----
+        REGT_TS(4)
         mbar_wait(&bar_c, ph);
         tc_fence_after();
+        REGT_TS(5)
         {
-          float raw[32];
-          tmem_ld32(tlane + 2 * HH + c0, raw);
+          float raw[CW];
+          tmem_ld<CW>(tlane + 2 * HH + c0, raw);
           const float pt = consts[Cfg::C_PROBS + t];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CW; ++j) {
             const float hc = fast_tanh(raw[j] + consts[Cfg::C_CC + c0 + j]);
             raw[j] = hc;
             acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
           }
-          PlaneIO<FMT, HH>::store32(a.Hcp, a.nqt, t, qt, r, c0, raw);
+          PlaneIO<FMT, HH>::store(a.Hcp, a.nqt, t, qt, r, c0, raw);
         }
+        if (hmma && !Cfg::PIPE && !last) {  // single-buffered small tile: refill after the candidate MMA is done
+          if (ch == 0) {
+            float sv[8], xv[8], uv[8];
+            load_feats(a, valid, q, b, s0, s1, t + 1, sv, xv, uv);
+            write_small_fwd<FMT, HH>(SMf, r, sv, xv, uv);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bar_x);
+        }
+        REGT_TS(6)
+        ++dbg_n;
         ph ^= 1;
+        if (Cfg::PIPE) buf ^= 1;
       }
       if (valid) {
         float* o = a.hid_part + ((size_t)tc_i * a.BN + q) * HH + c0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
     }
     tc_fence_before();
   } else {
-    // ================= MMA issuer (warp 8, one elected lane) =================
+    // ================= MMA issuer (one elected lane of the last warp) =================
     const uint32_t idesc_zr = make_idesc(FMT, 128, 2 * HH, 0, 0), idesc_c = make_idesc(FMT, 128, HH, 0, 0);
-    const uint32_t ah = smem_u32(Ah), as = smem_u32(As), w = smem_u32(W);
+    const uint32_t ah = smem_u32(Ah), smf = smem_u32(SMf), w = smem_u32(W);
+    constexpr int SMB = Cfg::NSPLIT * Cfg::SMF_TILE;                 // bytes per small-tile buffer
+    constexpr int XU = Cfg::SMF_XU_CHUNK * TC_ROWS * 16;             // offset of the X | U chunks
+    uint32_t phx = 0;
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      for (int t = 0; t < a.tp; ++t) {
+      int buf = 0;
+      if (hmma) {
+        mbar_wait(&bar_x, phx);
+        phx ^= 1;
+        tc_fence_after();
+        if (lane == 0) {
+          issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
+          umma_commit(&bar_h);
+        }
+        __syncwarp();
+      }
+      for (int ti = 0; ti < a.tp; ++ti) {
+        const bool last = (ti + 1 == a.tp);
+        const uint32_t as = smf + buf * SMB;
         mbar_wait(&bar_a, ph);
         tc_fence_after();
         if (lane == 0) {
@@ -438,15 +586,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
           issue_gate_mma<FMT, HH>(tmem + 2 * HH, ah, as, w + Cfg::WZR_H + Cfg::WZR_S,
                                   w + Cfg::WZR_H + Cfg::WZR_S + Cfg::WC_H, HH, idesc_c);
           umma_commit(&bar_c);
+          if (hmma && Cfg::PIPE && !last) {  // next period's h_pre, off the critical path
+            issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + (buf ^ 1) * SMB + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
+            umma_commit(&bar_h);
+          }
         }
         __syncwarp();
+        if (hmma && !Cfg::PIPE && !last) {
+          mbar_wait(&bar_x, phx);
+          phx ^= 1;
+          tc_fence_after();
+          if (lane == 0) {
+            issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
+            umma_commit(&bar_h);
+          }
+          __syncwarp();
+        }
         ph ^= 1;
+        if (Cfg::PIPE) buf ^= 1;
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256);
+  if (warp == NEPI_WARPS) tmem_dealloc(tmem, 256);
 }
 
 // out_hidden[q][j] = sum over the t-chunks of the per-item partial attention sums
@@ -467,6 +630,7 @@ __global__ void k_hid_reduce(const float* __restrict__ part, int ntc, long long 
 int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y, int B,
                      int n_out, int n_in, int width, cudaStream_t st);
 int launch_prep(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int T, float* Xt, float* St, float* Ut, cudaStream_t st);
 
 static int num_sms() {
   static int n = 0;
@@ -498,16 +662,18 @@ static int choose_tp(int nqt, int T, int slots) {
 static TcArgs make_tcargs(const regt_args* a, const Layout& L, int slots) {
   TcArgs k{};
   k.BN = a->B * a->N; k.N = a->N; k.T = a->T; k.nseg = a->plan.nseg; k.mode = a->mode;
+  k.hmma = (a->plan.R == 1) ? 1 : 0;   // one regional list: every row uses the same M1 block
   k.nqt = (k.BN + TC_ROWS - 1) / TC_ROWS;
   k.tp = choose_tp(k.nqt, a->T, slots);
   k.ntc = a->T / k.tp;
   k.items = k.nqt * k.ntc;
-  k.x = a->x; k.S = L.S; k.U = L.U;
+  k.Xt = L.Xt; k.St = L.S; k.Ut = L.U; k.Bsz = a->B;
   k.seg_ptr = a->plan.seg_ptr; k.seg_reg = a->plan.seg_reg;
   k.M1t = L.M1t;
   k.img = L.tc_img_f;
   k.Zp = L.Zp; k.Rp = L.Rp; k.Hcp = L.Hcp; k.hid_part = L.hid_part;
   k.G = L.G; k.dhp = L.dhp_p; k.wpart = L.tc_wpart; k.dprobs_part = L.tc_dpp;
+  k.dbg = getenv("REGT_TC_DEBUG") ? reinterpret_cast<long long*>(L.tc_wpart) : nullptr;  // scratch reuse (debug only)
   return k;
 }
 
@@ -515,14 +681,15 @@ template <int FMT, int HH>
 static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   using Cfg = TcCfg<FMT, HH>;
   static_assert(Cfg::FWD_IMG <= TC_IMG_BYTES && Cfg::BWD_IMG <= TC_IMG_BYTES, "weight image too large");
-  const int n_pack = 2 * HH * HH + 2 * HH * 16 + HH * HH + HH * 16 + Cfg::C_FLOATS + 3 * HH * HH;
+  const int n_pack = 2 * HH * HH + 2 * HH * 16 + HH * HH + HH * 16 + Cfg::C_FLOATS + 3 * HH * HH + HH * 16;
   k_pack_tc<FMT, HH><<<cdiv(n_pack, 256), 256, 0, st>>>(L.Wzr, L.Wc, L.czr, L.cc, L.c0, L.M0t, L.M1t, L.probs, a->T,
                                                        a->p.lin_w[0], a->p.lin_w[1], a->p.lin_w[2], L.tc_img_f,
                                                        L.tc_img_b);
   REGT_LAUNCHED("k_pack_tc", st);
   const int slots = num_sms();
   TcArgs k = make_tcargs(a, L, slots);
-  const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + Cfg::NSPLIT * (Cfg::A_TILE + Cfg::AS_TILE);
+  const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + Cfg::NSPLIT * Cfg::A_TILE +
+                      (Cfg::PIPE ? 2 : 1) * Cfg::NSPLIT * Cfg::SMF_TILE;
   REGT_CUDA(cudaFuncSetAttribute(k_cell_fwd_tc<FMT, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(slots, k.items);
   k_cell_fwd_tc<FMT, HH><<<grid, NTHREADS, smem, st>>>(k);
@@ -538,11 +705,7 @@ int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   REGT_CHECK(a->mode != REGT_MODE_TGCN, "tensor-core precisions do not cover the bare TGCN cell; use precision fp32");
   REGT_CHECK(a->T <= 64, "tensor-core path supports up to 64 periods");
   if (launch_prep(a, L, st)) return -1;
-  if (launch_spmm_rows(a->plan.g_rowptr, a->plan.g_col, a->plan.g_val, a->x, L.S, a->B, a->N, a->N, F * a->T, st)) return -1;
-  if (a->plan.nseg > 0) {
-    if (launch_spmm_rows(a->plan.seg_eptr, a->plan.c_col, a->plan.c_val, a->x, L.U, a->B, a->plan.nseg, a->N, F * a->T, st))
-      return -1;
-  }
+  if (launch_feat_tc(a->plan, a->x, a->B, a->T, L.Xt, L.S, L.U, st)) return -1;
   if (a->precision == REGT_PREC_TF32X3) return run_fwd_tc<FMT_TF32, 64>(a, L, st);
   return run_fwd_tc<FMT_BF16, 64>(a, L, st);
 }
@@ -551,7 +714,8 @@ int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
 // backward (bf16 operands): data gradients and ALL weight gradients on the tensor cores
 // ------------------------------------------------------------------------------------------
 // Per period and 128-row tile (same work items / thread ownership as the forward):
-//   E0  recompute h; read saved Z,R,H~ (bulk-prefetched tile); dH' = probs[t] G;
+//   H0  h_pre = [X|U] . [M0;M1]  (recompute, TMEM cols 320..383; issued one period ahead)
+//   E0  h = act(h_pre + c0); read saved Z,R,H~ (bulk-prefetched tile); dH' = probs[t] G;
 //       Dh = dH~ (1-H~^2), Dz = dZ Z(1-Z); operand tiles Dh, Dz, h, h*R -> smem
 //   M1  dHR = Dh . B_h                                  (TMEM cols   0.. 63)
 //   E1  dh += dHR R ; Dr = dHR h R(1-R) -> smem
@@ -572,25 +736,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   using PIO = PlaneIO<FMT, HH>;
   constexpr int TILE = Cfg::A_TILE;          // 16 KB
   constexpr int PT = PIO::TILE_BYTES;        // 16 KB
+  constexpr int SMT = 4 * TC_ROWS * 16;      // small tile: S | X | U | ones
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* W = smem;                                     // Bt_z | Bt_r | Bt_h | consts
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* W = smem;                                     // Bt_z | Bt_r | Bt_h | B0 | consts
   uint8_t* T_DH = W + ((Cfg::BWD_IMG + 1023) & ~1023);
   uint8_t* T_DHP = T_DH + TILE;
   uint8_t* T_DZ = T_DHP + TILE;
   uint8_t* T_DR = T_DZ + TILE;
   uint8_t* T_H = T_DR + TILE;
   uint8_t* T_HR = T_H + TILE;
-  uint8_t* SM = T_HR + TILE;                             // chunk tile: S | X | U | ones  (4 chunks)
-  uint8_t* STG = SM + 4 * TC_ROWS * 16;                  // staged Z | R | H~ tiles
-  __shared__ uint64_t bar_stage, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w;
+  uint8_t* SM = T_HR + TILE;                             // [2] small tiles (double-buffered)
+  uint8_t* STG = SM + 2 * SMT;                           // staged Z | R | H~ tiles
+  float* GS = reinterpret_cast<float*>(STG + 3 * PT);    // G tile [HH/4][128][4] fp32
+  __shared__ uint64_t bar_stage, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w, bar_img, bar_x, bar_h;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[2][8];
+  __shared__ float red[2][NEPI_WARPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < Cfg::BWD_IMG / 16; i += NTHREADS)
-    reinterpret_cast<uint4*>(W)[i] = __ldg(reinterpret_cast<const uint4*>(a.img) + i);
   if (tid == 0) {
+    mbar_init(&bar_img, 1);
     mbar_init(&bar_stage, 1);
     mbar_init(&bar_e0, NEPI);
     mbar_init(&bar_m1, 1);
@@ -598,22 +763,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     mbar_init(&bar_m2, 1);
     mbar_init(&bar_e2, NEPI);
     mbar_init(&bar_w, 1);
+    mbar_init(&bar_x, NEPI);
+    mbar_init(&bar_h, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(&bar_img, Cfg::BWD_IMG);
+    for (int o = 0; o < Cfg::BWD_IMG; o += 16384)
+      bulk_g2s(W + o, a.img + o, min(16384, Cfg::BWD_IMG - o), &bar_img);
   }
-  if (warp == 8) tmem_alloc(&tmem_base_s, 512);
-  fence_proxy_async();
+  if (warp == NEPI_WARPS) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(&bar_img, 0);
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(W + Cfg::BWD_W);
   uint32_t ph = 0;
   int gstep = 0;
+  const bool hmma = a.hmma != 0;
 
-  if (warp < 8) {
+  auto write_small_bwd = [&](uint8_t* sm, int r, const float (&sv)[8], const float (&xv)[8], const float (&uv)[8]) {
+    store_small8<FMT, HH>(sm, 0, r, 0, sv);
+    store_small8<FMT, HH>(sm, 0, r, 8, xv);
+    store_small8<FMT, HH>(sm, 0, r, 16, uv);
+    *reinterpret_cast<uint4*>(sm + chunk_off(r, 3, TC_ROWS)) = make_uint4(0x00003F80u, 0, 0, 0);  // bf16 1.0
+  };
+
+  if (warp < NEPI_WARPS) {
     const int r = (warp & 3) * 32 + lane;
     const int ch = warp >> 2;
-    const int c0 = ch * 32;
+    const int c0 = ch * CW;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
       const int qt = item / a.ntc, tc_i = item % a.ntc;
@@ -625,21 +803,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
         s0 = a.seg_ptr[n];
         s1 = a.seg_ptr[n + 1];
       }
-      for (int t = tc_i * a.tp; t < (tc_i + 1) * a.tp; ++t) {
-        float h[32], dh[32], rr[32], sv[8];
-        compute_h32<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
+      const int t_begin = tc_i * a.tp, t_end = t_begin + a.tp;
+      // ---- item prologue: first period's small tile (+ h_pre MMA) and the G tile into smem ----
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // previous item's readers of GS are done
+      {
+        const long long q_base = (long long)qt * TC_ROWS;
+        for (int i = tid; i < TC_ROWS * HH / 4; i += NEPI) {     // coalesced float4 reads of the row-major tile
+          const int row = i / (HH / 4), c4 = i % (HH / 4);
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q_base + row < a.BN) g = __ldg(reinterpret_cast<const float4*>(a.G + (q_base + row) * HH) + c4);
+          reinterpret_cast<float4*>(GS)[c4 * TC_ROWS + row] = g;
+        }
+      }
+      int buf = 0;
+      if (ch == 0) {
+        float sv[8], xv[8], uv[8];
+        load_feats(a, valid, q, b, s0, s1, t_begin, sv, xv, uv);
+        if (gstep > 0) mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));  // W2s of the previous step read SM[0/1]
+        write_small_bwd(SM, r, sv, xv, uv);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar_x);
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // GS visible to all epilogue threads
+
+      for (int t = t_begin; t < t_end; ++t) {
+        const bool last = (t + 1 == t_end);
+        float h[CW], dh[CW], rr[CW];
+        if (hmma) {
+          mbar_wait(&bar_h, ph);
+          tc_fence_after();
+          tmem_ld<CW>(tlane + 320 + c0, h);
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
+            h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
+          }
+        } else {
+          float sv[8];
+          compute_h<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
+        }
         const float pt = consts[Cfg::C_PROBS + t];
         float dp = 0.f;
         mbar_wait(&bar_stage, ph);
         {
-          float z[32], hc[32];
-          PIO::load32(STG, r, c0, z);
-          PIO::load32(STG + PT, r, c0, rr);
-          PIO::load32(STG + 2 * PT, r, c0, hc);
+          float z[CW], hc[CW];
+          PIO::load(STG, r, c0, z);
+          PIO::load(STG + PT, r, c0, rr);
+          PIO::load(STG + 2 * PT, r, c0, hc);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) g4 = __ldg(reinterpret_cast<const float4*>(a.G + q * HH + c0 + j));
+          for (int j = 0; j < CW; j += 4) {
+            const float4 g4 = reinterpret_cast<const float4*>(GS)[((c0 + j) / 4) * TC_ROWS + r];
             const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -653,42 +867,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
             }
           }
           if (gstep > 0) mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));  // previous step's MMAs released the tiles
-          store_operand32<FMT, HH>(T_DZ, r, c0, z);
-          store_operand32<FMT, HH>(T_DH, r, c0, hc);
+          store_operand<FMT, HH>(T_DZ, r, c0, z);
+          store_operand<FMT, HH>(T_DH, r, c0, hc);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] = h[j] * rr[j];
-          store_operand32<FMT, HH>(T_HR, r, c0, z);
-          store_operand32<FMT, HH>(T_H, r, c0, h);
-        }
-        if (ch == 0) {
-          float xv[8], uv[8];
-#pragma unroll
-          for (int f = 0; f < F; ++f) {
-            xv[f] = valid ? __ldg(a.x + q * F * a.T + f * a.T + t) : 0.f;
-            uv[f] = (s1 > s0) ? __ldg(a.U + ((size_t)b * a.nseg + s0) * F * a.T + f * a.T + t) : 0.f;
-          }
-          store_small8<FMT, HH>(SM, 0, r, 0, sv);
-          store_small8<FMT, HH>(SM, 0, r, 8, xv);
-          store_small8<FMT, HH>(SM, 0, r, 16, uv);
-          *reinterpret_cast<uint4*>(SM + chunk_off(r, 3, TC_ROWS)) = make_uint4(0x00003F80u, 0, 0, 0);  // bf16 1.0
+          for (int j = 0; j < CW; ++j) z[j] = h[j] * rr[j];
+          store_operand<FMT, HH>(T_HR, r, c0, z);
+          store_operand<FMT, HH>(T_H, r, c0, h);
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bar_e0);
+        if (!last && ch == 0) {  // next period's small tile while M1 runs (other buffer)
+          float sv[8], xv[8], uv[8];
+          load_feats(a, valid, q, b, s0, s1, t + 1, sv, xv, uv);
+          write_small_bwd(SM + (buf ^ 1) * SMT, r, sv, xv, uv);
+        }
 
         // ---- E1 ----
         mbar_wait(&bar_m1, ph);
         tc_fence_after();
         {
-          float raw[32];
-          tmem_ld32(tlane + c0, raw);
+          float raw[CW];
+          tmem_ld<CW>(tlane + c0, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CW; ++j) {
             const float dHR = raw[j];
             dh[j] = fmaf(dHR, rr[j], dh[j]);
             raw[j] = dHR * h[j] * rr[j] * (1.0f - rr[j]);   // Dr
           }
-          store_operand32<FMT, HH>(T_DR, r, c0, raw);
+          store_operand<FMT, HH>(T_DR, r, c0, raw);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -698,16 +905,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
         mbar_wait(&bar_m2, ph);
         tc_fence_after();
         {
-          float raw[32];
-          tmem_ld32(tlane + 64 + c0, raw);
+          float raw[CW];
+          tmem_ld<CW>(tlane + 64 + c0, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CW; ++j) {
             float v = dh[j] + raw[j];
             if (a.mode == REGT_MODE_REGIONAL) v *= (h[j] > 0.f ? 1.0f : 0.01f);
             raw[j] = v;
           }
-          store_operand32<FMT, HH>(T_DHP, r, c0, raw);
-          if (a.mode == REGT_MODE_REGIONAL) PlaneIO<FMT_TF32, HH>::store32(a.dhp, a.nqt, t, qt, r, c0, raw);
+          store_operand<FMT, HH>(T_DHP, r, c0, raw);
+          if (a.mode == REGT_MODE_REGIONAL && !hmma) PlaneIO<FMT_TF32, HH>::store(a.dhp, a.nqt, t, qt, r, c0, raw);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -717,14 +924,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) dp += __shfl_down_sync(0xffffffffu, dp, d);
         if (lane == 0) red[gstep & 1][warp] = dp;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
         if (tid == 0) {
           float sacc = 0.f;
 #pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) sacc += red[gstep & 1][w8];
+          for (int w8 = 0; w8 < NEPI_WARPS; ++w8) sacc += red[gstep & 1][w8];
           a.dprobs_part[(size_t)qt * a.T + t] = sacc;
         }
         ph ^= 1;
+        buf ^= 1;
         ++gstep;
       }
     }
@@ -733,29 +941,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     tc_fence_after();
     float* wp = a.wpart + ((size_t)blockIdx.x * TC_ROWS + r) * WP_COLS;
     {
-      float v[32];
-      tmem_ld32(tlane + 128 + c0, v);
+      float v[CW];
+      tmem_ld<CW>(tlane + 128 + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      tmem_ld32(tlane + 224 + c0, v);
+      for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(wp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      tmem_ld<CW>(tlane + 224 + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(wp + 96 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      float u[16];
-      tmem_ld16(tlane + 192 + ch * 16, u);
+      for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(wp + 96 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      constexpr int SW = 32 / (64 / CW);  // columns of the 32-wide accumulators per thread
+      float u[SW];
+      tmem_ld<SW>(tlane + 192 + ch * SW, u);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(wp + 64 + ch * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
-      tmem_ld16(tlane + 288 + ch * 16, u);
+      for (int j = 0; j < SW; j += 4) *reinterpret_cast<float4*>(wp + 64 + ch * SW + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+      tmem_ld<SW>(tlane + 288 + ch * SW, u);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(wp + 160 + ch * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+      for (int j = 0; j < SW; j += 4) *reinterpret_cast<float4*>(wp + 160 + ch * SW + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
     }
     tc_fence_before();
   } else {
-    // ================= MMA issuer + plane prefetch (warp 8, one elected lane) =================
+    // ================= MMA issuer + plane prefetch (one elected lane of the last warp) =================
     const uint32_t id_dg = make_idesc(FMT, 128, HH, 0, 0);        // data gradients (K-major)
     const uint32_t id_w = make_idesc(FMT, 128, HH, 1, 1);         // weight gradients (MN-major)
     const uint32_t id_ws = make_idesc(FMT, 128, 32, 1, 1);
     const uint32_t w = smem_u32(W), tdh = smem_u32(T_DH), tdz = smem_u32(T_DZ), tdr = smem_u32(T_DR), th = smem_u32(T_H),
-                   thr = smem_u32(T_HR), sm = smem_u32(SM);
+                   thr = smem_u32(T_HR), sm0 = smem_u32(SM);
+    constexpr int XU = 1 * TC_ROWS * 16;  // X | U are chunks 1,2 of the small tile
+    uint32_t phx = 0;
     auto prefetch = [&](int item, int t) {
       const int qt = item / a.ntc;
       mbar_arrive_expect_tx(&bar_stage, 3 * PT);
@@ -766,14 +977,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     if (lane == 0 && blockIdx.x < a.items) prefetch(blockIdx.x, (blockIdx.x % a.ntc) * a.tp);
     for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
       const int tc_i = item % a.ntc;
+      int buf = 0;
+      mbar_wait(&bar_x, phx);
+      phx ^= 1;
+      tc_fence_after();
+      if (lane == 0 && hmma) {
+        issue_h_mma<FMT, HH>(tmem + 320, sm0 + XU, 0, w + 3 * Cfg::BT, 0);
+        umma_commit(&bar_h);
+      }
+      __syncwarp();
       for (int ti = 0; ti < a.tp; ++ti) {
+        const bool last = (ti + 1 == a.tp);
         const uint32_t accw = gstep > 0 ? 1u : 0u;
+        const uint32_t sm = sm0 + buf * SMT;
         mbar_wait(&bar_e0, ph);
         tc_fence_after();
         if (lane == 0) {
           // the staged planes of this step are consumed: fetch the next step's
           int nitem = item, nt = tc_i * a.tp + ti + 1;
-          if (ti + 1 == a.tp) {
+          if (last) {
             nitem = item + gridDim.x;
             nt = (nitem % a.ntc) * a.tp;
           }
@@ -799,6 +1021,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
             umma<FMT>(tmem + 64, make_desc(tdr + s * 32, 16, 1024, LAYOUT_SW128),
                       make_desc(w + Cfg::BT + s * 32, 16, 1024, LAYOUT_SW128), id_dg, 1u);
           umma_commit(&bar_m2);
+          if (hmma && !last) {  // next period's h_pre (the other small-tile buffer was filled before bar_e1)
+            issue_h_mma<FMT, HH>(tmem + 320, sm0 + (buf ^ 1) * SMT + XU, 0, w + 3 * Cfg::BT, 0);
+            umma_commit(&bar_h);
+          }
           // W1 / W1s: [Dz|Dr]^T . h , [Dz|Dr]^T . [S|X|U|1]   (contraction over the 128 rows)
 #pragma unroll
           for (int s = 0; s < TC_ROWS / 16; ++s) {
@@ -822,13 +1048,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
         }
         __syncwarp();
         ph ^= 1;
+        buf ^= 1;
         ++gstep;
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == NEPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
 // sum the per-CTA partials and scatter them into the collapsed-weight gradient buffers
@@ -882,11 +1109,12 @@ __global__ void __launch_bounds__(HH) k_wgrad_m1_tc(const float* __restrict__ dh
     const int b = (int)(i % B);
     const long long q = (long long)b * N + seg_node[s];
     const int qt = (int)(q / TC_ROWS), row = (int)(q % TC_ROWS);
-    const float* ur = U + ((size_t)b * nseg + s) * F * T;
     for (int t = 0; t < T; ++t) {
       const float d = __ldg(dhp + ((((size_t)t * nqt + qt) * (HH / 4) + n / 4) * TC_ROWS + row) * 4 + (n & 3));
-#pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(ur + f * T + t), acc[f]);
+      const float4* up = reinterpret_cast<const float4*>(U + (((size_t)t * B + b) * nseg + s) * F);  // period-major Ut
+      const float4 u0 = __ldg(up), u1 = __ldg(up + 1);
+      acc[0] = fmaf(d, u0.x, acc[0]); acc[1] = fmaf(d, u0.y, acc[1]); acc[2] = fmaf(d, u0.z, acc[2]); acc[3] = fmaf(d, u0.w, acc[3]);
+      acc[4] = fmaf(d, u1.x, acc[4]); acc[5] = fmaf(d, u1.y, acc[5]); acc[6] = fmaf(d, u1.z, acc[6]); acc[7] = fmaf(d, u1.w, acc[7]);
     }
   }
   float* o = part + (((size_t)blockIdx.z * R + r) * HH + n) * F;
@@ -907,8 +1135,8 @@ int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   TcArgs k = make_tcargs(a, L, slots);
   k.img = L.tc_img_b;
   const int grid = min(min(slots, k.items), TC_MAX_CTAS);
-  const size_t smem = 1024 + ((Cfg::BWD_IMG + 1023) & ~1023) + 6 * Cfg::A_TILE + 4 * TC_ROWS * 16 +
-                      3 * PlaneIO<FMT_BF16, HH>::TILE_BYTES;
+  const size_t smem = 1024 + ((Cfg::BWD_IMG + 1023) & ~1023) + 6 * Cfg::A_TILE + 2 * 4 * TC_ROWS * 16 +
+                      3 * PlaneIO<FMT_BF16, HH>::TILE_BYTES + TC_ROWS * HH * 4;
   REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd_tc<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_cell_bwd_tc<HH><<<grid, NTHREADS, smem, st>>>(k);
   REGT_LAUNCHED("k_cell_bwd_tc", st);

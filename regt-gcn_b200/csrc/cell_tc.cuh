@@ -22,7 +22,15 @@ struct TcCfg {
   static constexpr int WZR_S = 2 * (2 * HH) * 16;
   static constexpr int WC_H = HH * KBYTES;
   static constexpr int WC_S = 2 * HH * 16;
-  static constexpr int FWD_SPLIT = WZR_H + WZR_S + WC_H + WC_S;   // per split, all multiples of 1024
+  // regional combine on the tensor core: B0[n][k] = (M0 | M1[0]) (K = 16 = X | U), chunk tile of HH rows
+  static constexpr int W0 = (FMT == tc::FMT_TF32 ? 4 : 2) * HH * 16;
+  static constexpr int FWD_SPLIT = WZR_H + WZR_S + WC_H + WC_S + W0;   // per split, all multiples of 1024
+  static constexpr int OFF_W0 = WZR_H + WZR_S + WC_H + WC_S;
+  // small per-row operand tile of the forward ([chunk][row][16 B]): S (+pad) | X | U
+  static constexpr int SMF_CHUNKS = (FMT == tc::FMT_TF32) ? 6 : 4;
+  static constexpr int SMF_TILE = SMF_CHUNKS * TC_ROWS * 16;
+  static constexpr int SMF_XU_CHUNK = 2;                           // first chunk of the X | U part
+  static constexpr bool PIPE = (FMT == tc::FMT_BF16);             // double-buffer the small tile
   static constexpr int FWD_W = NSPLIT * FWD_SPLIT;
   // fp32 constants after the tiles
   static constexpr int C_CZR = 0, C_CC = 2 * HH, C_C0 = 3 * HH, C_M0 = 4 * HH, C_M1 = 4 * HH + 8 * HH,
@@ -31,14 +39,17 @@ struct TcCfg {
   // backward weights (B operands of the data gradients, K-major over the gate index n):
   //   Bt_g[k][n] = linear_g.weight[n][HH + k]      rows = k (hidden input index), K = n
   static constexpr int BT = HH * KBYTES;
-  static constexpr int BWD_W = NSPLIT * 3 * BT;
+  static constexpr int BWD_SPLIT = 3 * BT + W0;
+  static constexpr int BWD_W = NSPLIT * BWD_SPLIT;
   static constexpr int BWD_IMG = BWD_W + C_FLOATS * 4;
   static_assert(KBYTES % 128 == 0, "H-wide operand must be whole 128-byte swizzle blocks");
 };
 
 struct TcArgs {
   int BN, N, T, nseg, mode, tp, ntc, nqt, items;
-  const float *x, *S, *U;
+  int hmma;                // 1: h_pre = [X|U] x [M0;M1] on the tensor core (single regional list)
+  const float *Xt, *St, *Ut;   // period-major F-wide features [T][rows][F]
+  int Bsz;
   const int32_t *seg_ptr, *seg_reg;
   const float* M1t;        // [R][F][H] fp32 (global; region 0 is also in the image)
   const uint8_t* img;      // weight image
@@ -49,6 +60,7 @@ struct TcArgs {
   float* dhp;              // d h_pre plane [T][nqt][H/4][128][4] (regional wgrad of M1)
   float* wpart;            // [grid][...] per-CTA weight-gradient partials
   float* dprobs_part;      // [items][tp]
+  long long* dbg;          // optional phase timestamps (REGT_TC_DEBUG)
 };
 
 }  // namespace regt

@@ -56,6 +56,48 @@ __global__ void __launch_bounds__(256) k_spmm_rows(const int32_t* __restrict__ r
   }
 }
 
+// Feature builder of the tensor-core path: the same warp-per-row gather, but the results are written
+// period-major so that one (tile, period) of the cell kernels reads contiguous 32-byte rows:
+//   Xt[t][q][F] = x[q][:, t]      St[t][q][F] = (A_hat x)[q][:, t]      Ut[t][b*nseg+s][F] = (L_hat_r x) per segment
+// warps [0, B*N) build Xt/St for row q; warps [B*N, B*N + B*nseg) build Ut for segment (b, s).
+__global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_rowptr, const int32_t* __restrict__ g_col,
+                                                 const float* __restrict__ g_val, const int32_t* __restrict__ seg_eptr,
+                                                 const int32_t* __restrict__ c_col, const float* __restrict__ c_val,
+                                                 const float* __restrict__ x, int B, int N, int nseg, int T,
+                                                 float* __restrict__ Xt, float* __restrict__ St, float* __restrict__ Ut) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long BN = (long long)B * N, BS = (long long)B * nseg;
+  if (warp >= BN + BS) return;
+  const bool is_seg = warp >= BN;
+  const long long w = is_seg ? warp - BN : warp;
+  const int b = (int)(w / (is_seg ? nseg : N)), r = (int)(w % (is_seg ? nseg : N));
+  const int* rowptr = is_seg ? seg_eptr : g_rowptr;
+  const int* col = is_seg ? c_col : g_col;
+  const float* val = is_seg ? c_val : g_val;
+  const int W = REGT_F * T;  // floats per row
+  const float* xb = x + (size_t)b * N * W;
+  const int e0 = rowptr[r], e1 = rowptr[r + 1];
+  const long long out_row = is_seg ? w : w;          // row index inside a period plane
+  const long long plane_rows = is_seg ? BS : BN;
+  float* dst = is_seg ? Ut : St;
+  for (int i = lane; i < W; i += 32) {
+    float acc = 0.f;
+    for (int e = e0; e < e1; ++e) acc = fmaf(__ldg(val + e), __ldg(xb + (size_t)__ldg(col + e) * W + i), acc);
+    const int f = i / T, t = i - f * T;
+    dst[((size_t)t * plane_rows + out_row) * REGT_F + f] = acc;
+    if (!is_seg) Xt[((size_t)t * BN + w) * REGT_F + f] = __ldg(xb + (size_t)r * W + i);
+  }
+}
+
+int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int T, float* Xt, float* St, float* Ut, cudaStream_t st) {
+  const long long warps = (long long)B * p.N + (long long)B * p.nseg;
+  k_feat_tc<<<cdiv(warps * 32, 256), 256, 0, st>>>(p.g_rowptr, p.g_col, p.g_val, p.seg_eptr, p.c_col, p.c_val, x, B, p.N,
+                                                  p.nseg, T, Xt, St, Ut);
+  REGT_LAUNCHED("k_feat_tc", st);
+  return 0;
+}
+
 int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y, int B,
                      int n_out, int n_in, int width, cudaStream_t st) {
   REGT_CHECK(width % 4 == 0 && width > 0, "spmm: width %d must be a positive multiple of 4", width);
