@@ -122,6 +122,9 @@ typedef struct regt_args {
   int32_t mode;           /* REGT_MODE_*                                                  */
   int32_t precision;      /* REGT_PREC_*                                                  */
   int32_t accumulate;     /* backward: 0 overwrite param grads, 1 add into them           */
+  int32_t fuse_head;      /* 1 (needs y): head_forward also runs the head's backward (d_out,  */
+  int32_t _reserved;      /*    gradient wrt out_hidden, weight-gradient partials) in the same */
+                          /*    kernel; head_backward then only reduces the partials           */
   regt_graph_plan plan;
   const float* x;         /* [B,N,F,T] f32, T innermost (load_dataset.py:456)             */
   const float* y;         /* [B,N,O] or NULL: if set head_forward also writes loss, d_out  */

@@ -102,6 +102,7 @@ struct Layout {
   float* dM1;    // [R][H][F]
   float* dc0;    // [H]
   float* dprobs; // [T]
+  float* hpart;  // fused-head per-CTA partials
   float* part;   // split-K partials
   size_t part_floats;
   // tensor-core path (precision != FP32): weight images, tile-layout planes, per-CTA partials

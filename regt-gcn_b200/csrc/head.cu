@@ -154,6 +154,253 @@ __global__ void k_copy_or_zero(const float* __restrict__ src, float* __restrict_
   if (i < n) dst[i] = src ? src[i] : 0.f;
 }
 
+// ------------------------------------------------------------------------------------------
+// fused training head (fuse_head): forward + loss + data gradients + weight-gradient partials in
+// ONE persistent kernel; weights stay in shared memory, dW1 accumulates in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int HP_MAX_CTAS = 148;
+__host__ __device__ inline int head_part_stride(int H, int O) { return HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 4; }
+
+template <int H>
+__global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restrict__ hpart, int ntiles) {
+  constexpr int HJ = H / 16;             // dW1 columns per thread
+  constexpr int LDA = H + 4, LD1 = HEAD_HID + 4;
+  extern __shared__ __align__(16) float smem[];
+  const int O = a.O, OP = (O + 3) & ~3, LDO = OP + 4;
+  float* W1t = smem;                      // [H][128]      linear1.weight^T
+  float* W1n = W1t + H * HEAD_HID;        // [128][H]      linear1.weight
+  float* W2t = W1n + HEAD_HID * H;        // [128][OP]     linear2.weight^T (zero padded)
+  float* W2n = W2t + HEAD_HID * OP;       // [O][128]      linear2.weight
+  float* A0 = W2n + O * HEAD_HID;         // [64][LDA]     relu(hid)
+  float* A1 = A0 + TMH * LDA;             // [64][LD1]     a1
+  float* D1 = A1 + TMH * LD1;             // [64][LD1]     d a1
+  float* Do = D1 + TMH * LD1;             // [64][LDO]     d out
+  float* W2acc = Do + TMH * LDO;          // [O][128]      dW2 accumulator
+  __shared__ float red[32];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  for (int i = tid; i < HEAD_HID * H; i += 256) {
+    const int m = i / H, k = i % H;
+    const float v = __ldg(a.w1 + i);
+    W1n[i] = v;
+    W1t[k * HEAD_HID + m] = v;
+  }
+  for (int i = tid; i < HEAD_HID * OP; i += 256) {
+    const int m = i / OP, o = i % OP;
+    W2t[i] = o < O ? __ldg(a.w2 + (size_t)o * HEAD_HID + m) : 0.f;
+  }
+  for (int i = tid; i < O * HEAD_HID; i += 256) {
+    W2n[i] = __ldg(a.w2 + i);
+    W2acc[i] = 0.f;
+  }
+  float dw1[8][HJ];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < HJ; ++j) dw1[i][j] = 0.f;
+  float dbias = 0.f, lsum = 0.f;
+  const float scale = 1.0f / ((float)a.N * (float)O);
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long q0 = (long long)tile * TMH;
+    // relu(hid) tile
+    for (int i = tid; i < TMH * (H / 4); i += 256) {
+      const int rl = i / (H / 4), c4 = i % (H / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + rl < a.BN) v = __ldg(reinterpret_cast<const float4*>(a.hid + (q0 + rl) * H) + c4);
+      float* d = A0 + rl * LDA + c4 * 4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;   // pre-activation kept: sign needed for d hid
+    }
+    __syncthreads();
+    // a1 = relu(relu(hid) W1^T + b1)
+    for (int n0 = 0; n0 < HEAD_HID; n0 += TN) {
+      float acc[4][4];
+      zero_acc(acc);
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(W1t + k * HEAD_HID + n0 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float av = fmaxf(A0[(ty * 4 + i) * LDA + k], 0.f);
+          acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
+          acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + tx * 4 + j;
+          A1[(ty * 4 + i) * LD1 + n] = fmaxf(acc[i][j] + __ldg(a.b1 + n), 0.f);
+        }
+    }
+    __syncthreads();
+    // out = a1 W2^T + b2 ; loss ; d_out
+    for (int n0 = 0; n0 < OP; n0 += TN) {
+      float acc[4][4];
+      zero_acc(acc);
+      if (n0 + tx * 4 < OP) {
+#pragma unroll 4
+        for (int k = 0; k < HEAD_HID; ++k) {
+          const float4 b = *reinterpret_cast<const float4*>(W2t + k * OP + n0 + tx * 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float av = A1[(ty * 4 + i) * LD1 + k];
+            acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
+            acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = ty * 4 + i;
+        const long long q = q0 + rl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + tx * 4 + j;
+          if (n >= OP) continue;
+          float dv = 0.f;
+          if (n < O && q < a.BN) {
+            const float v = acc[i][j] + __ldg(a.b2 + n);
+            a.out[q * O + n] = v;
+            const float diff = v - __ldg(a.y + q * O + n);
+            lsum = fmaf(diff, diff, lsum);
+            dv = 2.0f * diff * scale;
+            a.d_out[q * O + n] = dv;
+          }
+          Do[rl * LDO + n] = dv;
+        }
+      }
+    }
+    __syncthreads();
+    // d a1 = (d_out W2) * (a1 > 0)
+    for (int n0 = 0; n0 < HEAD_HID; n0 += TN) {
+      float acc[4][4];
+      zero_acc(acc);
+      for (int k = 0; k < O; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(W2n + k * HEAD_HID + n0 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float av = Do[(ty * 4 + i) * LDO + k];
+          acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
+          acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = (ty * 4 + i) * LD1 + n0 + tx * 4 + j;
+          D1[idx] = A1[idx] > 0.f ? acc[i][j] : 0.f;
+        }
+    }
+    __syncthreads();
+    // G = (d a1 W1) * (hid > 0) (+ d_hidden)
+    for (int n0 = 0; n0 < H; n0 += TN) {
+      float acc[4][4];
+      zero_acc(acc);
+      if (n0 + tx * 4 >= H) continue;   // H < 64: the upper thread columns have no output
+#pragma unroll 4
+      for (int k = 0; k < HEAD_HID; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(W1n + k * H + n0 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float av = D1[(ty * 4 + i) * LD1 + k];
+          acc[i][0] = fmaf(av, b.x, acc[i][0]); acc[i][1] = fmaf(av, b.y, acc[i][1]);
+          acc[i][2] = fmaf(av, b.z, acc[i][2]); acc[i][3] = fmaf(av, b.w, acc[i][3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = ty * 4 + i;
+        const long long q = q0 + rl;
+        if (q >= a.BN) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + tx * 4 + j;
+          v[j] = A0[rl * LDA + n] > 0.f ? acc[i][j] : 0.f;
+          if (a.d_hidden) v[j] += a.d_hidden[q * H + n];
+        }
+        *reinterpret_cast<float4*>(a.G + q * H + n0 + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    // weight gradients of this tile: dW1 += d a1^T relu(hid) (registers), dW2 += d_out^T a1 (smem), biases
+    {
+      const int m0 = (tid >> 4) * 8, j0 = (tid & 15) * HJ;
+      for (int rl = 0; rl < TMH; ++rl) {
+        float d[8], av[HJ];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = D1[rl * LD1 + m0 + i];
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) av[j] = fmaxf(A0[rl * LDA + j0 + j], 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) dw1[i][j] = fmaf(d[i], av[j], dw1[i][j]);
+      }
+      for (int i = tid; i < O * HEAD_HID; i += 256) {
+        const int o = i / HEAD_HID, m = i % HEAD_HID;
+        float sacc = 0.f;
+        for (int rl = 0; rl < TMH; ++rl) sacc = fmaf(Do[rl * LDO + o], A1[rl * LD1 + m], sacc);
+        W2acc[i] += sacc;
+      }
+      if (tid < HEAD_HID) {
+        for (int rl = 0; rl < TMH; ++rl) dbias += D1[rl * LD1 + tid];
+      } else if (tid - HEAD_HID < O) {
+        for (int rl = 0; rl < TMH; ++rl) dbias += Do[rl * LDO + tid - HEAD_HID];
+      }
+    }
+    __syncthreads();
+  }
+  // per-CTA partials: dW1 | dW2 | db1 | db2 | loss
+  float* hp = hpart + (size_t)blockIdx.x * head_part_stride(H, O);
+  {
+    const int m0 = (tid >> 4) * 8, j0 = (tid & 15) * HJ;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < HJ; ++j) hp[(m0 + i) * H + j0 + j] = dw1[i][j];
+  }
+  for (int i = tid; i < O * HEAD_HID; i += 256) hp[HEAD_HID * H + i] = W2acc[i];
+  if (tid < HEAD_HID) hp[HEAD_HID * H + O * HEAD_HID + tid] = dbias;
+  else if (tid - HEAD_HID < O) hp[HEAD_HID * H + O * HEAD_HID + HEAD_HID + tid - HEAD_HID] = dbias;
+  lsum = block_sum(lsum, red);
+  if (tid == 0) hp[HEAD_HID * H + O * HEAD_HID + HEAD_HID + O] = lsum * scale;
+}
+
+__global__ void k_head_loss_reduce(const float* __restrict__ hpart, int stride, int off, int ncta, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += hpart[(size_t)c * stride + off];
+    *loss = s;
+  }
+}
+__global__ void k_head_grad_reduce(const float* __restrict__ hpart, int stride, int ncta, int H, int O, int acc,
+                                   float* __restrict__ gw1, float* __restrict__ gw2, float* __restrict__ gb1,
+                                   float* __restrict__ gb2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n1 = HEAD_HID * H, n2 = O * HEAD_HID;
+  if (i >= n1 + n2 + HEAD_HID + O) return;
+  float s = 0.f;
+  for (int c = 0; c < ncta; ++c) s += hpart[(size_t)c * stride + i];
+  float* dst;
+  int j = i;
+  if (j < n1) dst = gw1;
+  else if ((j -= n1) < n2) dst = gw2;
+  else if ((j -= n2) < HEAD_HID) dst = gb1;
+  else { j -= HEAD_HID; dst = gb2; }
+  if (dst) dst[j] = acc ? dst[j] + s : s;
+}
+
+bool head_fusable(const regt_args* a) {
+  return a->fuse_head && a->y && a->d_out && a->loss && (a->H == 64 || a->H == 32) && a->O <= 64;
+}
+static int head_fused_grid(const regt_args* a) {
+  const long long BN = (long long)a->B * a->N;
+  return (int)min((long long)HP_MAX_CTAS, (BN + TMH - 1) / TMH);
+}
+
 static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* W2t) {
   HeadK k{};
   k.BN = (long long)a->B * a->N;
@@ -166,6 +413,24 @@ static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* 
 
 int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, O = a->O;
+  if (head_fusable(a)) {
+    HeadK k = make_headk(a, L, nullptr, nullptr);
+    const int grid = head_fused_grid(a), ntiles = cdiv(k.BN, TMH), OP = (O + 3) & ~3;
+    const size_t smem = ((size_t)2 * HEAD_HID * H + HEAD_HID * OP + 2 * O * HEAD_HID + TMH * (H + 4) +
+                         2 * TMH * (HEAD_HID + 4) + TMH * (OP + 4)) * sizeof(float);
+    if (H == 64) {
+      REGT_CUDA(cudaFuncSetAttribute(k_head_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_head_fused<64><<<grid, 256, smem, st>>>(k, L.hpart, ntiles);
+    } else {
+      REGT_CUDA(cudaFuncSetAttribute(k_head_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_head_fused<32><<<grid, 256, smem, st>>>(k, L.hpart, ntiles);
+    }
+    REGT_LAUNCHED("k_head_fused", st);
+    const int stride = head_part_stride(H, O);
+    k_head_loss_reduce<<<1, 32, 0, st>>>(L.hpart, stride, stride - 4, grid, a->loss);
+    REGT_LAUNCHED("k_head_loss_reduce", st);
+    return 0;
+  }
   // transposed head weights live at the tail of the split-K scratch's first page
   float* W1t = L.part + L.part_floats - ((size_t)H * HEAD_HID + (size_t)HEAD_HID * O);
   float* W2t = W1t + (size_t)H * HEAD_HID;
@@ -188,6 +453,13 @@ int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
 int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, O = a->O;
   const long long BN = (long long)a->B * a->N;
+  if (head_fusable(a)) {  // everything but the cross-CTA sum already happened in head_forward
+    const int stride = head_part_stride(H, O), n = HEAD_HID * H + O * HEAD_HID + HEAD_HID + O;
+    k_head_grad_reduce<<<cdiv(n, 256), 256, 0, st>>>(L.hpart, stride, head_fused_grid(a), H, O, a->accumulate,
+                                                     a->g.head_w1, a->g.head_w2, a->g.head_b1, a->g.head_b2);
+    REGT_LAUNCHED("k_head_grad_reduce", st);
+    return 0;
+  }
   if (!a->d_out) {  // only out_hidden carries gradient
     k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H);
     REGT_LAUNCHED("k_copy_or_zero", st);

@@ -35,6 +35,7 @@ class Params(C.Structure):
 class Args(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("O", C.c_int32),
                 ("mode", C.c_int32), ("precision", C.c_int32), ("accumulate", C.c_int32),
+                ("fuse_head", C.c_int32), ("_reserved", C.c_int32),
                 ("plan", GraphPlan),
                 ("x", vp), ("y", vp), ("h_ext", vp),
                 ("p", Params), ("g", Params),

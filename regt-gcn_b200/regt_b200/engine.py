@@ -75,7 +75,7 @@ def _stream() -> int:
 def build_state(mode: int, precision: int, plan: GraphPlanTensors, x: torch.Tensor, H: int, O: int,
                 params: Dict[str, torch.Tensor], y: Optional[torch.Tensor] = None,
                 h_ext: Optional[torch.Tensor] = None, head: bool = True,
-                workspace: Optional[torch.Tensor] = None) -> StepState:
+                workspace: Optional[torch.Tensor] = None, fuse_head: bool = False) -> StepState:
     """x [B,N,F,T] float32 CUDA.  Allocates outputs + workspace and fills ``regt_args``."""
     lib = _lib.load()
     dev = x.device
@@ -89,6 +89,7 @@ def build_state(mode: int, precision: int, plan: GraphPlanTensors, x: torch.Tens
     a = st.args
     a.B, a.N, a.T, a.H, a.O = B, N, T, H, O
     a.mode, a.precision, a.accumulate = mode, precision, 0
+    a.fuse_head = 1 if (fuse_head and head and y is not None) else 0
     a.plan = plan.c_struct()
     a.x = x.data_ptr()
     for k in keys_for(mode, head):

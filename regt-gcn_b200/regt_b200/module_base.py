@@ -108,7 +108,7 @@ class RegTModelBase(nn.Module):
         outs, hids = [], []
         for b0 in range(0, B, mb):
             st = engine.build_state(self._mode, self._prec(), plan, xb[b0:b0 + mb], self._hidden, self.output_dim,
-                                    params, yb[b0:b0 + mb], None, True, getattr(self, "_ws", None))
+                                    params, yb[b0:b0 + mb], None, True, getattr(self, "_ws", None), fuse_head=True)
             self._ws = st.workspace
             engine.run_forward(st, True)
             engine.run_backward(st, grads, st.d_out, None, True, True)
