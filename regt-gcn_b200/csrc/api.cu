@@ -52,7 +52,7 @@ Layout make_layout(const regt_args* a, void* base) {
     L.tc_dpp = c.take<float>(T * nqt + 64);
   }
   L.a1 = c.take<float>(BN * HEAD_HID);
-  L.G = c.take<float>(BN * H);
+  L.G = c.take<float>(((BN + 127) / 128) * 128 * H);   // padded: the tensor-core backward reads whole 128-row tiles
   L.d_a1 = c.take<float>(BN * HEAD_HID);
   L.dB = c.take<float>(3 * H * H);
   L.dP = c.take<float>(3 * H * F);

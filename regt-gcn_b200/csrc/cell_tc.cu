@@ -21,11 +21,29 @@ using namespace tc;
 constexpr int F = REGT_F;
 constexpr int CW = 32;                    // columns owned by one epilogue thread
 constexpr int NEPI_WARPS = 4 * (64 / CW);  // 4 lane quarters x column groups (hidden = 64)
-constexpr int NEPI = NEPI_WARPS * 32;      // epilogue threads; the next warp issues the MMAs
-constexpr int NTHREADS = NEPI + 32;
+constexpr int NEPI = NEPI_WARPS * 32;      // epilogue threads
+constexpr int WARP_MMA = NEPI_WARPS;       // issues every tcgen05.mma (one elected lane) + bulk prefetches
+constexpr int WARP_LOAD = NEPI_WARPS + 1;  // builds the F-wide operand tile of the NEXT period (off the critical path)
+constexpr int NTHREADS = NEPI + 64;
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float fast_tanh(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+// Gate nonlinearities.  tf32x3 (fp32-parity) mode: exp + reciprocal (2 MUFU each, ~1e-7 relative).
+// bf16 mode: the single-MUFU tanh.approx.f32 (max relative error 2^-11, below the bf16 operand
+// rounding of 2^-9), sigmoid(v) = 0.5 tanh(v/2) + 0.5 -- the kernel is MUFU-bound otherwise.
+template <int FMT>
+__device__ __forceinline__ float fast_tanh(float v) {
+  if constexpr (FMT == FMT_BF16) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+  } else {
+    return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v));
+  }
+}
+template <int FMT>
+__device__ __forceinline__ float fast_sigmoid(float v) {
+  if constexpr (FMT == FMT_BF16) return fmaf(0.5f, fast_tanh<FMT>(0.5f * v), 0.5f);
+  else return __fdividef(1.0f, 1.0f + __expf(-v));
+}
 __device__ __forceinline__ uint32_t tf32_rn_bits(float a) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
@@ -375,23 +393,61 @@ __device__ __forceinline__ void issue_h_mma(uint32_t tmem_d, uint32_t sm_xu, int
   }
 }
 
-#define REGT_TS(i) \
-  if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 24) a.dbg[dbg_n * 8 + (i)] = clock64();
+#define REGT_TS(i)                                                  \
+  if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 24) {         \
+    a.dbg[dbg_n * 10 + (i)] = clock64();                             \
+    a.dbg[dbg_n * 10 + 9] = 0x5245475444424721ll;                    \
+  }
 
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+// step s of a CTA -> (item, period): items blockIdx.x, +gridDim.x, ... ; tp periods per item
+struct StepIt {
+  int item, t, ti;
+  __device__ __forceinline__ void set(const TcArgs& a, int s) {
+    const int k = s / a.tp;
+    ti = s - k * a.tp;
+    item = blockIdx.x + k * gridDim.x;
+    t = (item % a.ntc) * a.tp + ti;
+  }
+};
+__device__ __forceinline__ int cta_steps(const TcArgs& a) {
+  const int n_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  return n_items * a.tp;
+}
+__device__ __forceinline__ bool ri_valid(const TcArgs& a, int item, int r) {
+  return (long long)(item / a.ntc) * TC_ROWS + r < a.BN;
+}
+struct RowInfo {
+  long long q;
+  int b, s0, s1;
+  bool valid;
+  __device__ __forceinline__ void set(const TcArgs& a, int item, int r, bool need_seg) {
+    q = (long long)(item / a.ntc) * TC_ROWS + r;
+    valid = q < a.BN;
+    b = valid ? (int)(q / a.N) : 0;
+    s0 = s1 = 0;
+    if (valid && need_seg) {
+      const int n = (int)(q - (long long)b * a.N);
+      s0 = a.seg_ptr[n];
+      s1 = a.seg_ptr[n + 1];
+    }
+  }
+};
+
 template <int FMT, int HH>
 __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   using Cfg = TcCfg<FMT, HH>;
   constexpr int NBUF = Cfg::PIPE ? 2 : 1;
+  constexpr int SMB = Cfg::NSPLIT * Cfg::SMF_TILE;     // bytes per small-tile buffer
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic only (an integer round trip would make
   // every later access a generic LD/ST instead of LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* W = smem;                                   // weight image (tiles + consts)
   uint8_t* Ah = W + ((Cfg::FWD_IMG + 1023) & ~1023);   // [NSPLIT][128 x HH]
-  uint8_t* SMf = Ah + Cfg::NSPLIT * Cfg::A_TILE;       // [NBUF][NSPLIT] small tiles
+  uint8_t* SMf = Ah + Cfg::NSPLIT * Cfg::A_TILE;       // [NBUF] small tiles  S(+pad) | X | U
   __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c, bar_img, bar_x, bar_h;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -402,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
     mbar_init(&bar_a2, NEPI);
     mbar_init(&bar_c, 1);
     mbar_init(&bar_img, 1);
-    mbar_init(&bar_x, NEPI);
+    mbar_init(&bar_x, 1);
     mbar_init(&bar_h, 1);
     fence_barrier_init();
     // weight image -> shared memory with the bulk-copy engine (16 KB pieces)
@@ -410,206 +466,178 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
     for (int o = 0; o < Cfg::FWD_IMG; o += 16384)
       bulk_g2s(W + o, a.img + o, min(16384, Cfg::FWD_IMG - o), &bar_img);
   }
-  if (warp == NEPI_WARPS) tmem_alloc(&tmem_base_s, 256);
+  if (warp == WARP_MMA) tmem_alloc(&tmem_base_s, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   mbar_wait(&bar_img, 0);
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(W + Cfg::FWD_W);
-  uint32_t ph = 0;
-  int dbg_n = 0;
   const bool hmma = a.hmma != 0;
+  const int S = cta_steps(a);
+  int dbg_n = 0;
 
   if (warp < NEPI_WARPS) {
-    // ================= epilogue / prologue threads =================
+    // ================= epilogue threads: thread = (row r, CW columns) =================
     const int r = (warp & 3) * 32 + lane;  // row = TMEM lane
     const int ch = warp >> 2;              // column group
     const int c0 = ch * CW;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      const int qt = item / a.ntc, tc_i = item % a.ntc;
-      const long long q = (long long)qt * TC_ROWS + r;
-      const bool valid = q < a.BN;
-      const int b = valid ? (int)(q / a.N) : 0, n = valid ? (int)(q % a.N) : 0;
-      int s0 = 0, s1 = 0;
-      if (valid) {
-        s0 = a.seg_ptr[n];
-        s1 = a.seg_ptr[n + 1];
-      }
-      const int t_begin = tc_i * a.tp, t_end = t_begin + a.tp;
-      int buf = 0;
-      if (hmma) {  // first period of the item: features -> small tile -> h_pre MMA
-        if (ch == 0) {
-          float sv[8], xv[8], uv[8];
-          load_feats(a, valid, q, b, s0, s1, t_begin, sv, xv, uv);
-          write_small_fwd<FMT, HH>(SMf, r, sv, xv, uv);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bar_x);
-      }
-      float acc[CW];
+    RowInfo ri;
+    float acc[CW];
+    StepIt it;
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      it.set(a, s);
+      const int qt = it.item / a.ntc;
+      if (it.ti == 0) {
+        ri.set(a, it.item, r, !hmma);
 #pragma unroll
-      for (int j = 0; j < CW; ++j) acc[j] = 0.f;
-      for (int t = t_begin; t < t_end; ++t) {
-        const bool last = (t + 1 == t_end);
-        uint8_t* sm_cur = SMf + buf * Cfg::NSPLIT * Cfg::SMF_TILE;
-        float h[CW];
-        REGT_TS(0)
-        if (hmma) {
-          mbar_wait(&bar_h, ph);
-          tc_fence_after();
-          tmem_ld<CW>(tlane + 3 * HH + c0, h);
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
-            h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
-          }
-        } else {
-          float sv[8];
-          compute_h<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
-          if (ch == 0) {
-            store_small8<FMT, HH>(sm_cur, Cfg::SMF_TILE, r, 0, sv);
-            if constexpr (FMT == FMT_BF16) *reinterpret_cast<uint4*>(sm_cur + chunk_off(r, 1, TC_ROWS)) = make_uint4(0, 0, 0, 0);
-          }
-        }
-        REGT_TS(1)
-        store_operand<FMT, HH>(Ah, r, c0, h);
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bar_a);
-        if (hmma && Cfg::PIPE && !last && ch == 0) {  // next period's features while the gate MMA runs
-          float sv[8], xv[8], uv[8];
-          load_feats(a, valid, q, b, s0, s1, t + 1, sv, xv, uv);
-          write_small_fwd<FMT, HH>(SMf + (buf ^ 1) * Cfg::NSPLIT * Cfg::SMF_TILE, r, sv, xv, uv);
-        }
-
-        // ---- E1: gates ----
-        REGT_TS(2)
-        mbar_wait(&bar_zr, ph);
+        for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+      }
+      float h[CW];
+      REGT_TS(0)
+      if (hmma) {
+        mbar_wait(&bar_h, ph);
         tc_fence_after();
-        REGT_TS(3)
-        float z[CW];
-        {
-          float raw[CW];
-          tmem_ld<CW>(tlane + c0, raw);
+        tmem_ld<CW>(tlane + 3 * HH + c0, h);
 #pragma unroll
-          for (int j = 0; j < CW; ++j) z[j] = fast_sigmoid(raw[j] + consts[Cfg::C_CZR + c0 + j]);
-          PlaneIO<FMT, HH>::store(a.Zp, a.nqt, t, qt, r, c0, z);
-          tmem_ld<CW>(tlane + HH + c0, raw);
-          float hr[CW];
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float rg = fast_sigmoid(raw[j] + consts[Cfg::C_CZR + HH + c0 + j]);
-            raw[j] = rg;
-            hr[j] = h[j] * rg;
-          }
-          PlaneIO<FMT, HH>::store(a.Rp, a.nqt, t, qt, r, c0, raw);
-          store_operand<FMT, HH>(Ah, r, c0, hr);
+        for (int j = 0; j < CW; ++j) {
+          const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
+          h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
         }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bar_a2);
-
-        // ---- E2: candidate, blend, attention accumulation ----
-        REGT_TS(4)
-        mbar_wait(&bar_c, ph);
-        tc_fence_after();
-        REGT_TS(5)
-        {
-          float raw[CW];
-          tmem_ld<CW>(tlane + 2 * HH + c0, raw);
-          const float pt = consts[Cfg::C_PROBS + t];
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float hc = fast_tanh(raw[j] + consts[Cfg::C_CC + c0 + j]);
-            raw[j] = hc;
-            acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
-          }
-          PlaneIO<FMT, HH>::store(a.Hcp, a.nqt, t, qt, r, c0, raw);
-        }
-        if (hmma && !Cfg::PIPE && !last) {  // single-buffered small tile: refill after the candidate MMA is done
-          if (ch == 0) {
-            float sv[8], xv[8], uv[8];
-            load_feats(a, valid, q, b, s0, s1, t + 1, sv, xv, uv);
-            write_small_fwd<FMT, HH>(SMf, r, sv, xv, uv);
-          }
-          fence_proxy_async();
-          tc_fence_before();
-          mbar_arrive(&bar_x);
-        }
-        REGT_TS(6)
-        ++dbg_n;
-        ph ^= 1;
-        if (Cfg::PIPE) buf ^= 1;
+      } else {
+        float sv[8];
+        compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, it.t, c0, h, sv);
       }
-      if (valid) {
-        float* o = a.hid_part + ((size_t)tc_i * a.BN + q) * HH + c0;
+      REGT_TS(1)
+      store_operand<FMT, HH>(Ah, r, c0, h);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar_a);
+
+      // ---- E1: gates ----
+      REGT_TS(2)
+      mbar_wait(&bar_zr, ph);
+      tc_fence_after();
+      REGT_TS(3)
+      float z[CW];
+      {
+        float raw[CW];
+        tmem_ld<CW>(tlane + c0, raw);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) z[j] = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + c0 + j]);
+        PlaneIO<FMT, HH>::store(a.Zp, a.nqt, it.t, qt, r, c0, z);
+        tmem_ld<CW>(tlane + HH + c0, raw);
+        float hr[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const float rg = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + HH + c0 + j]);
+          raw[j] = rg;
+          hr[j] = h[j] * rg;
+        }
+        PlaneIO<FMT, HH>::store(a.Rp, a.nqt, it.t, qt, r, c0, raw);
+        store_operand<FMT, HH>(Ah, r, c0, hr);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar_a2);
+
+      // ---- E2: candidate, blend, attention accumulation ----
+      REGT_TS(4)
+      mbar_wait(&bar_c, ph);
+      tc_fence_after();
+      REGT_TS(5)
+      {
+        float raw[CW];
+        tmem_ld<CW>(tlane + 2 * HH + c0, raw);
+        const float pt = consts[Cfg::C_PROBS + it.t];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const float hc = fast_tanh<FMT>(raw[j] + consts[Cfg::C_CC + c0 + j]);
+          raw[j] = hc;
+          acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
+        }
+        PlaneIO<FMT, HH>::store(a.Hcp, a.nqt, it.t, qt, r, c0, raw);
+      }
+      if (it.ti + 1 == a.tp && ri_valid(a, it.item, r)) {
+        const long long q = (long long)qt * TC_ROWS + r;
+        float* o = a.hid_part + ((size_t)(it.item % a.ntc) * a.BN + q) * HH + c0;
 #pragma unroll
         for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
+      REGT_TS(6)
+      ++dbg_n;
     }
     tc_fence_before();
-  } else {
-    // ================= MMA issuer (one elected lane of the last warp) =================
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer (one elected lane) =================
     const uint32_t idesc_zr = make_idesc(FMT, 128, 2 * HH, 0, 0), idesc_c = make_idesc(FMT, 128, HH, 0, 0);
     const uint32_t ah = smem_u32(Ah), smf = smem_u32(SMf), w = smem_u32(W);
-    constexpr int SMB = Cfg::NSPLIT * Cfg::SMF_TILE;                 // bytes per small-tile buffer
     constexpr int XU = Cfg::SMF_XU_CHUNK * TC_ROWS * 16;             // offset of the X | U chunks
-    uint32_t phx = 0;
-    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      int buf = 0;
-      if (hmma) {
-        mbar_wait(&bar_x, phx);
-        phx ^= 1;
+    if (S > 0) {  // the loader has built step 0's tile: h_pre of step 0
+      mbar_wait(&bar_x, 0);
+      tc_fence_after();
+      if (lane == 0 && hmma) {
+        issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
+        umma_commit(&bar_h);
+      }
+      __syncwarp();
+    }
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      const uint32_t as = smf + (s % NBUF) * SMB;
+      mbar_wait(&bar_a, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_gate_mma<FMT, HH>(tmem, ah, as, w, w + Cfg::WZR_H, 2 * HH, idesc_zr);
+        umma_commit(&bar_zr);
+      }
+      __syncwarp();
+      mbar_wait(&bar_a2, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_gate_mma<FMT, HH>(tmem + 2 * HH, ah, as, w + Cfg::WZR_H + Cfg::WZR_S,
+                                w + Cfg::WZR_H + Cfg::WZR_S + Cfg::WC_H, HH, idesc_c);
+        umma_commit(&bar_c);
+      }
+      __syncwarp();
+      if (s + 1 < S) {  // next period's small tile (built by the loader warp) -> its h_pre
+        mbar_wait(&bar_x, (s + 1) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
+        if (lane == 0 && hmma) {
+          issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + ((s + 1) % NBUF) * SMB + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
           umma_commit(&bar_h);
         }
         __syncwarp();
       }
-      for (int ti = 0; ti < a.tp; ++ti) {
-        const bool last = (ti + 1 == a.tp);
-        const uint32_t as = smf + buf * SMB;
-        mbar_wait(&bar_a, ph);
-        tc_fence_after();
-        if (lane == 0) {
-          issue_gate_mma<FMT, HH>(tmem, ah, as, w, w + Cfg::WZR_H, 2 * HH, idesc_zr);
-          umma_commit(&bar_zr);
-        }
-        __syncwarp();
-        mbar_wait(&bar_a2, ph);
-        tc_fence_after();
-        if (lane == 0) {
-          issue_gate_mma<FMT, HH>(tmem + 2 * HH, ah, as, w + Cfg::WZR_H + Cfg::WZR_S,
-                                  w + Cfg::WZR_H + Cfg::WZR_S + Cfg::WC_H, HH, idesc_c);
-          umma_commit(&bar_c);
-          if (hmma && Cfg::PIPE && !last) {  // next period's h_pre, off the critical path
-            issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + (buf ^ 1) * SMB + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
-            umma_commit(&bar_h);
-          }
-        }
-        __syncwarp();
-        if (hmma && !Cfg::PIPE && !last) {
-          mbar_wait(&bar_x, phx);
-          phx ^= 1;
-          tc_fence_after();
-          if (lane == 0) {
-            issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
-            umma_commit(&bar_h);
-          }
-          __syncwarp();
-        }
-        ph ^= 1;
-        if (Cfg::PIPE) buf ^= 1;
-      }
     }
     tc_fence_before();
+  } else {
+    // ================= loader warp: S(+pad) | X | U of the next period, 4 rows per lane =================
+    RowInfo ri[4];
+    StepIt it;
+    for (int s = 0; s < S; ++s) {
+      it.set(a, s);
+      if (it.ti == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ri[k].set(a, it.item, lane + 32 * k, true);
+      }
+      float sv[4][8], xv[4][8], uv[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load_feats(a, ri[k].valid, ri[k].q, ri[k].b, ri[k].s0, ri[k].s1, it.t, sv[k], xv[k], uv[k]);
+      // buffer s % NBUF was last read by the MMAs of step s - NBUF (gate MMAs complete at bar_c)
+      if (s >= NBUF) mbar_wait(&bar_c, (uint32_t)((s - NBUF) & 1));
+      uint8_t* sm = SMf + (s % NBUF) * SMB;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) write_small_fwd<FMT, HH>(sm, lane + 32 * k, sv[k], xv[k], uv[k]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_x);
+    }
   }
   __syncthreads();
-  if (warp == NEPI_WARPS) tmem_dealloc(tmem, 256);
+  if (warp == WARP_MMA) tmem_dealloc(tmem, 256);
 }
 
 // out_hidden[q][j] = sum over the t-chunks of the per-item partial attention sums
@@ -659,6 +687,12 @@ static int choose_tp(int nqt, int T, int slots) {
   return best;
 }
 
+bool head_fusable(const regt_args* a);
+int tc_num_chunks(const regt_args* a) {
+  const int BN = a->B * a->N, nqt = (BN + TC_ROWS - 1) / TC_ROWS;
+  return a->T / choose_tp(nqt, a->T, num_sms());
+}
+
 static TcArgs make_tcargs(const regt_args* a, const Layout& L, int slots) {
   TcArgs k{};
   k.BN = a->B * a->N; k.N = a->N; k.T = a->T; k.nseg = a->plan.nseg; k.mode = a->mode;
@@ -673,7 +707,7 @@ static TcArgs make_tcargs(const regt_args* a, const Layout& L, int slots) {
   k.img = L.tc_img_f;
   k.Zp = L.Zp; k.Rp = L.Rp; k.Hcp = L.Hcp; k.hid_part = L.hid_part;
   k.G = L.G; k.dhp = L.dhp_p; k.wpart = L.tc_wpart; k.dprobs_part = L.tc_dpp;
-  k.dbg = getenv("REGT_TC_DEBUG") ? reinterpret_cast<long long*>(L.tc_wpart) : nullptr;  // scratch reuse (debug only)
+  k.dbg = getenv("REGT_TC_DEBUG") ? reinterpret_cast<long long*>(L.part) : nullptr;  // scratch reuse (debug only)
   return k;
 }
 
@@ -694,9 +728,11 @@ static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int grid = min(slots, k.items);
   k_cell_fwd_tc<FMT, HH><<<grid, NTHREADS, smem, st>>>(k);
   REGT_LAUNCHED("k_cell_fwd_tc", st);
-  const long long count = (long long)k.BN * HH;
-  k_hid_reduce<<<cdiv(count / 4, 256), 256, 0, st>>>(L.hid_part, k.ntc, count, a->out_hidden);
-  REGT_LAUNCHED("k_hid_reduce", st);
+  if (!head_fusable(a)) {  // otherwise the fused head sums the partials while loading its tiles
+    const long long count = (long long)k.BN * HH;
+    k_hid_reduce<<<cdiv(count / 4, 256), 256, 0, st>>>(L.hid_part, k.ntc, count, a->out_hidden);
+    REGT_LAUNCHED("k_hid_reduce", st);
+  }
   return 0;
 }
 
@@ -737,6 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   constexpr int TILE = Cfg::A_TILE;          // 16 KB
   constexpr int PT = PIO::TILE_BYTES;        // 16 KB
   constexpr int SMT = 4 * TC_ROWS * 16;      // small tile: S | X | U | ones
+  constexpr int GT = TC_ROWS * HH * 4;       // G tile (fp32, [HH/4][128][4])
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* W = smem;                                     // Bt_z | Bt_r | Bt_h | B0 | consts
@@ -748,8 +785,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   uint8_t* T_HR = T_H + TILE;
   uint8_t* SM = T_HR + TILE;                             // [2] small tiles (double-buffered)
   uint8_t* STG = SM + 2 * SMT;                           // staged Z | R | H~ tiles
-  float* GS = reinterpret_cast<float*>(STG + 3 * PT);    // G tile [HH/4][128][4] fp32
-  __shared__ uint64_t bar_stage, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w, bar_img, bar_x, bar_h;
+  uint8_t* GS = STG + 3 * PT;                            // G tile of the current item
+  __shared__ uint64_t bar_stage, bar_g, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w, bar_img, bar_x, bar_h;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[2][NEPI_WARPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -757,187 +794,156 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   if (tid == 0) {
     mbar_init(&bar_img, 1);
     mbar_init(&bar_stage, 1);
+    mbar_init(&bar_g, 1);
     mbar_init(&bar_e0, NEPI);
     mbar_init(&bar_m1, 1);
     mbar_init(&bar_e1, NEPI);
     mbar_init(&bar_m2, 1);
     mbar_init(&bar_e2, NEPI);
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_x, NEPI);
+    mbar_init(&bar_x, 1);
     mbar_init(&bar_h, 1);
     fence_barrier_init();
     mbar_arrive_expect_tx(&bar_img, Cfg::BWD_IMG);
     for (int o = 0; o < Cfg::BWD_IMG; o += 16384)
       bulk_g2s(W + o, a.img + o, min(16384, Cfg::BWD_IMG - o), &bar_img);
   }
-  if (warp == NEPI_WARPS) tmem_alloc(&tmem_base_s, 512);
+  if (warp == WARP_MMA) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   mbar_wait(&bar_img, 0);
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(W + Cfg::BWD_W);
-  uint32_t ph = 0;
-  int gstep = 0;
   const bool hmma = a.hmma != 0;
-
-  auto write_small_bwd = [&](uint8_t* sm, int r, const float (&sv)[8], const float (&xv)[8], const float (&uv)[8]) {
-    store_small8<FMT, HH>(sm, 0, r, 0, sv);
-    store_small8<FMT, HH>(sm, 0, r, 8, xv);
-    store_small8<FMT, HH>(sm, 0, r, 16, uv);
-    *reinterpret_cast<uint4*>(sm + chunk_off(r, 3, TC_ROWS)) = make_uint4(0x00003F80u, 0, 0, 0);  // bf16 1.0
-  };
+  const int S = cta_steps(a);
+  int dbg_n = 0;
 
   if (warp < NEPI_WARPS) {
     const int r = (warp & 3) * 32 + lane;
     const int ch = warp >> 2;
     const int c0 = ch * CW;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      const int qt = item / a.ntc, tc_i = item % a.ntc;
-      const long long q = (long long)qt * TC_ROWS + r;
-      const bool valid = q < a.BN;
-      const int b = valid ? (int)(q / a.N) : 0, n = valid ? (int)(q % a.N) : 0;
-      int s0 = 0, s1 = 0;
-      if (valid) {
-        s0 = a.seg_ptr[n];
-        s1 = a.seg_ptr[n + 1];
+    RowInfo ri;
+    StepIt it;
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      it.set(a, s);
+      const int qt = it.item / a.ntc;
+      float h[CW], dh[CW], rr[CW];
+      REGT_TS(0)
+      if (it.ti == 0) {
+        ri.set(a, it.item, r, !hmma);
+        mbar_wait(&bar_g, (uint32_t)((s / a.tp) & 1));   // this item's G tile has landed in smem
       }
-      const int t_begin = tc_i * a.tp, t_end = t_begin + a.tp;
-      // ---- item prologue: first period's small tile (+ h_pre MMA) and the G tile into smem ----
-      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // previous item's readers of GS are done
-      {
-        const long long q_base = (long long)qt * TC_ROWS;
-        for (int i = tid; i < TC_ROWS * HH / 4; i += NEPI) {     // coalesced float4 reads of the row-major tile
-          const int row = i / (HH / 4), c4 = i % (HH / 4);
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q_base + row < a.BN) g = __ldg(reinterpret_cast<const float4*>(a.G + (q_base + row) * HH) + c4);
-          reinterpret_cast<float4*>(GS)[c4 * TC_ROWS + row] = g;
+      if (hmma) {
+        mbar_wait(&bar_h, ph);
+        tc_fence_after();
+        tmem_ld<CW>(tlane + 320 + c0, h);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
+          h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
         }
+      } else {
+        float sv[8];
+        compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, it.t, c0, h, sv);
       }
-      int buf = 0;
-      if (ch == 0) {
-        float sv[8], xv[8], uv[8];
-        load_feats(a, valid, q, b, s0, s1, t_begin, sv, xv, uv);
-        if (gstep > 0) mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));  // W2s of the previous step read SM[0/1]
-        write_small_bwd(SM, r, sv, xv, uv);
+      const float pt = consts[Cfg::C_PROBS + it.t];
+      float dp = 0.f;
+      REGT_TS(1)
+      mbar_wait(&bar_stage, ph);
+      {
+        float z[CW], hc[CW];
+        PIO::load(STG, r, c0, z);
+        PIO::load(STG + PT, r, c0, rr);
+        PIO::load(STG + 2 * PT, r, c0, hc);
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);   // rows past B*N: the padded part of G is never written
+          if (ri.valid) g4 = reinterpret_cast<const float4*>(GS)[((c0 + j) / 4) * TC_ROWS + r];
+          const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = j + e;
+            const float zz = z[jj], hcc = hc[jj], hv = h[jj];
+            dp = fmaf(gv[e], zz * hv + (1.0f - zz) * hcc, dp);
+            const float gs = pt * gv[e];
+            dh[jj] = gs * zz;
+            z[jj] = gs * (hv - hcc) * zz * (1.0f - zz);          // Dz
+            hc[jj] = gs * (1.0f - zz) * (1.0f - hcc * hcc);      // Dh
+          }
+        }
+        if (s > 0) mbar_wait(&bar_w, (uint32_t)((s - 1) & 1));  // previous step's MMAs released the tiles
+        store_operand<FMT, HH>(T_DZ, r, c0, z);
+        store_operand<FMT, HH>(T_DH, r, c0, hc);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) z[j] = h[j] * rr[j];
+        store_operand<FMT, HH>(T_HR, r, c0, z);
+        store_operand<FMT, HH>(T_H, r, c0, h);
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_x);
-      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // GS visible to all epilogue threads
+      mbar_arrive(&bar_e0);
+      REGT_TS(2)
 
-      for (int t = t_begin; t < t_end; ++t) {
-        const bool last = (t + 1 == t_end);
-        float h[CW], dh[CW], rr[CW];
-        if (hmma) {
-          mbar_wait(&bar_h, ph);
-          tc_fence_after();
-          tmem_ld<CW>(tlane + 320 + c0, h);
+      // ---- E1 ----
+      mbar_wait(&bar_m1, ph);
+      tc_fence_after();
+      REGT_TS(3)
+      {
+        float raw[CW];
+        tmem_ld<CW>(tlane + c0, raw);
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
-            h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
-          }
-        } else {
-          float sv[8];
-          compute_h<HH>(a, consts, valid, q, b, s0, s1, t, c0, h, sv);
+        for (int j = 0; j < CW; ++j) {
+          const float dHR = raw[j];
+          dh[j] = fmaf(dHR, rr[j], dh[j]);
+          raw[j] = dHR * h[j] * rr[j] * (1.0f - rr[j]);   // Dr
         }
-        const float pt = consts[Cfg::C_PROBS + t];
-        float dp = 0.f;
-        mbar_wait(&bar_stage, ph);
-        {
-          float z[CW], hc[CW];
-          PIO::load(STG, r, c0, z);
-          PIO::load(STG + PT, r, c0, rr);
-          PIO::load(STG + 2 * PT, r, c0, hc);
-#pragma unroll
-          for (int j = 0; j < CW; j += 4) {
-            const float4 g4 = reinterpret_cast<const float4*>(GS)[((c0 + j) / 4) * TC_ROWS + r];
-            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int jj = j + e;
-              const float zz = z[jj], hcc = hc[jj], hv = h[jj];
-              dp = fmaf(gv[e], zz * hv + (1.0f - zz) * hcc, dp);
-              const float gs = pt * gv[e];
-              dh[jj] = gs * zz;
-              z[jj] = gs * (hv - hcc) * zz * (1.0f - zz);          // Dz
-              hc[jj] = gs * (1.0f - zz) * (1.0f - hcc * hcc);      // Dh
-            }
-          }
-          if (gstep > 0) mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));  // previous step's MMAs released the tiles
-          store_operand<FMT, HH>(T_DZ, r, c0, z);
-          store_operand<FMT, HH>(T_DH, r, c0, hc);
-#pragma unroll
-          for (int j = 0; j < CW; ++j) z[j] = h[j] * rr[j];
-          store_operand<FMT, HH>(T_HR, r, c0, z);
-          store_operand<FMT, HH>(T_H, r, c0, h);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bar_e0);
-        if (!last && ch == 0) {  // next period's small tile while M1 runs (other buffer)
-          float sv[8], xv[8], uv[8];
-          load_feats(a, valid, q, b, s0, s1, t + 1, sv, xv, uv);
-          write_small_bwd(SM + (buf ^ 1) * SMT, r, sv, xv, uv);
-        }
-
-        // ---- E1 ----
-        mbar_wait(&bar_m1, ph);
-        tc_fence_after();
-        {
-          float raw[CW];
-          tmem_ld<CW>(tlane + c0, raw);
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float dHR = raw[j];
-            dh[j] = fmaf(dHR, rr[j], dh[j]);
-            raw[j] = dHR * h[j] * rr[j] * (1.0f - rr[j]);   // Dr
-          }
-          store_operand<FMT, HH>(T_DR, r, c0, raw);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bar_e1);
-
-        // ---- E2 ----
-        mbar_wait(&bar_m2, ph);
-        tc_fence_after();
-        {
-          float raw[CW];
-          tmem_ld<CW>(tlane + 64 + c0, raw);
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            float v = dh[j] + raw[j];
-            if (a.mode == REGT_MODE_REGIONAL) v *= (h[j] > 0.f ? 1.0f : 0.01f);
-            raw[j] = v;
-          }
-          store_operand<FMT, HH>(T_DHP, r, c0, raw);
-          if (a.mode == REGT_MODE_REGIONAL && !hmma) PlaneIO<FMT_TF32, HH>::store(a.dhp, a.nqt, t, qt, r, c0, raw);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bar_e2);
-
-        // ---- attention gradient partial: fixed-order block reduction ----
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) dp += __shfl_down_sync(0xffffffffu, dp, d);
-        if (lane == 0) red[gstep & 1][warp] = dp;
-        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
-        if (tid == 0) {
-          float sacc = 0.f;
-#pragma unroll
-          for (int w8 = 0; w8 < NEPI_WARPS; ++w8) sacc += red[gstep & 1][w8];
-          a.dprobs_part[(size_t)qt * a.T + t] = sacc;
-        }
-        ph ^= 1;
-        buf ^= 1;
-        ++gstep;
+        store_operand<FMT, HH>(T_DR, r, c0, raw);
       }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar_e1);
+      REGT_TS(4)
+
+      // ---- E2 ----
+      mbar_wait(&bar_m2, ph);
+      tc_fence_after();
+      REGT_TS(5)
+      {
+        float raw[CW];
+        tmem_ld<CW>(tlane + 64 + c0, raw);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          float v = dh[j] + raw[j];
+          if (a.mode == REGT_MODE_REGIONAL) v *= (h[j] > 0.f ? 1.0f : 0.01f);
+          raw[j] = v;
+        }
+        store_operand<FMT, HH>(T_DHP, r, c0, raw);
+        if (a.mode == REGT_MODE_REGIONAL && !hmma) PlaneIO<FMT_TF32, HH>::store(a.dhp, a.nqt, it.t, qt, r, c0, raw);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar_e2);
+      REGT_TS(6)
+
+      // ---- attention gradient partial: fixed-order block reduction ----
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) dp += __shfl_down_sync(0xffffffffu, dp, d);
+      if (lane == 0) red[s & 1][warp] = dp;
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+      if (tid == 0) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < NEPI_WARPS; ++w8) sacc += red[s & 1][w8];
+        a.dprobs_part[(size_t)qt * a.T + it.t] = sacc;
+      }
+      REGT_TS(7)
+      ++dbg_n;
     }
     // ---- flush the persistent weight-gradient accumulators ----
-    mbar_wait(&bar_w, (uint32_t)((gstep - 1) & 1));
+    mbar_wait(&bar_w, (uint32_t)((S - 1) & 1));
     tc_fence_after();
     float* wp = a.wpart + ((size_t)blockIdx.x * TC_ROWS + r) * WP_COLS;
     {
@@ -958,115 +964,170 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       for (int j = 0; j < SW; j += 4) *reinterpret_cast<float4*>(wp + 160 + ch * SW + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
     }
     tc_fence_before();
-  } else {
-    // ================= MMA issuer + plane prefetch (one elected lane of the last warp) =================
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer + bulk prefetch of the saved planes / G tile =================
     const uint32_t id_dg = make_idesc(FMT, 128, HH, 0, 0);        // data gradients (K-major)
     const uint32_t id_w = make_idesc(FMT, 128, HH, 1, 1);         // weight gradients (MN-major)
     const uint32_t id_ws = make_idesc(FMT, 128, 32, 1, 1);
     const uint32_t w = smem_u32(W), tdh = smem_u32(T_DH), tdz = smem_u32(T_DZ), tdr = smem_u32(T_DR), th = smem_u32(T_H),
                    thr = smem_u32(T_HR), sm0 = smem_u32(SM);
     constexpr int XU = 1 * TC_ROWS * 16;  // X | U are chunks 1,2 of the small tile
-    uint32_t phx = 0;
-    auto prefetch = [&](int item, int t) {
-      const int qt = item / a.ntc;
+    auto prefetch = [&](const StepIt& n) {
+      const int qt = n.item / a.ntc;
       mbar_arrive_expect_tx(&bar_stage, 3 * PT);
-      bulk_g2s(STG, PIO::tile(a.Zp, a.nqt, t, qt), PT, &bar_stage);
-      bulk_g2s(STG + PT, PIO::tile(a.Rp, a.nqt, t, qt), PT, &bar_stage);
-      bulk_g2s(STG + 2 * PT, PIO::tile(a.Hcp, a.nqt, t, qt), PT, &bar_stage);
+      bulk_g2s(STG, PIO::tile(a.Zp, a.nqt, n.t, qt), PT, &bar_stage);
+      bulk_g2s(STG + PT, PIO::tile(a.Rp, a.nqt, n.t, qt), PT, &bar_stage);
+      bulk_g2s(STG + 2 * PT, PIO::tile(a.Hcp, a.nqt, n.t, qt), PT, &bar_stage);
     };
-    if (lane == 0 && blockIdx.x < a.items) prefetch(blockIdx.x, (blockIdx.x % a.ntc) * a.tp);
-    for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-      const int tc_i = item % a.ntc;
-      int buf = 0;
-      mbar_wait(&bar_x, phx);
-      phx ^= 1;
+    auto fetch_g = [&](int item) {
+      mbar_arrive_expect_tx(&bar_g, GT);
+      bulk_g2s(GS, reinterpret_cast<const uint8_t*>(a.G) + (size_t)(item / a.ntc) * GT, GT, &bar_g);
+    };
+    StepIt it, nx;
+    if (S > 0) {
+      it.set(a, 0);
+      if (lane == 0) {
+        prefetch(it);
+        fetch_g(it.item);
+      }
+      mbar_wait(&bar_x, 0);
       tc_fence_after();
       if (lane == 0 && hmma) {
         issue_h_mma<FMT, HH>(tmem + 320, sm0 + XU, 0, w + 3 * Cfg::BT, 0);
         umma_commit(&bar_h);
       }
       __syncwarp();
-      for (int ti = 0; ti < a.tp; ++ti) {
-        const bool last = (ti + 1 == a.tp);
-        const uint32_t accw = gstep > 0 ? 1u : 0u;
-        const uint32_t sm = sm0 + buf * SMT;
-        mbar_wait(&bar_e0, ph);
-        tc_fence_after();
-        if (lane == 0) {
-          // the staged planes of this step are consumed: fetch the next step's
-          int nitem = item, nt = tc_i * a.tp + ti + 1;
-          if (last) {
-            nitem = item + gridDim.x;
-            nt = (nitem % a.ntc) * a.tp;
-          }
-          if (nitem < a.items) prefetch(nitem, nt);
-          // M1: dHR = Dh . B_h
-#pragma unroll
-          for (int s = 0; s < HH / 16; ++s)
-            umma<FMT>(tmem, make_desc(tdh + s * 32, 16, 1024, LAYOUT_SW128),
-                      make_desc(w + 2 * Cfg::BT + s * 32, 16, 1024, LAYOUT_SW128), id_dg, s > 0 ? 1u : 0u);
-          umma_commit(&bar_m1);
+    }
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      const uint32_t accw = s > 0 ? 1u : 0u;
+      const uint32_t sm = sm0 + (s & 1) * SMT;
+      it.set(a, s);
+      const bool more = s + 1 < S;
+      if (more) nx.set(a, s + 1);
+      mbar_wait(&bar_e0, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        // this step's staged planes (and, on its last period, the item's G tile) are consumed
+        if (more) {
+          prefetch(nx);
+          if (nx.ti == 0) fetch_g(nx.item);
         }
-        __syncwarp();
-        mbar_wait(&bar_e1, ph);
-        tc_fence_after();
-        if (lane == 0) {
-          // M2: dhg = Dz . B_z + Dr . B_r
+        // M1: dHR = Dh . B_h
 #pragma unroll
-          for (int s = 0; s < HH / 16; ++s)
-            umma<FMT>(tmem + 64, make_desc(tdz + s * 32, 16, 1024, LAYOUT_SW128),
-                      make_desc(w + s * 32, 16, 1024, LAYOUT_SW128), id_dg, s > 0 ? 1u : 0u);
-#pragma unroll
-          for (int s = 0; s < HH / 16; ++s)
-            umma<FMT>(tmem + 64, make_desc(tdr + s * 32, 16, 1024, LAYOUT_SW128),
-                      make_desc(w + Cfg::BT + s * 32, 16, 1024, LAYOUT_SW128), id_dg, 1u);
-          umma_commit(&bar_m2);
-          if (hmma && !last) {  // next period's h_pre (the other small-tile buffer was filled before bar_e1)
-            issue_h_mma<FMT, HH>(tmem + 320, sm0 + (buf ^ 1) * SMT + XU, 0, w + 3 * Cfg::BT, 0);
-            umma_commit(&bar_h);
-          }
-          // W1 / W1s: [Dz|Dr]^T . h , [Dz|Dr]^T . [S|X|U|1]   (contraction over the 128 rows)
-#pragma unroll
-          for (int s = 0; s < TC_ROWS / 16; ++s) {
-            const uint64_t da = make_desc(tdz + s * 2048, TILE, 1024, LAYOUT_SW128);
-            umma<FMT>(tmem + 128, da, make_desc(th + s * 2048, TILE, 1024, LAYOUT_SW128), id_w, (s > 0) ? 1u : accw);
-            umma<FMT>(tmem + 192, da, make_desc(sm + s * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (s > 0) ? 1u : accw);
-          }
-        }
-        __syncwarp();
-        mbar_wait(&bar_e2, ph);
-        tc_fence_after();
-        if (lane == 0) {
-          // W2 / W2s: [Dh|dhp]^T . (h*R) , [Dh|dhp]^T . [S|X|U|1]
-#pragma unroll
-          for (int s = 0; s < TC_ROWS / 16; ++s) {
-            const uint64_t da = make_desc(tdh + s * 2048, TILE, 1024, LAYOUT_SW128);
-            umma<FMT>(tmem + 224, da, make_desc(thr + s * 2048, TILE, 1024, LAYOUT_SW128), id_w, (s > 0) ? 1u : accw);
-            umma<FMT>(tmem + 288, da, make_desc(sm + s * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (s > 0) ? 1u : accw);
-          }
-          umma_commit(&bar_w);
-        }
-        __syncwarp();
-        ph ^= 1;
-        buf ^= 1;
-        ++gstep;
+        for (int k = 0; k < HH / 16; ++k)
+          umma<FMT>(tmem, make_desc(tdh + k * 32, 16, 1024, LAYOUT_SW128),
+                    make_desc(w + 2 * Cfg::BT + k * 32, 16, 1024, LAYOUT_SW128), id_dg, k > 0 ? 1u : 0u);
+        umma_commit(&bar_m1);
       }
+      __syncwarp();
+      mbar_wait(&bar_e1, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        // M2: dhg = Dz . B_z + Dr . B_r
+#pragma unroll
+        for (int k = 0; k < HH / 16; ++k)
+          umma<FMT>(tmem + 64, make_desc(tdz + k * 32, 16, 1024, LAYOUT_SW128),
+                    make_desc(w + k * 32, 16, 1024, LAYOUT_SW128), id_dg, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HH / 16; ++k)
+          umma<FMT>(tmem + 64, make_desc(tdr + k * 32, 16, 1024, LAYOUT_SW128),
+                    make_desc(w + Cfg::BT + k * 32, 16, 1024, LAYOUT_SW128), id_dg, 1u);
+        umma_commit(&bar_m2);
+      }
+      __syncwarp();
+      if (more) {  // next period's h_pre from the tile the loader warp has built
+        mbar_wait(&bar_x, (uint32_t)((s + 1) & 1));
+        tc_fence_after();
+        if (lane == 0 && hmma) {
+          issue_h_mma<FMT, HH>(tmem + 320, sm0 + ((s + 1) & 1) * SMT + XU, 0, w + 3 * Cfg::BT, 0);
+          umma_commit(&bar_h);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        // W1 / W1s: [Dz|Dr]^T . h , [Dz|Dr]^T . [S|X|U|1]   (contraction over the 128 rows)
+#pragma unroll
+        for (int k = 0; k < TC_ROWS / 16; ++k) {
+          const uint64_t da = make_desc(tdz + k * 2048, TILE, 1024, LAYOUT_SW128);
+          umma<FMT>(tmem + 128, da, make_desc(th + k * 2048, TILE, 1024, LAYOUT_SW128), id_w, (k > 0) ? 1u : accw);
+          umma<FMT>(tmem + 192, da, make_desc(sm + k * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (k > 0) ? 1u : accw);
+        }
+      }
+      __syncwarp();
+      mbar_wait(&bar_e2, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        // W2 / W2s: [Dh|dhp]^T . (h*R) , [Dh|dhp]^T . [S|X|U|1]
+#pragma unroll
+        for (int k = 0; k < TC_ROWS / 16; ++k) {
+          const uint64_t da = make_desc(tdh + k * 2048, TILE, 1024, LAYOUT_SW128);
+          umma<FMT>(tmem + 224, da, make_desc(thr + k * 2048, TILE, 1024, LAYOUT_SW128), id_w, (k > 0) ? 1u : accw);
+          umma<FMT>(tmem + 288, da, make_desc(sm + k * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (k > 0) ? 1u : accw);
+        }
+        umma_commit(&bar_w);
+      }
+      __syncwarp();
     }
     tc_fence_before();
+  } else {
+    // ================= loader warp: S | X | U | 1 of the next period, 4 rows per lane =================
+    RowInfo ri[4];
+    StepIt it;
+    for (int s = 0; s < S; ++s) {
+      it.set(a, s);
+      if (it.ti == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ri[k].set(a, it.item, lane + 32 * k, true);
+      }
+      float sv[4][8], xv[4][8], uv[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load_feats(a, ri[k].valid, ri[k].q, ri[k].b, ri[k].s0, ri[k].s1, it.t, sv[k], xv[k], uv[k]);
+      if (s >= 2) mbar_wait(&bar_w, (uint32_t)((s - 2) & 1));   // W1s / W2s of step s-2 were the last readers
+      uint8_t* sm = SM + (s & 1) * SMT;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = lane + 32 * k;
+        store_small8<FMT, HH>(sm, 0, row, 0, sv[k]);
+        store_small8<FMT, HH>(sm, 0, row, 8, xv[k]);
+        store_small8<FMT, HH>(sm, 0, row, 16, uv[k]);
+        *reinterpret_cast<uint4*>(sm + chunk_off(row, 3, TC_ROWS)) = make_uint4(0x00003F80u, 0, 0, 0);  // bf16 1.0
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_x);
+    }
   }
   __syncthreads();
-  if (warp == NEPI_WARPS) tmem_dealloc(tmem, 512);
+  if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
 }
 
 // sum the per-CTA partials and scatter them into the collapsed-weight gradient buffers
 __global__ void k_tc_wreduce(const float* __restrict__ wpart, int ncta, int HH, int R, float* __restrict__ dB,
                              float* __restrict__ dP, float* __restrict__ dcg, float* __restrict__ dM0,
-                             float* __restrict__ dM1, float* __restrict__ dc0) {
+                             float* __restrict__ dM1, float* __restrict__ dc0, const float* __restrict__ dpp, int nqt,
+                             int T, float* __restrict__ dprobs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= TC_ROWS * WP_COLS) return;
+  if (i >= TC_ROWS * WP_COLS) {
+    const int t = i - TC_ROWS * WP_COLS;   // attention-gradient partials: dprobs[t] = sum_qt dpp[qt][t]
+    if (t < T) {
+      float sp = 0.f;
+      for (int q = 0; q < nqt; ++q) sp += dpp[(size_t)q * T + t];
+      dprobs[t] = sp;
+    }
+    return;
+  }
   const int m = i / WP_COLS, c = i % WP_COLS;
-  float s = 0.f;
-  for (int k = 0; k < ncta; ++k) s += wpart[(size_t)k * TC_ROWS * WP_COLS + i];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= ncta; k += 4) {
+    s0 += wpart[(size_t)k * TC_ROWS * WP_COLS + i];
+    s1 += wpart[(size_t)(k + 1) * TC_ROWS * WP_COLS + i];
+    s2 += wpart[(size_t)(k + 2) * TC_ROWS * WP_COLS + i];
+    s3 += wpart[(size_t)(k + 3) * TC_ROWS * WP_COLS + i];
+  }
+  for (; k < ncta; ++k) s0 += wpart[(size_t)k * TC_ROWS * WP_COLS + i];
+  const float s = (s0 + s1) + (s2 + s3);
   const int g = m / HH, n = m % HH;
   if (c < 64) {
     dB[((size_t)g * HH + n) * HH + c] = s;                     // dB_z / dB_r
@@ -1141,9 +1202,9 @@ int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   k_cell_bwd_tc<HH><<<grid, NTHREADS, smem, st>>>(k);
   REGT_LAUNCHED("k_cell_bwd_tc", st);
   const int R = a->plan.R;
-  k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS, 256), 256, 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1, L.dc0);
+  k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS + a->T, 256), 256, 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1,
+                                                                     L.dc0, L.tc_dpp, k.nqt, a->T, L.dprobs);
   REGT_LAUNCHED("k_tc_wreduce", st);
-  if (launch_reduce_splits(L.tc_dpp, L.dprobs, a->T, k.nqt, 0, st)) return -1;
   if (a->mode == REGT_MODE_REGIONAL && R > 1) {
     const int zs = (int)max(1ll, min(64ll, 1024ll / R));
     k_wgrad_m1_tc<HH><<<dim3(R, 1, zs), HH, 0, st>>>(L.dhp_p, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,

@@ -15,7 +15,14 @@ struct HeadK {
   const float *w1, *w2;                        // natural layouts for the data gradients
   const float* d_hidden;
   float *a1, *out, *d_out, *loss_part, *d_a1, *G;
+  const float* hid_part;  // tensor-core cell: [ntc][BN][H] partial attention sums (NULL: hid is final)
+  int ntc;
+  float* hid_out;         // where the summed out_hidden goes when hid_part is used
+  int g_tiled;            // 1: G is written as [qt][H/4][128][4] tiles (tensor-core backward), 0: row-major
 };
+__device__ __forceinline__ size_t g_off(long long q, int n, int H, int tiled) {
+  return tiled ? ((((size_t)(q >> 7) * (H >> 2) + (n >> 2)) * 128 + (size_t)(q & 127)) * 4 + (n & 3)) : ((size_t)q * H + n);
+}
 
 __global__ void k_head_transpose(const float* __restrict__ w1, const float* __restrict__ w2, int H, int O,
                                  float* __restrict__ W1t, float* __restrict__ W2t) {
@@ -142,16 +149,16 @@ __global__ void __launch_bounds__(TMH * 4) k_head_bwd(HeadK a) {
         if (n >= H) continue;
         float v = a.hid[q * H + n] > 0.f ? acc[i][j] : 0.f;
         if (a.d_hidden) v += a.d_hidden[q * H + n];
-        a.G[q * H + n] = v;
+        a.G[g_off(q, n, H, a.g_tiled)] = v;
       }
     }
   }
 }
 
 // gradient flowing only through out_hidden (no head gradient): G = d_hidden or 0
-__global__ void k_copy_or_zero(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+__global__ void k_copy_or_zero(const float* __restrict__ src, float* __restrict__ dst, long long n, int H, int tiled) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src ? src[i] : 0.f;
+  if (i < n) dst[g_off(i / H, (int)(i % H), H, tiled)] = src ? src[i] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -207,7 +214,17 @@ __global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restric
     for (int i = tid; i < TMH * (H / 4); i += 256) {
       const int rl = i / (H / 4), c4 = i % (H / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q0 + rl < a.BN) v = __ldg(reinterpret_cast<const float4*>(a.hid + (q0 + rl) * H) + c4);
+      if (q0 + rl < a.BN) {
+        if (a.hid_part) {  // sum the per-chunk attention partials of the tensor-core cell (fixed order)
+          for (int c = 0; c < a.ntc; ++c) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(a.hid_part + ((size_t)c * a.BN + q0 + rl) * H) + c4);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+          }
+          reinterpret_cast<float4*>(a.hid_out + (q0 + rl) * H)[c4] = v;
+        } else {
+          v = __ldg(reinterpret_cast<const float4*>(a.hid + (q0 + rl) * H) + c4);
+        }
+      }
       float* d = A0 + rl * LDA + c4 * 4;
       d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;   // pre-activation kept: sign needed for d hid
     }
@@ -322,7 +339,7 @@ __global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restric
           v[j] = A0[rl * LDA + n] > 0.f ? acc[i][j] : 0.f;
           if (a.d_hidden) v[j] += a.d_hidden[q * H + n];
         }
-        *reinterpret_cast<float4*>(a.G + q * H + n0 + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(a.G + g_off(q, n0 + tx * 4, H, a.g_tiled)) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
     // weight gradients of this tile: dW1 += d a1^T relu(hid) (registers), dW2 += d_out^T a1 (smem), biases
@@ -369,21 +386,27 @@ __global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restric
   if (tid == 0) hp[HEAD_HID * H + O * HEAD_HID + HEAD_HID + O] = lsum * scale;
 }
 
-__global__ void k_head_loss_reduce(const float* __restrict__ hpart, int stride, int off, int ncta, float* __restrict__ loss) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += hpart[(size_t)c * stride + off];
-    *loss = s;
-  }
-}
+// sums the per-CTA partials into the head gradients; thread 0 of block 0 also finalises the loss
 __global__ void k_head_grad_reduce(const float* __restrict__ hpart, int stride, int ncta, int H, int O, int acc,
                                    float* __restrict__ gw1, float* __restrict__ gw2, float* __restrict__ gb1,
-                                   float* __restrict__ gb2) {
+                                   float* __restrict__ gb2, float* __restrict__ loss) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n1 = HEAD_HID * H, n2 = O * HEAD_HID;
-  if (i >= n1 + n2 + HEAD_HID + O) return;
-  float s = 0.f;
-  for (int c = 0; c < ncta; ++c) s += hpart[(size_t)c * stride + i];
+  const int n1 = HEAD_HID * H, n2 = O * HEAD_HID, ntot = n1 + n2 + HEAD_HID + O;
+  if (i > ntot) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= ncta; c += 4) {
+    s0 += hpart[(size_t)c * stride + i];
+    s1 += hpart[(size_t)(c + 1) * stride + i];
+    s2 += hpart[(size_t)(c + 2) * stride + i];
+    s3 += hpart[(size_t)(c + 3) * stride + i];
+  }
+  for (; c < ncta; ++c) s0 += hpart[(size_t)c * stride + i];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (i == ntot) {  // the loss slot follows the gradients
+    if (loss) *loss = s;
+    return;
+  }
   float* dst;
   int j = i;
   if (j < n1) dst = gw1;
@@ -401,6 +424,8 @@ static int head_fused_grid(const regt_args* a) {
   return (int)min((long long)HP_MAX_CTAS, (BN + TMH - 1) / TMH);
 }
 
+bool head_fusable(const regt_args* a);
+int tc_num_chunks(const regt_args* a);
 static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* W2t) {
   HeadK k{};
   k.BN = (long long)a->B * a->N;
@@ -408,6 +433,12 @@ static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* 
   k.hid = a->out_hidden; k.y = a->y; k.W1t = W1t; k.W2t = W2t; k.b1 = a->p.head_b1; k.b2 = a->p.head_b2;
   k.w1 = a->p.head_w1; k.w2 = a->p.head_w2; k.d_hidden = a->d_hidden;
   k.a1 = L.a1; k.out = a->out; k.d_out = a->d_out; k.loss_part = L.part; k.d_a1 = L.d_a1; k.G = L.G;
+  k.hid_part = nullptr; k.ntc = 0; k.hid_out = a->out_hidden;
+  k.g_tiled = a->precision != REGT_PREC_FP32;
+  if (a->precision != REGT_PREC_FP32 && head_fusable(a)) {  // the cell left per-chunk partials (see cell_tc.cu)
+    k.hid_part = L.hid_part;
+    k.ntc = tc_num_chunks(a);
+  }
   return k;
 }
 
@@ -426,10 +457,7 @@ int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
       k_head_fused<32><<<grid, 256, smem, st>>>(k, L.hpart, ntiles);
     }
     REGT_LAUNCHED("k_head_fused", st);
-    const int stride = head_part_stride(H, O);
-    k_head_loss_reduce<<<1, 32, 0, st>>>(L.hpart, stride, stride - 4, grid, a->loss);
-    REGT_LAUNCHED("k_head_loss_reduce", st);
-    return 0;
+    return 0;   // loss and head gradients are finalised by k_head_grad_reduce in regt_head_backward
   }
   // transposed head weights live at the tail of the split-K scratch's first page
   float* W1t = L.part + L.part_floats - ((size_t)H * HEAD_HID + (size_t)HEAD_HID * O);
@@ -455,13 +483,13 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const long long BN = (long long)a->B * a->N;
   if (head_fusable(a)) {  // everything but the cross-CTA sum already happened in head_forward
     const int stride = head_part_stride(H, O), n = HEAD_HID * H + O * HEAD_HID + HEAD_HID + O;
-    k_head_grad_reduce<<<cdiv(n, 256), 256, 0, st>>>(L.hpart, stride, head_fused_grid(a), H, O, a->accumulate,
-                                                     a->g.head_w1, a->g.head_w2, a->g.head_b1, a->g.head_b2);
+    k_head_grad_reduce<<<cdiv(n + 1, 256), 256, 0, st>>>(L.hpart, stride, head_fused_grid(a), H, O, a->accumulate,
+                                                         a->g.head_w1, a->g.head_w2, a->g.head_b1, a->g.head_b2, a->loss);
     REGT_LAUNCHED("k_head_grad_reduce", st);
     return 0;
   }
   if (!a->d_out) {  // only out_hidden carries gradient
-    k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H);
+    k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H, H, a->precision != REGT_PREC_FP32);
     REGT_LAUNCHED("k_copy_or_zero", st);
     return 0;
   }

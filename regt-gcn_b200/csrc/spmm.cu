@@ -75,18 +75,43 @@ __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_r
   const int* rowptr = is_seg ? seg_eptr : g_rowptr;
   const int* col = is_seg ? c_col : g_col;
   const float* val = is_seg ? c_val : g_val;
-  const int W = REGT_F * T;  // floats per row
-  const float* xb = x + (size_t)b * N * W;
+  const int W = REGT_F * T, W4 = W >> 2;  // floats / float4 per row (W % 4 == 0 since F = 8)
+  const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * N * W4;
   const int e0 = rowptr[r], e1 = rowptr[r + 1];
-  const long long out_row = is_seg ? w : w;          // row index inside a period plane
   const long long plane_rows = is_seg ? BS : BN;
   float* dst = is_seg ? Ut : St;
-  for (int i = lane; i < W; i += 32) {
-    float acc = 0.f;
-    for (int e = e0; e < e1; ++e) acc = fmaf(__ldg(val + e), __ldg(xb + (size_t)__ldg(col + e) * W + i), acc);
-    const int f = i / T, t = i - f * T;
-    dst[((size_t)t * plane_rows + out_row) * REGT_F + f] = acc;
-    if (!is_seg) Xt[((size_t)t * BN + w) * REGT_F + f] = __ldg(xb + (size_t)r * W + i);
+  for (int c = lane; c < W4; c += 32) {   // lane c owns float4 #c of the F*T-wide row (coalesced 128-bit gathers)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {
+      float4 v[4];
+      float wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        wv[u] = __ldg(val + e + u);
+        v[u] = __ldg(xb + (size_t)__ldg(col + e + u) * W4 + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x = fmaf(wv[u], v[u].x, acc.x); acc.y = fmaf(wv[u], v[u].y, acc.y);
+        acc.z = fmaf(wv[u], v[u].z, acc.z); acc.w = fmaf(wv[u], v[u].w, acc.w);
+      }
+    }
+    for (; e < e1; ++e) {
+      const float wv = __ldg(val + e);
+      const float4 v = __ldg(xb + (size_t)__ldg(col + e) * W4 + c);
+      acc.x = fmaf(wv, v.x, acc.x); acc.y = fmaf(wv, v.y, acc.y); acc.z = fmaf(wv, v.z, acc.z); acc.w = fmaf(wv, v.w, acc.w);
+    }
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+    float4 xv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!is_seg) xv4 = __ldg(xb + (size_t)r * W4 + c);
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {   // period-major scatter: (t, row) -> 8 contiguous floats = one 32-byte sector
+      const int i = 4 * c + u, f = i / T, t = i - f * T;
+      dst[((size_t)t * plane_rows + w) * REGT_F + f] = av[u];
+      if (!is_seg) Xt[((size_t)t * BN + w) * REGT_F + f] = xv[u];
+    }
   }
 }
 

@@ -39,11 +39,18 @@ __global__ void k_prep(regt_params p, int H, int R, int T, int mode, const float
     int k = rem / H, j = rem % H;  // j fastest: coalesced writes
     float v;
     if (k < F) {
-      double s = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const float* A = p.lin_w[g] + (size_t)j * 2 * H;
       const float* W = p.conv_w[g];
-      for (int m = 0; m < H; ++m) s += (double)A[m] * (double)W[m * F + k];
-      v = (float)s;
+#pragma unroll 4
+      for (int m = 0; m < H; m += 4) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(A + m));
+        s0 += (double)a4.x * (double)__ldg(W + m * F + k);
+        s1 += (double)a4.y * (double)__ldg(W + (m + 1) * F + k);
+        s2 += (double)a4.z * (double)__ldg(W + (m + 2) * F + k);
+        s3 += (double)a4.w * (double)__ldg(W + (m + 3) * F + k);
+      }
+      v = (float)((s0 + s1) + (s2 + s3));
     } else {
       v = p.lin_w[g][(size_t)j * 2 * H + H + (k - F)];
     }
