@@ -22,6 +22,8 @@ def dump(ncol, names):
     for row in t[:12]:
         if row[9]!=0x5245475444424721: break
         print(" ".join(f"{names[i]}={row[i+1]-row[i]:6d}" for i in range(ncol-1)), "| step=%6d start=%d"%(row[ncol-1]-row[0], row[0]-t[0,0]))
+    e=v[i0+240:i0+243]
+    print("entry->first step", t[0,0]-e[0], " first step->epilogue done", e[1]-t[0,0], " wait others", e[2]-e[1])
 if which=="fwd":
     dump(7,["P","st","wM1","E1","wM2","E2"])
 else:

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "cell_tc.cuh"
+#include "gemm_simt.cuh"
 
 namespace regt {
 using namespace tc;
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c, bar_img, bar_x, bar_h;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[240] = clock64();
 
   if (tid == 0) {
     mbar_init(&bar_a, NEPI);
@@ -636,7 +638,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
       if (lane == 0) mbar_arrive(&bar_x);
     }
   }
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[241] = clock64();
   __syncthreads();
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[242] = clock64();
   if (warp == WARP_MMA) tmem_dealloc(tmem, 256);
 }
 
@@ -790,6 +794,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[2][NEPI_WARPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[240] = clock64();
 
   if (tid == 0) {
     mbar_init(&bar_img, 1);
@@ -1098,36 +1103,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       if (lane == 0) mbar_arrive(&bar_x);
     }
   }
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[241] = clock64();
   __syncthreads();
+  if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[242] = clock64();
   if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
 }
 
 // sum the per-CTA partials and scatter them into the collapsed-weight gradient buffers
-__global__ void k_tc_wreduce(const float* __restrict__ wpart, int ncta, int HH, int R, float* __restrict__ dB,
-                             float* __restrict__ dP, float* __restrict__ dcg, float* __restrict__ dM0,
-                             float* __restrict__ dM1, float* __restrict__ dc0, const float* __restrict__ dpp, int nqt,
-                             int T, float* __restrict__ dprobs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= TC_ROWS * WP_COLS) {
-    const int t = i - TC_ROWS * WP_COLS;   // attention-gradient partials: dprobs[t] = sum_qt dpp[qt][t]
-    if (t < T) {
-      float sp = 0.f;
-      for (int q = 0; q < nqt; ++q) sp += dpp[(size_t)q * T + t];
-      dprobs[t] = sp;
-    }
+__global__ void __launch_bounds__(256) k_tc_wreduce(const float* __restrict__ wpart, int ncta, int HH, int R,
+                                                    float* __restrict__ dB, float* __restrict__ dP,
+                                                    float* __restrict__ dcg, float* __restrict__ dM0,
+                                                    float* __restrict__ dM1, float* __restrict__ dc0,
+                                                    const float* __restrict__ dpp, int nqt, int T,
+                                                    float* __restrict__ dprobs) {
+  __shared__ float red[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  constexpr int NW = TC_ROWS * WP_COLS;
+  // outputs [0, NW): weight-gradient partials of the CTAs; [NW, NW+T): dprobs[t] = sum_qt dpp[qt][t]
+  const bool is_w = i < NW, is_p = !is_w && (i - NW) < T;
+  const float s = sum_parts_32x8(is_w ? wpart : dpp, is_w ? (size_t)NW : (size_t)T, is_w ? ncta : nqt,
+                                 is_w ? i : i - NW, is_w || is_p, red);
+  if (threadIdx.y != 0) return;
+  if (is_p) {
+    dprobs[i - NW] = s;
     return;
   }
+  if (!is_w) return;
   const int m = i / WP_COLS, c = i % WP_COLS;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= ncta; k += 4) {
-    s0 += wpart[(size_t)k * TC_ROWS * WP_COLS + i];
-    s1 += wpart[(size_t)(k + 1) * TC_ROWS * WP_COLS + i];
-    s2 += wpart[(size_t)(k + 2) * TC_ROWS * WP_COLS + i];
-    s3 += wpart[(size_t)(k + 3) * TC_ROWS * WP_COLS + i];
-  }
-  for (; k < ncta; ++k) s0 += wpart[(size_t)k * TC_ROWS * WP_COLS + i];
-  const float s = (s0 + s1) + (s2 + s3);
   const int g = m / HH, n = m % HH;
   if (c < 64) {
     dB[((size_t)g * HH + n) * HH + c] = s;                     // dB_z / dB_r
@@ -1202,7 +1204,7 @@ int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   k_cell_bwd_tc<HH><<<grid, NTHREADS, smem, st>>>(k);
   REGT_LAUNCHED("k_cell_bwd_tc", st);
   const int R = a->plan.R;
-  k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS + a->T, 256), 256, 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1,
+  k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS + a->T, 32), dim3(32, 8), 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1,
                                                                      L.dc0, L.tc_dpp, k.nqt, a->T, L.dprobs);
   REGT_LAUNCHED("k_tc_wreduce", st);
   if (a->mode == REGT_MODE_REGIONAL && R > 1) {

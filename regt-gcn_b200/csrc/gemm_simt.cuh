@@ -74,6 +74,30 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 32 floats *
   return s;
 }
 
+// deterministic sum over per-CTA partials: blockDim = (32 outputs, 8 partial subsets).
+// Thread (x, y) adds partials y, y+8, ... of output i; the 8 subset sums are combined in a fixed
+// order.  Valid result in the threads with threadIdx.y == 0.  All threads of the block must call.
+__device__ __forceinline__ float sum_parts_32x8(const float* __restrict__ part, size_t stride, int nparts, long long i,
+                                                bool in_range, float (*red)[32]) {
+  float s0 = 0.f, s1 = 0.f;
+  if (in_range) {
+    int p = threadIdx.y;
+    for (; p + 8 < nparts; p += 16) {
+      s0 += __ldg(part + (size_t)p * stride + i);
+      s1 += __ldg(part + (size_t)(p + 8) * stride + i);
+    }
+    if (p < nparts) s0 += __ldg(part + (size_t)p * stride + i);
+  }
+  red[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+  }
+  return s;
+}
+
 // ---- split-K "TN" GEMM:  C[m][n] = sum_r A[r*lda + m] * B[r*ldb + n]  (weight gradients) ----
 struct TNProb {
   const float* A;

@@ -386,24 +386,17 @@ __global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restric
   if (tid == 0) hp[HEAD_HID * H + O * HEAD_HID + HEAD_HID + O] = lsum * scale;
 }
 
-// sums the per-CTA partials into the head gradients; thread 0 of block 0 also finalises the loss
-__global__ void k_head_grad_reduce(const float* __restrict__ hpart, int stride, int ncta, int H, int O, int acc,
-                                   float* __restrict__ gw1, float* __restrict__ gw2, float* __restrict__ gb1,
-                                   float* __restrict__ gb2, float* __restrict__ loss) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// sums the per-CTA partials into the head gradients; the slot after the gradients is the loss
+__global__ void __launch_bounds__(256) k_head_grad_reduce(const float* __restrict__ hpart, int stride, int ncta, int H,
+                                                          int O, int acc, float* __restrict__ gw1,
+                                                          float* __restrict__ gw2, float* __restrict__ gb1,
+                                                          float* __restrict__ gb2, float* __restrict__ loss) {
+  __shared__ float red[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
   const int n1 = HEAD_HID * H, n2 = O * HEAD_HID, ntot = n1 + n2 + HEAD_HID + O;
-  if (i > ntot) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int c = 0;
-  for (; c + 4 <= ncta; c += 4) {
-    s0 += hpart[(size_t)c * stride + i];
-    s1 += hpart[(size_t)(c + 1) * stride + i];
-    s2 += hpart[(size_t)(c + 2) * stride + i];
-    s3 += hpart[(size_t)(c + 3) * stride + i];
-  }
-  for (; c < ncta; ++c) s0 += hpart[(size_t)c * stride + i];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (i == ntot) {  // the loss slot follows the gradients
+  const float s = sum_parts_32x8(hpart, stride, ncta, i, i <= ntot, red);
+  if (threadIdx.y != 0 || i > ntot) return;
+  if (i == ntot) {
     if (loss) *loss = s;
     return;
   }
@@ -483,7 +476,7 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const long long BN = (long long)a->B * a->N;
   if (head_fusable(a)) {  // everything but the cross-CTA sum already happened in head_forward
     const int stride = head_part_stride(H, O), n = HEAD_HID * H + O * HEAD_HID + HEAD_HID + O;
-    k_head_grad_reduce<<<cdiv(n + 1, 256), 256, 0, st>>>(L.hpart, stride, head_fused_grid(a), H, O, a->accumulate,
+    k_head_grad_reduce<<<cdiv(n + 1, 32), dim3(32, 8), 0, st>>>(L.hpart, stride, head_fused_grid(a), H, O, a->accumulate,
                                                          a->g.head_w1, a->g.head_w2, a->g.head_b1, a->g.head_b2, a->loss);
     REGT_LAUNCHED("k_head_grad_reduce", st);
     return 0;

@@ -65,10 +65,12 @@ __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_r
                                                  const int32_t* __restrict__ c_col, const float* __restrict__ c_val,
                                                  const float* __restrict__ x, int B, int N, int nseg, int T,
                                                  float* __restrict__ Xt, float* __restrict__ St, float* __restrict__ Ut) {
+  extern __shared__ __align__(16) float feat_stage[];   // [warps per block][2][F*T]
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long BN = (long long)B * N, BS = (long long)B * nseg;
   if (warp >= BN + BS) return;
+  float* stage = feat_stage + (threadIdx.x >> 5) * 2 * REGT_F * T;
   const bool is_seg = warp >= BN;
   const long long w = is_seg ? warp - BN : warp;
   const int b = (int)(w / (is_seg ? nseg : N)), r = (int)(w % (is_seg ? nseg : N));
@@ -102,22 +104,32 @@ __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_r
       const float4 v = __ldg(xb + (size_t)__ldg(col + e) * W4 + c);
       acc.x = fmaf(wv, v.x, acc.x); acc.y = fmaf(wv, v.y, acc.y); acc.z = fmaf(wv, v.z, acc.z); acc.w = fmaf(wv, v.w, acc.w);
     }
-    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
-    float4 xv4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!is_seg) xv4 = __ldg(xb + (size_t)r * W4 + c);
-    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {   // period-major scatter: (t, row) -> 8 contiguous floats = one 32-byte sector
-      const int i = 4 * c + u, f = i / T, t = i - f * T;
-      dst[((size_t)t * plane_rows + w) * REGT_F + f] = av[u];
-      if (!is_seg) Xt[((size_t)t * BN + w) * REGT_F + f] = xv[u];
+    // stage the row in shared memory so that the period-major write is one 32-byte row per lane
+    reinterpret_cast<float4*>(stage)[c] = acc;
+    if (!is_seg) reinterpret_cast<float4*>(stage + W)[c] = __ldg(xb + (size_t)r * W4 + c);
+  }
+  __syncwarp();
+  for (int t = lane; t < T; t += 32) {   // lane t gathers its 8 features (stride T) and writes 2 x float4
+    float4 lo, hi;
+    lo.x = stage[0 * T + t]; lo.y = stage[1 * T + t]; lo.z = stage[2 * T + t]; lo.w = stage[3 * T + t];
+    hi.x = stage[4 * T + t]; hi.y = stage[5 * T + t]; hi.z = stage[6 * T + t]; hi.w = stage[7 * T + t];
+    float4* d = reinterpret_cast<float4*>(dst + ((size_t)t * plane_rows + w) * REGT_F);
+    d[0] = lo;
+    d[1] = hi;
+    if (!is_seg) {
+      const float* sx = stage + W;
+      lo.x = sx[0 * T + t]; lo.y = sx[1 * T + t]; lo.z = sx[2 * T + t]; lo.w = sx[3 * T + t];
+      hi.x = sx[4 * T + t]; hi.y = sx[5 * T + t]; hi.z = sx[6 * T + t]; hi.w = sx[7 * T + t];
+      float4* dx = reinterpret_cast<float4*>(Xt + ((size_t)t * BN + w) * REGT_F);
+      dx[0] = lo;
+      dx[1] = hi;
     }
   }
 }
 
 int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int T, float* Xt, float* St, float* Ut, cudaStream_t st) {
   const long long warps = (long long)B * p.N + (long long)B * p.nseg;
-  k_feat_tc<<<cdiv(warps * 32, 256), 256, 0, st>>>(p.g_rowptr, p.g_col, p.g_val, p.seg_eptr, p.c_col, p.c_val, x, B, p.N,
+  k_feat_tc<<<cdiv(warps * 32, 256), 256, 8 * 2 * REGT_F * T * sizeof(float), st>>>(p.g_rowptr, p.g_col, p.g_val, p.seg_eptr, p.c_col, p.c_val, x, B, p.N,
                                                   p.nseg, T, Xt, St, Ut);
   REGT_LAUNCHED("k_feat_tc", st);
   return 0;
