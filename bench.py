@@ -6,10 +6,13 @@
 
 One "step" = one pass of the hot path (forward + MSE loss + backward, all parameter gradients)
 over one batch of B synthetic snapshots.  Workload at N=1: BASELINE.json configs[1]
-(A3TGCN/TemporalGCN, METR-LA shape: 207 nodes, 12 periods, batch 64, hidden 64).  For N>1 every
-rank runs the same per-GPU batch on its own synthetic snapshots (weak scaling over the batch
-dimension -- the snapshots are independent units) and the shared-weight gradients are
-all-reduced over NCCL inside the step.
+(A3TGCN/TemporalGCN, METR-LA shape: 207 nodes, 12 periods, batch 64, hidden 64).  For N>1:
+  * workloads without regions (config 2): every rank runs the same per-GPU batch on its own
+    synthetic snapshots (weak scaling over the batch dimension -- snapshots are independent units);
+  * regional workloads (--workload 3|4|5): each GPU owns a set of regions (LPT bin packing), reads
+    its rows + 1-hop halo rows of x, and the whole job processes the config's B snapshots (strong
+    scaling, SURVEY 8(e));
+in both cases the shared-weight gradients (+ the loss) are all-reduced over NCCL inside the step.
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset)
 between timed steps, barrier + synchronize on both sides, max over ranks.
@@ -47,6 +50,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch B")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
     ap.add_argument("--micro-batch", type=int, default=None)
+    ap.add_argument("--shard", default="auto", choices=["auto", "region", "batch"],
+                    help="N>1: 'region' = each GPU owns a set of regions (strong scaling, SURVEY 8(e)); "
+                         "'batch' = each GPU runs its own per-GPU batch (weak scaling); auto = region when the workload has regions")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -228,23 +234,34 @@ def main():
     model = model.to(dev)
     graph_args = tuple(None if a is None else a.to(dev) for a in w.graph_args())
 
-    # one flat gradient buffer so that a single NCCL all-reduce covers every shared weight
-    live = [p for n, p in model.named_parameters() if p.requires_grad]
-    offs, tot = [], 0
-    for p in live:
-        offs.append(tot); tot += (p.numel() + 3) // 4 * 4
-    flat = torch.zeros(tot, device=dev)
-    for p, o in zip(live, offs):
-        p.grad = flat[o:o + p.numel()].view_as(p)
+    from regt_b200 import shard as S
+    sharded = world > 1 and w.R > 0 and args.shard != "batch"
+    if args.shard == "region" and world > 1 and w.R == 0:
+        raise SystemExit("--shard region needs a regional workload (3, 4 or 5)")
 
-    # host (pinned) and device-resident inputs; every rank gets its own snapshots
-    xh, yh = w.inputs(B, seed_offset=rank)
+    # host (pinned) and device-resident inputs
+    sm = None
+    if sharded:
+        # region shards: every rank sees every snapshot, owns the nodes of its regions (+ halo rows)
+        sm = S.RegionShardedModel(model, graph_args[0], list(graph_args[1:1 + w.R]), list(graph_args[1 + w.R:]), rank, world)
+        ex = sm.exchange
+        xh, yh = w.inputs(B)
+        xh = xh.index_select(1, torch.from_numpy(sm.shard.perm)).contiguous()   # the rank's loader reads its rows only
+        yh = yh.index_select(1, torch.from_numpy(sm.shard.own)).contiguous()
+    else:
+        # one flat gradient buffer so that a single NCCL all-reduce covers every shared weight
+        ex = S.GradExchange([p for n, p in model.named_parameters() if p.requires_grad], world)
+        xh, yh = w.inputs(B, seed_offset=rank)     # batch shards: every rank gets its own snapshots
     xh, yh = xh.pin_memory(), yh.pin_memory()
     xd, yd = xh.to(dev), yh.to(dev)
     loss_h = torch.zeros(1).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def raw_step():
+        if world > 1:
+            ex.zero()     # per-step exchange: the buffer holds this step's contribution only
+        if sharded:
+            return sm.fused_step(None, None, micro_batch=args.micro_batch, local_inputs=(xd, yd), sync=False)[0]
         return model.fused_step(xd, yd, *graph_args, micro_batch=args.micro_batch)[0]
 
     # warm-up (eager) -- also builds and caches the static-graph plan (K1), excluded from timing
@@ -269,13 +286,15 @@ def main():
         torch.cuda.synchronize()
 
     def step():
+        nonlocal loss_d
         if graph is not None:
             graph.replay()
         else:
-            nonlocal loss_d
             loss_d = raw_step()
         if dist is not None:
-            dist.all_reduce(flat)  # shared-weight gradients, NCCL over NVLink
+            if not sharded:
+                ex.add_loss(loss_d)
+            loss_d = ex.sync()   # the exchange step: shared-weight gradients + loss, one NCCL all-reduce
 
     for _ in range(3):
         step()
@@ -364,17 +383,22 @@ def main():
                "sample": f"{n} snapshots of the same workload in {el:.1f}s (oracle fp32 port, one snapshot at a time)"}
 
     if rank == 0:
+        job_B = B if sharded else world * B     # snapshots the whole job processes per step
         h2d = xh.numel() * 4 + yh.numel() * 4
         out = {
-            "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": job_B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor cores)", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
             "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, l2="flushed between timed steps (256 MiB memset)",
                            cuda_graph=graph is not None, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
-                           parallelism=f"batch-sharded x{world}, NCCL all-reduce of the flat gradient buffer" if world > 1 else "single GPU"),
+                           parallelism=("single GPU" if world == 1 else
+                                        f"region-sharded x{world} (LPT regions->ranks, halo rows of x read locally), NCCL all-reduce of the flat gradient buffer"
+                                        if sharded else
+                                        f"batch-sharded x{world}, NCCL all-reduce of the flat gradient buffer")),
             "clocks": clocks,
-            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "e2e": {"value": job_B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches_per_step * K),
             "launches_per_step": int(launches_per_step),

@@ -95,6 +95,19 @@ int regt_cheb_plan_build(const int64_t* edge_index, const float* edge_weight, co
 int regt_spmm_f8(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
                  int32_t B, int32_t N, int32_t width, regt_stream_t stream);
 
+/* ---- K4: regional gather / scatter of node rows -------------------------------------- */
+/* The reference has no node subsets (a region is an edge list over global ids,
+ * models/RegionalTemporalGCN.py:136-140; the slices of load_dataset.py:458-467 are computed and
+ * discarded); the region-sharded multi-GPU path needs them: a rank's input is its owned rows
+ * followed by the 1-hop halo rows, its outputs are scattered back into global node order.
+ *   gather : dst[b][i][:] = src[b][idx[i]][:]   src [B,n_src,width], dst [B,n_idx,width]
+ *   scatter: dst[b][idx[i]][:] = src[b][i][:]   src [B,n_idx,width], dst [B,n_dst,width]
+ * idx int64 [n_idx] (device), rows of `width` floats.                                     */
+int regt_gather_rows(const float* src, const int64_t* idx, float* dst, int32_t B, int32_t n_src, int32_t n_idx,
+                     int32_t width, regt_stream_t stream);
+int regt_scatter_rows(const float* src, const int64_t* idx, float* dst, int32_t B, int32_t n_idx, int32_t n_dst,
+                      int32_t width, regt_stream_t stream);
+
 /* ---- the cell + head ---------------------------------------------------------------- */
 typedef struct regt_params {            /* reference state_dict layouts      */
   float* attention;                     /* tgnn._attention [T]                             */
@@ -123,10 +136,17 @@ typedef struct regt_args {
   int32_t precision;      /* REGT_PREC_*                                                  */
   int32_t accumulate;     /* backward: 0 overwrite param grads, 1 add into them           */
   int32_t fuse_head;      /* 1 (needs y): head_forward also runs the head's backward (d_out,  */
-  int32_t _reserved;      /*    gradient wrt out_hidden, weight-gradient partials) in the same */
+                          /*    gradient wrt out_hidden, weight-gradient partials) in the same */
                           /*    kernel; head_backward then only reduces the partials           */
+  int32_t x_rows;         /* region shards: node rows per snapshot of x (>= N; 0 means N).     */
+                          /*    Rows [0,N) are the nodes this call owns (outputs are written   */
+                          /*    for them); rows [N,x_rows) are halo inputs that only the plan's */
+                          /*    column indices address (1-hop neighbours owned by other ranks). */
+  int32_t loss_nodes;     /* region shards: node count of the loss mean (0 means N), so that   */
+                          /*    the per-rank losses and gradients ADD to the full-graph ones    */
+  int32_t _reserved;
   regt_graph_plan plan;
-  const float* x;         /* [B,N,F,T] f32, T innermost (load_dataset.py:456)             */
+  const float* x;         /* [B,x_rows,F,T] f32, T innermost (load_dataset.py:456)        */
   const float* y;         /* [B,N,O] or NULL: if set head_forward also writes loss, d_out  */
   const float* h_ext;     /* REGT_MODE_TGCN: [B,N,T,H] state or NULL (= zeros)            */
   regt_params p;          /* parameters                                                   */

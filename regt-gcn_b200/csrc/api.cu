@@ -80,6 +80,7 @@ static int validate(const regt_args* a, const char* who) {
   REGT_CHECK(a->B > 0 && a->N > 0 && a->T > 0 && a->O > 0, "%s: bad dims B=%d N=%d T=%d O=%d", who, a->B, a->N, a->T, a->O);
   REGT_CHECK(a->H >= 8 && a->H % 8 == 0 && a->H <= 1024, "%s: H=%d must be a multiple of 8 in [8,1024]", who, a->H);
   REGT_CHECK(a->mode >= 0 && a->mode <= 2, "%s: bad mode %d", who, a->mode);
+  REGT_CHECK(a->x_rows == 0 || a->x_rows >= a->N, "%s: x_rows=%d must be 0 or >= N=%d", who, a->x_rows, a->N);
   REGT_CHECK(a->plan.N == a->N, "%s: plan built for %d nodes, args say %d", who, a->plan.N, a->N);
   REGT_CHECK((long long)a->B * a->N * a->T < (1ll << 31), "%s: B*N*T overflows int32 rows", who);
   REGT_CHECK(a->workspace && a->workspace_bytes >= regt_workspace_bytes(a), "%s: workspace missing or too small", who);

@@ -15,7 +15,7 @@ namespace regt {
 constexpr int F = REGT_F;
 
 struct CellK {
-  int rows, N, T, H, nseg, mode;
+  int rows, N, xN, T, H, nseg, mode;   // xN: node rows per snapshot of x (>= N: halo rows of a region shard)
   const float *x, *S, *U, *h_ext;
   const int32_t *seg_ptr, *seg_reg;
   const float *M0t, *M1t, *c0, *Wzr, *Wc, *czr, *cc, *probs;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TM * 4) k_cell_fwd(CellK a) {
         const long long q = row / T;
         const int t = (int)(row - q * T);
         const int b = (int)(q / a.N), n = (int)(q - (long long)b * a.N);
-        const float* xr = a.x + q * F * T + t;
+        const float* xr = a.x + ((size_t)b * a.xN + n) * F * T + t;
         float acc = a.c0[j];
 #pragma unroll
         for (int f = 0; f < F; ++f) acc = fmaf(__ldg(xr + f * T), __ldg(a.M0t + f * H + j), acc);
@@ -288,20 +288,22 @@ __global__ void __launch_bounds__(256) k_dprobs(const float* __restrict__ G, con
 // ---- F-wide weight gradients: dP_g = D_g^T S, dM0 = D_3^T X, biases = column sums ----------
 // thread c owns one column of D; part[split][c][F+1]
 __global__ void __launch_bounds__(128) k_wgrad_skinny(const float* __restrict__ D, const float* __restrict__ S,
-                                                      const float* __restrict__ x, int H, int T, long long rows,
-                                                      int ncol, long long chunk, float* __restrict__ part) {
+                                                      const float* __restrict__ x, int N, int xN, int H, int T,
+                                                      long long rows, int ncol, long long chunk,
+                                                      float* __restrict__ part) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
   float acc[F + 1];
 #pragma unroll
   for (int f = 0; f <= F; ++f) acc[f] = 0.f;
   if (c < ncol) {
-    const float* feat = (c < 3 * H) ? S : x;
+    const bool from_x = c >= 3 * H;
     for (long long r = r0; r < r1; ++r) {
       const float d = __ldg(D + r * 4 * H + c);
-      const long long q = r / T;
+      long long q = r / T;
       const int t = (int)(r - q * T);
-      const float* fr = feat + q * F * T + t;
+      if (from_x && xN != N) q = (q / N) * xN + q % N;   // x carries halo rows after the N owned ones
+      const float* fr = (from_x ? x : S) + q * F * T + t;
 #pragma unroll
       for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(fr + f * T), acc[f]);
       acc[F] += d;
@@ -474,7 +476,7 @@ int launch_chain(const regt_args* a, const Layout& L, cudaStream_t st);
 static CellK make_cellk(const regt_args* a, const Layout& L) {
   CellK k{};
   k.rows = a->B * a->N * a->T;
-  k.N = a->N; k.T = a->T; k.H = a->H; k.nseg = a->plan.nseg; k.mode = a->mode;
+  k.N = a->N; k.xN = a->x_rows > 0 ? a->x_rows : a->N; k.T = a->T; k.H = a->H; k.nseg = a->plan.nseg; k.mode = a->mode;
   k.x = a->x; k.S = L.S; k.U = L.U; k.h_ext = a->h_ext;
   k.seg_ptr = a->plan.seg_ptr; k.seg_reg = a->plan.seg_reg;
   k.M0t = L.M0t; k.M1t = L.M1t; k.c0 = L.c0; k.Wzr = L.Wzr; k.Wc = L.Wc; k.czr = L.czr; k.cc = L.cc; k.probs = L.probs;
@@ -504,11 +506,12 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
 int cell_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, T = a->T;
   const long long BN = (long long)a->B * a->N;
+  const int xN = a->x_rows > 0 ? a->x_rows : a->N;
   if (launch_prep(a, L, st)) return -1;
   // F-wide SpMM: S = A_hat X on rows of F*T floats; U per (node, region) segment
-  if (launch_spmm_rows(a->plan.g_rowptr, a->plan.g_col, a->plan.g_val, a->x, L.S, a->B, a->N, a->N, F * T, st)) return -1;
+  if (launch_spmm_rows(a->plan.g_rowptr, a->plan.g_col, a->plan.g_val, a->x, L.S, a->B, a->N, xN, F * T, st)) return -1;
   if (a->mode != REGT_MODE_TGCN && a->plan.nseg > 0) {
-    if (launch_spmm_rows(a->plan.seg_eptr, a->plan.c_col, a->plan.c_val, a->x, L.U, a->B, a->plan.nseg, a->N, F * T, st))
+    if (launch_spmm_rows(a->plan.seg_eptr, a->plan.c_col, a->plan.c_val, a->x, L.U, a->B, a->plan.nseg, xN, F * T, st))
       return -1;
   }
   CellK k = make_cellk(a, L);
@@ -553,7 +556,7 @@ int cell_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   // F-wide weight gradients
   const int ncol = (a->mode == REGT_MODE_TGCN) ? 3 * H : 4 * H;
   long long chunk = (rows + splits - 1) / splits;
-  k_wgrad_skinny<<<dim3(cdiv(ncol, 128), splits), 128, 0, st>>>(L.D, L.S, a->x, H, T, rows, ncol, chunk, part);
+  k_wgrad_skinny<<<dim3(cdiv(ncol, 128), splits), 128, 0, st>>>(L.D, L.S, a->x, a->N, a->x_rows > 0 ? a->x_rows : a->N, H, T, rows, ncol, chunk, part);
   REGT_LAUNCHED("k_wgrad_skinny", st);
   k_skinny_reduce<<<cdiv((long long)ncol * (F + 1), 256), 256, 0, st>>>(part, splits, H, ncol, L.dP, L.dcg, L.dM0, L.dc0);
   REGT_LAUNCHED("k_skinny_reduce", st);

@@ -662,7 +662,7 @@ __global__ void k_hid_reduce(const float* __restrict__ part, int ntc, long long 
 int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y, int B,
                      int n_out, int n_in, int width, cudaStream_t st);
 int launch_prep(const regt_args* a, const Layout& L, cudaStream_t st);
-int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int T, float* Xt, float* St, float* Ut, cudaStream_t st);
+int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int xN, int T, float* Xt, float* St, float* Ut, cudaStream_t st);
 
 static int num_sms() {
   static int n = 0;
@@ -745,7 +745,7 @@ int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   REGT_CHECK(a->mode != REGT_MODE_TGCN, "tensor-core precisions do not cover the bare TGCN cell; use precision fp32");
   REGT_CHECK(a->T <= 64, "tensor-core path supports up to 64 periods");
   if (launch_prep(a, L, st)) return -1;
-  if (launch_feat_tc(a->plan, a->x, a->B, a->T, L.Xt, L.S, L.U, st)) return -1;
+  if (launch_feat_tc(a->plan, a->x, a->B, a->x_rows > 0 ? a->x_rows : a->N, a->T, L.Xt, L.S, L.U, st)) return -1;
   if (a->precision == REGT_PREC_TF32X3) return run_fwd_tc<FMT_TF32, 64>(a, L, st);
   return run_fwd_tc<FMT_BF16, 64>(a, L, st);
 }

@@ -10,7 +10,7 @@ constexpr int TMH = 64;
 
 struct HeadK {
   long long BN;
-  int N, H, O;
+  int N, H, O;   // N = node count of the loss mean (regt_args.loss_nodes or N)
   const float *hid, *y, *W1t, *W2t, *b1, *b2;  // W1t [H][128], W2t [128][O]
   const float *w1, *w2;                        // natural layouts for the data gradients
   const float* d_hidden;
@@ -422,7 +422,7 @@ int tc_num_chunks(const regt_args* a);
 static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* W2t) {
   HeadK k{};
   k.BN = (long long)a->B * a->N;
-  k.N = a->N; k.H = a->H; k.O = a->O;
+  k.N = a->loss_nodes > 0 ? a->loss_nodes : a->N; k.H = a->H; k.O = a->O;
   k.hid = a->out_hidden; k.y = a->y; k.W1t = W1t; k.W2t = W2t; k.b1 = a->p.head_b1; k.b2 = a->p.head_b2;
   k.w1 = a->p.head_w1; k.w2 = a->p.head_w2; k.d_hidden = a->d_hidden;
   k.a1 = L.a1; k.out = a->out; k.d_out = a->d_out; k.loss_part = L.part; k.d_a1 = L.d_a1; k.G = L.G;

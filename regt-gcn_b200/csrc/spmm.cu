@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_spmm_rows(const int32_t* __restrict__ r
 __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_rowptr, const int32_t* __restrict__ g_col,
                                                  const float* __restrict__ g_val, const int32_t* __restrict__ seg_eptr,
                                                  const int32_t* __restrict__ c_col, const float* __restrict__ c_val,
-                                                 const float* __restrict__ x, int B, int N, int nseg, int T,
+                                                 const float* __restrict__ x, int B, int N, int xN, int nseg, int T,
                                                  float* __restrict__ Xt, float* __restrict__ St, float* __restrict__ Ut) {
   extern __shared__ __align__(16) float feat_stage[];   // [warps per block][2][F*T]
   const int lane = threadIdx.x & 31;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_r
   const int* col = is_seg ? c_col : g_col;
   const float* val = is_seg ? c_val : g_val;
   const int W = REGT_F * T, W4 = W >> 2;  // floats / float4 per row (W % 4 == 0 since F = 8)
-  const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * N * W4;
+  const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * xN * W4;   // xN >= N: halo rows follow the owned ones
   const int e0 = rowptr[r], e1 = rowptr[r + 1];
   const long long plane_rows = is_seg ? BS : BN;
   float* dst = is_seg ? Ut : St;
@@ -127,10 +127,10 @@ __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_r
   }
 }
 
-int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int T, float* Xt, float* St, float* Ut, cudaStream_t st) {
+int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int xN, int T, float* Xt, float* St, float* Ut, cudaStream_t st) {
   const long long warps = (long long)B * p.N + (long long)B * p.nseg;
   k_feat_tc<<<cdiv(warps * 32, 256), 256, 8 * 2 * REGT_F * T * sizeof(float), st>>>(p.g_rowptr, p.g_col, p.g_val, p.seg_eptr, p.c_col, p.c_val, x, B, p.N,
-                                                  p.nseg, T, Xt, St, Ut);
+                                                  xN, p.nseg, T, Xt, St, Ut);
   REGT_LAUNCHED("k_feat_tc", st);
   return 0;
 }
@@ -146,7 +146,48 @@ int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val
   return 0;
 }
 
+// K4 regional gather / scatter of node rows (region shards: owned + halo rows in, owned rows out)
+//   gather : dst[b][i][:] = src[b][idx[i]][:]   i < n_idx   (src has n_src rows, dst n_idx rows)
+//   scatter: dst[b][idx[i]][:] = src[b][i][:]   i < n_idx   (src has n_idx rows, dst n_dst rows)
+template <bool SCATTER, typename V>
+__global__ void __launch_bounds__(256) k_move_rows(const V* __restrict__ src, const int64_t* __restrict__ idx,
+                                                   V* __restrict__ dst, int n_idx, int n_other, int WV, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % WV);
+  const long long br = i / WV;
+  const int r = (int)(br % n_idx), b = (int)(br / n_idx);
+  const size_t packed = ((size_t)b * n_idx + r) * WV + c;
+  const size_t strided = ((size_t)b * n_other + (size_t)__ldg(idx + r)) * WV + c;
+  if (SCATTER) dst[strided] = src[packed];
+  else dst[packed] = __ldg(src + strided);
+}
+
+template <bool SCATTER>
+static int launch_move_rows(const float* src, const int64_t* idx, float* dst, int B, int n_idx, int n_other, int width,
+                            cudaStream_t st) {
+  REGT_CHECK(src && idx && dst, "gather/scatter_rows: NULL pointer");
+  REGT_CHECK(B >= 0 && n_idx >= 0 && n_other >= 0 && width > 0, "gather/scatter_rows: bad sizes");
+  if (B == 0 || n_idx == 0) return 0;
+  const bool v4 = width % 4 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+  const int WV = v4 ? width / 4 : width;
+  const long long total = (long long)B * n_idx * WV;
+  if (v4) k_move_rows<SCATTER, float4><<<cdiv(total, 256), 256, 0, st>>>((const float4*)src, idx, (float4*)dst, n_idx, n_other, WV, total);
+  else k_move_rows<SCATTER, float><<<cdiv(total, 256), 256, 0, st>>>(src, idx, dst, n_idx, n_other, WV, total);
+  REGT_LAUNCHED(SCATTER ? "k_scatter_rows" : "k_gather_rows", st);
+  return 0;
+}
+
 }  // namespace regt
+
+extern "C" int regt_gather_rows(const float* src, const int64_t* idx, float* dst, int32_t B, int32_t n_src, int32_t n_idx,
+                                int32_t width, regt_stream_t stream) {
+  return regt::launch_move_rows<false>(src, idx, dst, B, n_idx, n_src, width, (cudaStream_t)stream);
+}
+extern "C" int regt_scatter_rows(const float* src, const int64_t* idx, float* dst, int32_t B, int32_t n_idx, int32_t n_dst,
+                                 int32_t width, regt_stream_t stream) {
+  return regt::launch_move_rows<true>(src, idx, dst, B, n_idx, n_dst, width, (cudaStream_t)stream);
+}
 
 extern "C" int regt_spmm_f8(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
                             int32_t B, int32_t N, int32_t width, regt_stream_t stream) {

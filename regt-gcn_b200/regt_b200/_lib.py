@@ -35,7 +35,7 @@ class Params(C.Structure):
 class Args(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("O", C.c_int32),
                 ("mode", C.c_int32), ("precision", C.c_int32), ("accumulate", C.c_int32),
-                ("fuse_head", C.c_int32), ("_reserved", C.c_int32),
+                ("fuse_head", C.c_int32), ("x_rows", C.c_int32), ("loss_nodes", C.c_int32), ("_reserved", C.c_int32),
                 ("plan", GraphPlan),
                 ("x", vp), ("y", vp), ("h_ext", vp),
                 ("p", Params), ("g", Params),
@@ -48,7 +48,7 @@ PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
 
 EXPORTS = ["regt_version", "regt_last_error", "regt_launch_count", "regt_plan_workspace_bytes",
-           "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_workspace_bytes",
+           "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_gather_rows", "regt_scatter_rows", "regt_workspace_bytes",
            "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward",
            "regt_profile", "regt_profile_begin", "regt_profile_read"]
 
@@ -85,6 +85,10 @@ def load() -> C.CDLL:
                                         [c_i32p, vp, C.c_size_t, vp]
     lib.regt_spmm_f8.restype = C.c_int
     lib.regt_spmm_f8.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    for name in ("regt_gather_rows", "regt_scatter_rows"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.regt_workspace_bytes.restype = C.c_size_t
     lib.regt_workspace_bytes.argtypes = [C.POINTER(Args)]
     for name in ("regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward"):

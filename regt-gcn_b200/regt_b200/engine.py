@@ -75,21 +75,28 @@ def _stream() -> int:
 def build_state(mode: int, precision: int, plan: GraphPlanTensors, x: torch.Tensor, H: int, O: int,
                 params: Dict[str, torch.Tensor], y: Optional[torch.Tensor] = None,
                 h_ext: Optional[torch.Tensor] = None, head: bool = True,
-                workspace: Optional[torch.Tensor] = None, fuse_head: bool = False) -> StepState:
-    """x [B,N,F,T] float32 CUDA.  Allocates outputs + workspace and fills ``regt_args``."""
+                workspace: Optional[torch.Tensor] = None, fuse_head: bool = False,
+                loss_nodes: Optional[int] = None) -> StepState:
+    """x [B,N,F,T] float32 CUDA.  Allocates outputs + workspace and fills ``regt_args``.
+    Region shards (shard.py): x is [B,x_rows,F,T] with x_rows >= plan.N -- the plan's N owned rows
+    followed by halo rows that only the plan's column indices address -- and ``loss_nodes`` is the
+    node count of the full graph, so the per-rank losses and gradients add up to the unsharded ones."""
     lib = _lib.load()
     dev = x.device
     _check(x, "x", dev)
-    B, N, Fx, T = x.shape
+    B, x_rows, Fx, T = x.shape
+    N = plan.N
     if Fx != F_IN:
         raise ValueError(f"regt_b200: node_features must be {F_IN} (reference run.py:116), got {Fx}")
-    if N != plan.N:
-        raise ValueError(f"regt_b200: x has {N} nodes, graph plan has {plan.N}")
+    if x_rows < N or (x_rows != N and x_rows != N + getattr(plan, "n_halo", 0)):
+        raise ValueError(f"regt_b200: x has {x_rows} nodes, graph plan has {N} (+{getattr(plan, 'n_halo', 0)} halo)")
     st = StepState()
     a = st.args
     a.B, a.N, a.T, a.H, a.O = B, N, T, H, O
     a.mode, a.precision, a.accumulate = mode, precision, 0
     a.fuse_head = 1 if (fuse_head and head and y is not None) else 0
+    a.x_rows = x_rows
+    a.loss_nodes = int(loss_nodes) if loss_nodes else 0
     a.plan = plan.c_struct()
     a.x = x.data_ptr()
     for k in keys_for(mode, head):

@@ -88,7 +88,8 @@ class RegTModelBase(nn.Module):
         return out, hid
 
     # ---- fused training step: forward + loss + backward in one pass, no autograd graph ----
-    def _fused_step(self, x: torch.Tensor, y: torch.Tensor, plan, micro_batch: Optional[int] = None):
+    def _fused_step(self, x: torch.Tensor, y: torch.Tensor, plan, micro_batch: Optional[int] = None,
+                    loss_nodes: Optional[int] = None):
         """run.py:170-192 for a whole batch of snapshots: loss = sum_b mean((out_b-y_b)^2);
         gradients are ACCUMULATED into ``.grad`` (the reference accumulates over the epoch and
         steps once, run.py:190-195).  Returns (loss [1] device tensor, out, out_hidden)."""
@@ -108,7 +109,8 @@ class RegTModelBase(nn.Module):
         outs, hids = [], []
         for b0 in range(0, B, mb):
             st = engine.build_state(self._mode, self._prec(), plan, xb[b0:b0 + mb], self._hidden, self.output_dim,
-                                    params, yb[b0:b0 + mb], None, True, getattr(self, "_ws", None), fuse_head=True)
+                                    params, yb[b0:b0 + mb], None, True, getattr(self, "_ws", None), fuse_head=True,
+                                    loss_nodes=loss_nodes)
             self._ws = st.workspace
             engine.run_forward(st, True)
             engine.run_backward(st, grads, st.d_out, None, True, True)
