@@ -174,7 +174,10 @@ int regt_cell_forward(const regt_args* a);
  * given, the loss of the call site (run.py:180).                                        */
 int regt_head_forward(const regt_args* a);
 /* autograd of the head (run.py:190): consumes d_out, writes g.head_* and the gradient
- * wrt out_hidden (kept in the workspace for regt_cell_backward).                        */
+ * wrt out_hidden (kept in the workspace for regt_cell_backward).  With fuse_head=1 in precision
+ * bf16 the head ran its backward inside regt_head_forward and left per-CTA partials; their sum
+ * (g.head_*, loss) is then finalised by the regt_cell_backward that must follow, beside the cell
+ * kernel on a second stream.                                                             */
 int regt_head_backward(const regt_args* a);
 /* autograd of the cell (run.py:190): all parameter gradients of the cell.  No gradient
  * wrt x is produced (x is data in the reference: batch.x never requires grad).          */

@@ -68,7 +68,7 @@ Layout make_layout(const regt_args* a, void* base) {
   pf = max(pf, (size_t)32 * (O * HEAD_HID + HEAD_HID * H));         // head split-K partials
   pf = max(pf, BN / 64 + 2);                                        // loss partials
   pf += H * HEAD_HID + HEAD_HID * O + 64;                           // transposed head weights (tail)
-  L.hpart = c.take<float>((size_t)148 * (HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 4));
+  L.hpart = c.take<float>((size_t)148 * (HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 8));
   L.part = c.take<float>(pf);
   L.part_floats = pf;
   L.total = align_up(c.off, 256);

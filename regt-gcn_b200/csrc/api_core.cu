@@ -32,6 +32,47 @@ void prof_mark(const char* name, cudaStream_t st) {
   cudaEventRecord(ev, st);
   g_marks.push_back(Mark{name, ev});
 }
+
+// ---- fork / join onto a library-owned side stream (independent kernels of one step run concurrently;
+// legal under stream capture: the side stream joins the caller's capture through the fork event) ----
+struct Side {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static thread_local Side g_side;
+
+cudaStream_t fork_side(cudaStream_t main) {
+  if (g_prof) return nullptr;   // the per-kernel profiler brackets kernels on ONE stream
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (g_side.device != dev) {
+    if (g_side.stream) {
+      cudaStreamDestroy(g_side.stream);
+      cudaEventDestroy(g_side.fork);
+      cudaEventDestroy(g_side.join);
+      g_side = Side{};
+    }
+    if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      g_side = Side{};
+      return nullptr;
+    }
+    g_side.device = dev;
+  }
+  if (cudaEventRecord(g_side.fork, main) != cudaSuccess || cudaStreamWaitEvent(g_side.stream, g_side.fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return g_side.stream;
+}
+int join_side(cudaStream_t main) {
+  REGT_CUDA(cudaEventRecord(g_side.join, g_side.stream));
+  REGT_CUDA(cudaStreamWaitEvent(main, g_side.join, 0));
+  return 0;
+}
 }  // namespace regt
 
 extern "C" int regt_version(void) { return REGT_VERSION; }

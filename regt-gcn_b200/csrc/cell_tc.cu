@@ -692,6 +692,8 @@ static int choose_tp(int nqt, int T, int slots) {
 }
 
 bool head_fusable(const regt_args* a);
+bool head_tc_usable(const regt_args* a);
+int launch_head_grad_reduce(const regt_args* a, const Layout& L, cudaStream_t st);
 int tc_num_chunks(const regt_args* a) {
   const int BN = a->B * a->N, nqt = (BN + TC_ROWS - 1) / TC_ROWS;
   return a->T / choose_tp(nqt, a->T, num_sms());
@@ -716,7 +718,7 @@ static TcArgs make_tcargs(const regt_args* a, const Layout& L, int slots) {
 }
 
 template <int FMT, int HH>
-static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
+static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st, bool forked) {
   using Cfg = TcCfg<FMT, HH>;
   static_assert(Cfg::FWD_IMG <= TC_IMG_BYTES && Cfg::BWD_IMG <= TC_IMG_BYTES, "weight image too large");
   const int n_pack = 2 * HH * HH + 2 * HH * 16 + HH * HH + HH * 16 + Cfg::C_FLOATS + 3 * HH * HH + HH * 16;
@@ -724,6 +726,7 @@ static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
                                                        a->p.lin_w[0], a->p.lin_w[1], a->p.lin_w[2], L.tc_img_f,
                                                        L.tc_img_b);
   REGT_LAUNCHED("k_pack_tc", st);
+  if (forked && join_side(st)) return -1;   // the feature builder ran beside the weight collapse
   const int slots = num_sms();
   TcArgs k = make_tcargs(a, L, slots);
   const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + Cfg::NSPLIT * Cfg::A_TILE +
@@ -744,10 +747,12 @@ int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   REGT_CHECK(a->H == 64, "tensor-core precisions are built for hidden=64 (got %d); use precision fp32", a->H);
   REGT_CHECK(a->mode != REGT_MODE_TGCN, "tensor-core precisions do not cover the bare TGCN cell; use precision fp32");
   REGT_CHECK(a->T <= 64, "tensor-core path supports up to 64 periods");
+  // features (graph + x) and collapsed weights (parameters) are independent: two streams
+  cudaStream_t side = fork_side(st);
+  if (launch_feat_tc(a->plan, a->x, a->B, a->x_rows > 0 ? a->x_rows : a->N, a->T, L.Xt, L.S, L.U, side ? side : st)) return -1;
   if (launch_prep(a, L, st)) return -1;
-  if (launch_feat_tc(a->plan, a->x, a->B, a->x_rows > 0 ? a->x_rows : a->N, a->T, L.Xt, L.S, L.U, st)) return -1;
-  if (a->precision == REGT_PREC_TF32X3) return run_fwd_tc<FMT_TF32, 64>(a, L, st);
-  return run_fwd_tc<FMT_BF16, 64>(a, L, st);
+  if (a->precision == REGT_PREC_TF32X3) return run_fwd_tc<FMT_TF32, 64>(a, L, st, side != nullptr);
+  return run_fwd_tc<FMT_BF16, 64>(a, L, st, side != nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1201,8 +1206,13 @@ int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   const size_t smem = 1024 + ((Cfg::BWD_IMG + 1023) & ~1023) + 6 * Cfg::A_TILE + 2 * 4 * TC_ROWS * 16 +
                       3 * PlaneIO<FMT_BF16, HH>::TILE_BYTES + TC_ROWS * HH * 4;
   REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd_tc<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the head's partial sums (left by the tensor-core head in regt_head_forward) are reduced beside the cell backward
+  const bool head_sum = head_tc_usable(a);
+  cudaStream_t side = head_sum ? fork_side(st) : nullptr;
+  if (head_sum && launch_head_grad_reduce(a, L, side ? side : st)) return -1;
   k_cell_bwd_tc<HH><<<grid, NTHREADS, smem, st>>>(k);
   REGT_LAUNCHED("k_cell_bwd_tc", st);
+  if (side && join_side(st)) return -1;
   const int R = a->plan.R;
   k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS + a->T, 32), dim3(32, 8), 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1,
                                                                      L.dc0, L.tc_dpp, k.nqt, a->T, L.dprobs);

@@ -11,6 +11,10 @@ namespace regt {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 void prof_mark(const char* name, cudaStream_t st);
+// fork: returns a library-owned side stream that waits for everything enqueued on `main` so far (or
+// nullptr: run serially); join: `main` waits for everything enqueued on the side stream
+cudaStream_t fork_side(cudaStream_t main);
+int join_side(cudaStream_t main);
 
 #define REGT_CHECK(cond, ...)         \
   do {                                \

@@ -166,7 +166,8 @@ __global__ void k_copy_or_zero(const float* __restrict__ src, float* __restrict_
 // ONE persistent kernel; weights stay in shared memory, dW1 accumulates in registers.
 // ------------------------------------------------------------------------------------------
 constexpr int HP_MAX_CTAS = 148;
-__host__ __device__ inline int head_part_stride(int H, int O) { return HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 4; }
+// multiple of 4 floats: the tensor-core head writes its dW1 partial with 16-byte stores
+__host__ __device__ inline int head_part_stride(int H, int O) { return (HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 4 + 3) & ~3; }
 
 template <int H>
 __global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restrict__ hpart, int ntiles) {
@@ -419,6 +420,11 @@ static int head_fused_grid(const regt_args* a) {
 
 bool head_fusable(const regt_args* a);
 int tc_num_chunks(const regt_args* a);
+// tcgen05 head (head_tc.cu): bf16 precision, hidden 64, output_dim <= 16
+bool head_tc_usable(const regt_args* a);
+int head_tc_grid(const regt_args* a);
+int head_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st, bool cell_left_partials);
+int head_part_stride_host(int H, int O) { return head_part_stride(H, O); }
 static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* W2t) {
   HeadK k{};
   k.BN = (long long)a->B * a->N;
@@ -437,6 +443,7 @@ static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* 
 
 int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, O = a->O;
+  if (head_tc_usable(a)) return head_forward_tc(a, L, st, true);
   if (head_fusable(a)) {
     HeadK k = make_headk(a, L, nullptr, nullptr);
     const int grid = head_fused_grid(a), ntiles = cdiv(k.BN, TMH), OP = (O + 3) & ~3;
@@ -471,15 +478,23 @@ int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   return 0;
 }
 
+int launch_head_grad_reduce(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int H = a->H, O = a->O;
+  const int stride = head_part_stride(H, O), n = HEAD_HID * H + O * HEAD_HID + HEAD_HID + O;
+  k_head_grad_reduce<<<cdiv(n + 1, 32), dim3(32, 8), 0, st>>>(L.hpart, stride, head_tc_usable(a) ? head_tc_grid(a) : head_fused_grid(a),
+                                                            H, O, a->accumulate, a->g.head_w1, a->g.head_w2, a->g.head_b1,
+                                                            a->g.head_b2, a->loss);
+  REGT_LAUNCHED("k_head_grad_reduce", st);
+  return 0;
+}
+
 int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, O = a->O;
   const long long BN = (long long)a->B * a->N;
   if (head_fusable(a)) {  // everything but the cross-CTA sum already happened in head_forward
-    const int stride = head_part_stride(H, O), n = HEAD_HID * H + O * HEAD_HID + HEAD_HID + O;
-    k_head_grad_reduce<<<cdiv(n + 1, 32), dim3(32, 8), 0, st>>>(L.hpart, stride, head_fused_grid(a), H, O, a->accumulate,
-                                                         a->g.head_w1, a->g.head_w2, a->g.head_b1, a->g.head_b2, a->loss);
-    REGT_LAUNCHED("k_head_grad_reduce", st);
-    return 0;
+    // tensor-core step: the sum runs beside the cell backward (launch_head_grad_reduce from cell_backward_tc)
+    if (head_tc_usable(a)) return 0;
+    return launch_head_grad_reduce(a, L, st);
   }
   if (!a->d_out) {  // only out_hidden carries gradient
     k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H, H, a->precision != REGT_PREC_FP32);

@@ -24,106 +24,90 @@ __global__ void k_lsum(const float* __restrict__ comb_w, int H, int R, float* __
   Lsum[i] = (float)s;
 }
 
-// flat output space: [0, n_w) packed gate weights, then biases, cheb pieces, probs
-__global__ void k_prep(regt_params p, int H, int R, int T, int mode, const float* __restrict__ Lsum,
-                       float* __restrict__ Wzr, float* __restrict__ Wc, float* __restrict__ czr,
-                       float* __restrict__ cc, float* __restrict__ M0t, float* __restrict__ M1t,
-                       float* __restrict__ c0, float* __restrict__ probs) {
+// flat output space: [0, n_w) packed gate weights, then biases, cheb pieces, probs.
+// PG consecutive lanes share one output: each sums a slice of the H-long contraction in fp64, the
+// slices are combined with a shuffle tree (the step waits on this kernel, so its latency -- a chain
+// of H dependent loads from cold HBM per output in a one-thread-per-output form -- matters).
+constexpr int PG = 8;
+__global__ void __launch_bounds__(256) k_prep(regt_params p, int H, int R, int T, int mode, const float* __restrict__ Lsum,
+                                              float* __restrict__ Wzr, float* __restrict__ Wc, float* __restrict__ czr,
+                                              float* __restrict__ cc, float* __restrict__ M0t, float* __restrict__ M1t,
+                                              float* __restrict__ c0, float* __restrict__ probs) {
   const long long nW = (long long)3 * (F + H) * H;  // gate weights
   const long long nC = 3 * H;                       // gate biases
   const long long nM0 = (long long)F * H, nM1 = (long long)R * F * H, nc0 = H;
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long i = gt / PG;
+  const int sub = (int)(gt % PG), m0 = sub * (H / PG), m1 = m0 + H / PG;   // H % 8 == 0 (validated)
+  double s = 0.0;       // this lane's slice of the contraction (or the whole value for copies, lane 0)
+  float* dst = nullptr;
   if (i < nW) {
     int g = (int)(i / ((F + H) * H));
     int rem = (int)(i % ((F + H) * H));
     int k = rem / H, j = rem % H;  // j fastest: coalesced writes
-    float v;
     if (k < F) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const float* A = p.lin_w[g] + (size_t)j * 2 * H;
       const float* W = p.conv_w[g];
-#pragma unroll 4
-      for (int m = 0; m < H; m += 4) {
-        const float4 a4 = __ldg(reinterpret_cast<const float4*>(A + m));
-        s0 += (double)a4.x * (double)__ldg(W + m * F + k);
-        s1 += (double)a4.y * (double)__ldg(W + (m + 1) * F + k);
-        s2 += (double)a4.z * (double)__ldg(W + (m + 2) * F + k);
-        s3 += (double)a4.w * (double)__ldg(W + (m + 3) * F + k);
-      }
-      v = (float)((s0 + s1) + (s2 + s3));
-    } else {
-      v = p.lin_w[g][(size_t)j * 2 * H + H + (k - F)];
+      for (int m = m0; m < m1; ++m) s += (double)__ldg(A + m) * (double)__ldg(W + m * F + k);
+    } else if (sub == 0) {
+      s = p.lin_w[g][(size_t)j * 2 * H + H + (k - F)];
     }
-    if (g < 2) Wzr[(size_t)k * 2 * H + g * H + j] = v;
-    else Wc[(size_t)k * H + j] = v;
-    return;
-  }
-  i -= nW;
-  if (i < nC) {
+    dst = (g < 2) ? Wzr + (size_t)k * 2 * H + g * H + j : Wc + (size_t)k * H + j;
+  } else if ((i -= nW) < nC) {
     int g = (int)(i / H), j = (int)(i % H);
-    double s = p.lin_b[g][j];
+    if (sub == 0) s = p.lin_b[g][j];
     const float* A = p.lin_w[g] + (size_t)j * 2 * H;
-    for (int m = 0; m < H; ++m) s += (double)A[m] * (double)p.conv_b[g][m];
-    if (g < 2) czr[g * H + j] = (float)s; else cc[j] = (float)s;
-    return;
-  }
-  i -= nC;
-  if (mode == REGT_MODE_TGCN) {  // no Chebyshev branch: only probs (T == 1 -> 1.0)
-    if (i == 0) {
+    for (int m = m0; m < m1; ++m) s += (double)__ldg(A + m) * (double)__ldg(p.conv_b[g] + m);
+    dst = (g < 2) ? czr + g * H + j : cc + j;
+  } else if (mode == REGT_MODE_TGCN) {  // no Chebyshev branch: only probs (T == 1 -> 1.0)
+    i -= nC;
+    if (i == 0 && sub == 0) {
       float mx = -INFINITY;
       for (int t = 0; t < T; ++t) mx = fmaxf(mx, p.attention ? p.attention[t] : 0.f);
       double den = 0.0;
       for (int t = 0; t < T; ++t) den += exp((double)(p.attention ? p.attention[t] : 0.f) - mx);
       for (int t = 0; t < T; ++t) probs[t] = (float)(exp((double)(p.attention ? p.attention[t] : 0.f) - mx) / den);
     }
-    return;
-  }
-  if (i < nM0) {
+  } else if ((i -= nC) < nM0) {
     int f = (int)(i / H), j = (int)(i % H);
     if (mode == REGT_MODE_REGIONAL) {
-      double s = 0.0;
-      for (int m = 0; m < H; ++m) s += (double)Lsum[(size_t)j * H + m] * (double)p.cheb_w0[m * F + f];
-      M0t[i] = (float)s;
-    } else {
-      M0t[i] = p.cheb_w0[j * F + f];
+      for (int m = m0; m < m1; ++m) s += (double)__ldg(Lsum + (size_t)j * H + m) * (double)__ldg(p.cheb_w0 + m * F + f);
+    } else if (sub == 0) {
+      s = p.cheb_w0[j * F + f];
     }
-    return;
-  }
-  i -= nM0;
-  if (i < nM1) {
+    dst = M0t + i;
+  } else if ((i -= nM0) < nM1) {
     int r = (int)(i / (F * H));
     int rem = (int)(i % (F * H));
     int f = rem / H, j = rem % H;
     if (mode == REGT_MODE_REGIONAL) {
-      double s = 0.0;
       const float* L = p.comb_w + (size_t)j * R * H + (size_t)r * H;
-      for (int m = 0; m < H; ++m) s += (double)L[m] * (double)p.cheb_w1[m * F + f];
-      M1t[i] = (float)s;
-    } else {
-      M1t[i] = p.cheb_w1[j * F + f];
+      for (int m = m0; m < m1; ++m) s += (double)__ldg(L + m) * (double)__ldg(p.cheb_w1 + m * F + f);
+    } else if (sub == 0) {
+      s = p.cheb_w1[j * F + f];
     }
-    return;
-  }
-  i -= nM1;
-  if (i < nc0) {
+    dst = M1t + i;
+  } else if ((i -= nM1) < nc0) {
     int j = (int)i;
     if (mode == REGT_MODE_REGIONAL) {
-      double s = p.comb_b[j];
-      for (int m = 0; m < H; ++m) s += (double)Lsum[(size_t)j * H + m] * (double)p.cheb_b[m];
-      c0[j] = (float)s;
-    } else {
-      c0[j] = p.cheb_b[j];
+      if (sub == 0) s = p.comb_b[j];
+      for (int m = m0; m < m1; ++m) s += (double)__ldg(Lsum + (size_t)j * H + m) * (double)__ldg(p.cheb_b + m);
+    } else if (sub == 0) {
+      s = p.cheb_b[j];
     }
-    return;
-  }
-  i -= nc0;
-  if (i == 0) {  // softmax over the T learned scalars (models/RegionalTemporalGCN.py:134)
+    dst = c0 + j;
+  } else if ((i -= nc0) == 0 && sub == 0) {
+    // softmax over the T learned scalars (models/RegionalTemporalGCN.py:134)
     float mx = -INFINITY;
     for (int t = 0; t < T; ++t) mx = fmaxf(mx, p.attention[t]);
     double den = 0.0;
     for (int t = 0; t < T; ++t) den += exp((double)p.attention[t] - mx);
     for (int t = 0; t < T; ++t) probs[t] = (float)(exp((double)p.attention[t] - mx) / den);
   }
+  // all 32 lanes reach this point: combine the PG slices (fixed tree: deterministic)
+#pragma unroll
+  for (int d = PG / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (dst && sub == 0) *dst = (float)s;
 }
 
 int launch_prep(const regt_args* a, const Layout& L, cudaStream_t st) {
@@ -133,7 +117,7 @@ int launch_prep(const regt_args* a, const Layout& L, cudaStream_t st) {
     REGT_LAUNCHED("k_lsum", st);
   }
   long long n = (long long)3 * (F + H) * H + 3 * H + (long long)F * H + (long long)R * F * H + H + 1;
-  k_prep<<<cdiv(n, 256), 256, 0, st>>>(a->p, H, R, a->T, a->mode, L.Lsum, L.Wzr, L.Wc, L.czr, L.cc, L.M0t, L.M1t, L.c0,
+  k_prep<<<cdiv(n * PG, 256), 256, 0, st>>>(a->p, H, R, a->T, a->mode, L.Lsum, L.Wzr, L.Wc, L.czr, L.cc, L.M0t, L.M1t, L.c0,
                                       L.probs);
   REGT_LAUNCHED("k_prep", st);
   return 0;
