@@ -48,7 +48,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="2", help="SURVEY 8(d) config id (default 2 = BASELINE configs[1])")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch B")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32x3", "bf16"],
+                    help="bf16 = tcgen05 path (bf16 operands, fp32 accumulate; stated tolerance, tests/test_gpu_tc.py); "
+                         "fp32 = FFMA path with 1e-5 parity; the default run reports both (fp32 under 'fp32_parity_mode')")
     ap.add_argument("--micro-batch", type=int, default=None)
     ap.add_argument("--shard", default="auto", choices=["auto", "region", "batch"],
                     help="N>1: 'region' = each GPU owns a set of regions (strong scaling, SURVEY 8(e)); "
@@ -253,11 +255,13 @@ def main():
         ex = S.GradExchange([p for n, p in model.named_parameters() if p.requires_grad], world)
         xh, yh = w.inputs(B, seed_offset=rank)     # batch shards: every rank gets its own snapshots
     xh, yh = xh.pin_memory(), yh.pin_memory()
-    xd, yd = xh.to(dev), yh.to(dev)
-    loss_h = torch.zeros(1).pin_memory()
+    # two device input buffers: the end-to-end loop copies step k+1's inputs while step k computes
+    bufs = [(xh.to(dev), yh.to(dev)), (xh.to(dev), yh.to(dev))]
+    loss_h = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def raw_step():
+    def raw_step(b=0):
+        xd, yd = bufs[b]
         if world > 1:
             ex.zero()     # per-step exchange: the buffer holds this step's contribution only
         if sharded:
@@ -272,7 +276,7 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = lib.regt_launch_count(1) // max(3, args.warmup)
 
-    graph = None
+    graphs, graph_loss = None, [None, None]
     if not args.no_graph:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -280,17 +284,20 @@ def main():
             raw_step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss_d = raw_step()
-        torch.cuda.synchronize()
+        graphs = [torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()]   # one per input buffer
+        for b in (0, 1):
+            with torch.cuda.graph(graphs[b]):
+                graph_loss[b] = raw_step(b)
+            torch.cuda.synchronize()
+    graph = graphs[0] if graphs else None
 
-    def step():
+    def step(b=0):
         nonlocal loss_d
-        if graph is not None:
-            graph.replay()
+        if graphs is not None:
+            graphs[b].replay()
+            loss_d = graph_loss[b]
         else:
-            loss_d = raw_step()
+            loss_d = raw_step(b)
         if dist is not None:
             if not sharded:
                 ex.add_loss(loss_d)
@@ -322,18 +329,46 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---------------- end to end: host buffers in, loss out, every step ----------------
+    # Every step's x,y are copied from pinned host memory and every step's loss is read on the host, all
+    # inside the timed region.  The copies run on a second stream into the buffer the running step does
+    # not use, and a step's loss is read while the next step computes (the reference reads it
+    # synchronously, run.py:180; the values are the same, only one step late).
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main, cs = torch.cuda.current_stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def h2d(b, wait_free):
+        with torch.cuda.stream(cs):
+            if wait_free:
+                cs.wait_event(ev_done[b])       # the step that last used this buffer has finished
+            bufs[b][0].copy_(xh, non_blocking=True)
+            bufs[b][1].copy_(yh, non_blocking=True)
+            ev_in[b].record(cs)
+
     barrier()
+    cs.wait_stream(main)
     e0.record()
-    for _ in range(K):
-        xd.copy_(xh, non_blocking=True)
-        yd.copy_(yh, non_blocking=True)
-        step()
-        loss_h.copy_(loss_d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the loss every step (run.py:180)
-        _ = float(loss_h)
+    h2d(0, False)
+    losses = []
+    for k in range(K):
+        b = k & 1
+        if k + 1 < K:
+            h2d(1 - b, k >= 1)
+        main.wait_event(ev_in[b])
+        step(b)
+        ev_done[b].record(main)
+        loss_h[b].copy_(loss_d, non_blocking=True)
+        ev_loss[b].record(main)
+        if k >= 1:
+            ev_loss[1 - b].synchronize()
+            losses.append(float(loss_h[1 - b]))
+    ev_loss[(K - 1) & 1].synchronize()
+    losses.append(float(loss_h[(K - 1) & 1]))
     e1.record()
     barrier()
+    assert len(losses) == K and all(v == v for v in losses), "end-to-end loop lost a loss value"
     e2e_ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
@@ -366,14 +401,42 @@ def main():
         if dom is not None:
             t_launch = per_kernel[dom] / counts[dom] * 1e-3
             ach = ab[dom] / t_launch / 1e9
+            # DRAM bytes of that kernel per launch from the committed `ncu --set full` capture of this same
+            # command (profiles/ncu_traffic.json, written by tools/ncu_summary.py); null for other workloads
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath) and str(args.workload) == "2" and args.precision == "bf16" and not args.batch and world == 1:
+                traffic = json.load(open(tpath)).get(dom, {}).get("bytes_per_launch")
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                        "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
                         "alg_bytes_per_launch": ab[dom], "launch_ms": t_launch * 1e3,
                         "share_of_step": per_kernel[dom] / step_sum}
         step_bytes = W.alg_bytes_per_step(w, B)
         step_roof = {"alg_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                      "frac_of_hbm_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
                      "fwd_bwd_flops_per_step": 3 * W.fwd_flops_per_step(w, B)}
+
+    # ---------------- the fp32 (1e-5 parity) mode of the same step, same inputs, same run ----------------
+    fp32_mode = None
+    if rank == 0 and world == 1 and args.precision != "fp32":
+        m32 = (TemporalGCN(8, w.T, w.O, hidden=w.H, precision="fp32") if w.model == "TemporalGCN"
+               else RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R, precision="fp32"))
+        W.init_params_synthetic(m32, 1234)
+        m32 = m32.to(dev)
+        xd, yd = bufs[0]
+        for _ in range(3):
+            m32.fused_step(xd, yd, *graph_args, micro_batch=args.micro_batch)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); m32.fused_step(xd, yd, *graph_args, micro_batch=args.micro_batch); b_.record()
+            torch.cuda.synchronize()
+            ts.append(a_.elapsed_time(b_))
+        ms32 = sum(ts) / len(ts)
+        fp32_mode = {"value": B / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "steps": 5,
+                     "note": "precision=fp32 (FFMA kernels, 1e-5 normwise parity vs the fp64 oracle), eager launches"}
+        del m32
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
@@ -384,12 +447,12 @@ def main():
 
     if rank == 0:
         job_B = B if sharded else world * B     # snapshots the whole job processes per step
-        h2d = xh.numel() * 4 + yh.numel() * 4
+        h2d_bytes = xh.numel() * 4 + yh.numel() * 4
         out = {
             "metric": METRIC, "value": job_B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor cores)", "bf16": "bf16"}[args.precision],
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor cores)", "bf16": "bf16 operands, f32 accumulate (f32 inputs, outputs, loss, gradients)"}[args.precision],
             "data": "synthetic",
             "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, l2="flushed between timed steps (256 MiB memset)",
                            cuda_graph=graph is not None, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
@@ -398,11 +461,12 @@ def main():
                                         if sharded else
                                         f"batch-sharded x{world}, NCCL all-reduce of the flat gradient buffer")),
             "clocks": clocks,
-            "e2e": {"value": job_B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms},
+            "e2e": {"value": job_B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms, "pipeline": "double-buffered H2D on a copy stream; each step's loss read on the host one step late"},
             "gpu_launches": int(launches_per_step * K),
             "launches_per_step": int(launches_per_step),
             "roofline": roofline, "roofline_step": step_roof, "kernels": breakdown, "cpu_baseline": cpu,
+            "fp32_parity_mode": fp32_mode,
         }
         print(json.dumps(out))
     if dist is not None:

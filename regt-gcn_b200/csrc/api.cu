@@ -47,9 +47,9 @@ Layout make_layout(const regt_args* a, void* base) {
     L.Hcp = c.take<float>(plane);
     L.dhp_p = c.take<float>(a->mode == REGT_MODE_REGIONAL ? plane : 4);
     L.Xt = c.take<float>(BN * F * T);
-    L.hid_part = c.take<float>(T * BN * H);
+    L.hid_part = c.take<float>(T * nqt * 128 * H);
     L.tc_wpart = c.take<float>((size_t)TC_MAX_CTAS * 128 * 192);
-    L.tc_dpp = c.take<float>(T * nqt + 64);
+    L.tc_dpp = c.take<float>(T * TC_MAX_CTAS + 64);   // one attention-gradient partial per (CTA, period)
   }
   L.a1 = c.take<float>(BN * HEAD_HID);
   L.G = c.take<float>(((BN + 127) / 128) * 128 * H);   // padded: the tensor-core backward reads whole 128-row tiles

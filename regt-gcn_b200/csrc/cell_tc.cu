@@ -448,19 +448,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* W = smem;                                   // weight image (tiles + consts)
   uint8_t* Ah = W + ((Cfg::FWD_IMG + 1023) & ~1023);   // [NSPLIT][128 x HH]
-  uint8_t* SMf = Ah + Cfg::NSPLIT * Cfg::A_TILE;       // [NBUF] small tiles  S(+pad) | X | U
-  __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c, bar_img, bar_x, bar_h;
+  uint8_t* Ah2 = Cfg::PIPE ? Ah + Cfg::NSPLIT * Cfg::A_TILE : Ah;   // h*R operand tile (own buffer when pipelined)
+  uint8_t* SMf = Ah2 + Cfg::NSPLIT * Cfg::A_TILE;      // [NBUF] small tiles  S(+pad) | X | U
+  __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c, bar_img, bar_h;
+  __shared__ uint64_t bar_x[2];   // per small-tile buffer, like bar_free: tile written / tile consumed
+  // bar_free[b]: completes once per use of small-tile buffer b (the MMAs that read it are done).  The
+  // loader waits on it instead of bar_c: a waiter may lag an mbarrier by at most ONE phase, and only
+  // a per-buffer barrier guarantees that (its next phase needs the loader's own next tile).
+  __shared__ uint64_t bar_free[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[240] = clock64();
 
   if (tid == 0) {
-    mbar_init(&bar_a, NEPI);
+    mbar_init(&bar_free[0], 1);
+    mbar_init(&bar_free[1], 1);
+    mbar_init(&bar_a, NEPI_WARPS);
     mbar_init(&bar_zr, 1);
-    mbar_init(&bar_a2, NEPI);
+    mbar_init(&bar_a2, NEPI_WARPS);
     mbar_init(&bar_c, 1);
     mbar_init(&bar_img, 1);
-    mbar_init(&bar_x, 1);
+    mbar_init(&bar_x[0], 1);
+    mbar_init(&bar_x[1], 1);
     mbar_init(&bar_h, 1);
     fence_barrier_init();
     // weight image -> shared memory with the bulk-copy engine (16 KB pieces)
@@ -472,7 +481,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  mbar_wait(&bar_img, 0);
+  // the loader warp does not read the weight image: it starts on the first tile while the image lands
+  if (warp != WARP_LOAD) mbar_wait(&bar_img, 0);
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(W + Cfg::FWD_W);
   const bool hmma = a.hmma != 0;
@@ -488,97 +498,202 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
     RowInfo ri;
     float acc[CW];
     StepIt it;
-    for (int s = 0; s < S; ++s) {
-      const uint32_t ph = s & 1;
-      it.set(a, s);
-      const int qt = it.item / a.ntc;
-      if (it.ti == 0) {
-        ri.set(a, it.item, r, !hmma);
-#pragma unroll
-        for (int j = 0; j < CW; ++j) acc[j] = 0.f;
-      }
-      float h[CW];
-      REGT_TS(0)
+    // h of one step: from the tensor-core h_pre (single regional list) or on the CUDA cores
+    auto make_h = [&](const StepIt& st_, uint32_t ph_, float (&h_)[CW]) {
       if (hmma) {
-        mbar_wait(&bar_h, ph);
+        mbar_wait(&bar_h, ph_);
         tc_fence_after();
-        tmem_ld<CW>(tlane + 3 * HH + c0, h);
+        tmem_ld<CW>(tlane + 3 * HH + c0, h_);
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-          const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
-          h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
+          const float v = h_[j] + consts[Cfg::C_C0 + c0 + j];
+          h_[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
         }
       } else {
         float sv[8];
-        compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, it.t, c0, h, sv);
+        compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, st_.t, c0, h_, sv);
       }
-      REGT_TS(1)
-      store_operand<FMT, HH>(Ah, r, c0, h);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&bar_a);
-
-      // ---- E1: gates ----
-      REGT_TS(2)
-      mbar_wait(&bar_zr, ph);
-      tc_fence_after();
-      REGT_TS(3)
-      float z[CW];
-      {
-        float raw[CW];
-        tmem_ld<CW>(tlane + c0, raw);
+    };
+    if constexpr (Cfg::PIPE) {
+      // Software-pipelined order (two operand tiles: Ah = h, Ah2 = h*R).  Per step s:
+      //   E1r  r gate -> R plane, h*R tile -> M2(s) starts        E1z  z gate -> Z plane (under M2)
+      //   P    h of step s+1 -> h tile -> M1(s+1) starts          E2   candidate, blend (under M1(s+1))
+      // so neither MMA's latency is exposed.
+      float h[CW], hn[CW];
+      if (S > 0) {
+        it.set(a, 0);
+        ri.set(a, it.item, r, !hmma);
+        make_h(it, 0u, hn);
+        store_operand<FMT, HH>(Ah, r, c0, hn);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive_warp(&bar_a);
+      }
+      for (int s = 0; s < S; ++s) {
+        const uint32_t ph = s & 1;
+        it.set(a, s);
+        const int qt = it.item / a.ntc;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) z[j] = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + c0 + j]);
-        PlaneIO<FMT, HH>::store(a.Zp, a.nqt, it.t, qt, r, c0, z);
-        tmem_ld<CW>(tlane + HH + c0, raw);
-        float hr[CW];
+        for (int j = 0; j < CW; ++j) h[j] = hn[j];
+        if (it.ti == 0) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          const float rg = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + HH + c0 + j]);
-          raw[j] = rg;
-          hr[j] = h[j] * rg;
+          for (int j = 0; j < CW; ++j) acc[j] = 0.f;
         }
-        PlaneIO<FMT, HH>::store(a.Rp, a.nqt, it.t, qt, r, c0, raw);
-        store_operand<FMT, HH>(Ah, r, c0, hr);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&bar_a2);
-
-      // ---- E2: candidate, blend, attention accumulation ----
-      REGT_TS(4)
-      mbar_wait(&bar_c, ph);
-      tc_fence_after();
-      REGT_TS(5)
-      {
-        float raw[CW];
-        tmem_ld<CW>(tlane + 2 * HH + c0, raw);
-        const float pt = consts[Cfg::C_PROBS + it.t];
+        REGT_TS(0)
+        mbar_wait(&bar_zr, ph);
+        tc_fence_after();
+        REGT_TS(1)
+        float z[CW];
+        {
+          float raw[CW], hr[CW];
+          tmem_ld<CW>(tlane + HH + c0, raw);
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          const float hc = fast_tanh<FMT>(raw[j] + consts[Cfg::C_CC + c0 + j]);
-          raw[j] = hc;
-          acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
+          for (int j = 0; j < CW; ++j) {
+            const float rg = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + HH + c0 + j]);
+            raw[j] = rg;
+            hr[j] = h[j] * rg;
+          }
+          store_operand<FMT, HH>(Ah2, r, c0, hr);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive_warp(&bar_a2);
+          PlaneIO<FMT, HH>::store(a.Rp, a.nqt, it.t, qt, r, c0, raw);
+          REGT_TS(2)
+          tmem_ld<CW>(tlane + c0, raw);
+#pragma unroll
+          for (int j = 0; j < CW; ++j) z[j] = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + c0 + j]);
+          PlaneIO<FMT, HH>::store(a.Zp, a.nqt, it.t, qt, r, c0, z);
         }
-        PlaneIO<FMT, HH>::store(a.Hcp, a.nqt, it.t, qt, r, c0, raw);
-      }
-      if (it.ti + 1 == a.tp && ri_valid(a, it.item, r)) {
-        const long long q = (long long)qt * TC_ROWS + r;
-        float* o = a.hid_part + ((size_t)(it.item % a.ntc) * a.BN + q) * HH + c0;
+        REGT_TS(3)
+        if (s + 1 < S) {   // h of the next step: M1(s) has finished reading the h tile (bar_zr above)
+          StepIt nx;
+          nx.set(a, s + 1);
+          if (nx.ti == 0) ri.set(a, nx.item, r, !hmma);
+          make_h(nx, (uint32_t)((s + 1) & 1), hn);
+          store_operand<FMT, HH>(Ah, r, c0, hn);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive_warp(&bar_a);
+        }
+        REGT_TS(4)
+        mbar_wait(&bar_c, ph);
+        tc_fence_after();
+        REGT_TS(5)
+        {
+          float raw[CW];
+          tmem_ld<CW>(tlane + 2 * HH + c0, raw);
+          const float pt = consts[Cfg::C_PROBS + it.t];
 #pragma unroll
-        for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          for (int j = 0; j < CW; ++j) {
+            const float hc = fast_tanh<FMT>(raw[j] + consts[Cfg::C_CC + c0 + j]);
+            raw[j] = hc;
+            acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
+          }
+          PlaneIO<FMT, HH>::store(a.Hcp, a.nqt, it.t, qt, r, c0, raw);
+        }
+        if (it.ti + 1 == a.tp) {   // item done: its partial attention sum, tile layout [chunk][qt][HH/4][128][4]
+          float4* o = reinterpret_cast<float4*>(a.hid_part) + ((size_t)(it.item % a.ntc) * a.nqt + qt) * (HH / 4) * TC_ROWS;
+#pragma unroll
+          for (int j = 0; j < CW; j += 4)
+            o[(size_t)((c0 + j) >> 2) * TC_ROWS + r] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+        REGT_TS(6)
+        ++dbg_n;
       }
-      REGT_TS(6)
-      ++dbg_n;
+      tc_fence_before();
+    } else {
+    for (int s = 0; s < S; ++s) {
+        const uint32_t ph = s & 1;
+        it.set(a, s);
+        const int qt = it.item / a.ntc;
+        if (it.ti == 0) {
+          ri.set(a, it.item, r, !hmma);
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+        }
+        float h[CW];
+        REGT_TS(0)
+        if (hmma) {
+          mbar_wait(&bar_h, ph);
+          tc_fence_after();
+          tmem_ld<CW>(tlane + 3 * HH + c0, h);
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
+            h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
+          }
+        } else {
+          float sv[8];
+          compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, it.t, c0, h, sv);
+        }
+        REGT_TS(1)
+        store_operand<FMT, HH>(Ah, r, c0, h);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive_warp(&bar_a);
+  
+        // ---- E1: gates ----
+        REGT_TS(2)
+        mbar_wait(&bar_zr, ph);
+        tc_fence_after();
+        REGT_TS(3)
+        float z[CW];
+        {
+          float raw[CW];
+          tmem_ld<CW>(tlane + c0, raw);
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) z[j] = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + c0 + j]);
+          PlaneIO<FMT, HH>::store(a.Zp, a.nqt, it.t, qt, r, c0, z);
+          tmem_ld<CW>(tlane + HH + c0, raw);
+          float hr[CW];
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float rg = fast_sigmoid<FMT>(raw[j] + consts[Cfg::C_CZR + HH + c0 + j]);
+            raw[j] = rg;
+            hr[j] = h[j] * rg;
+          }
+          PlaneIO<FMT, HH>::store(a.Rp, a.nqt, it.t, qt, r, c0, raw);
+          store_operand<FMT, HH>(Ah, r, c0, hr);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive_warp(&bar_a2);
+  
+        // ---- E2: candidate, blend, attention accumulation ----
+        REGT_TS(4)
+        mbar_wait(&bar_c, ph);
+        tc_fence_after();
+        REGT_TS(5)
+        {
+          float raw[CW];
+          tmem_ld<CW>(tlane + 2 * HH + c0, raw);
+          const float pt = consts[Cfg::C_PROBS + it.t];
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float hc = fast_tanh<FMT>(raw[j] + consts[Cfg::C_CC + c0 + j]);
+            raw[j] = hc;
+            acc[j] = fmaf(pt, z[j] * h[j] + (1.0f - z[j]) * hc, acc[j]);
+          }
+          PlaneIO<FMT, HH>::store(a.Hcp, a.nqt, it.t, qt, r, c0, raw);
+        }
+        if (it.ti + 1 == a.tp) {   // item done: its partial attention sum, tile layout [chunk][qt][HH/4][128][4]
+          float4* o = reinterpret_cast<float4*>(a.hid_part) + ((size_t)(it.item % a.ntc) * a.nqt + qt) * (HH / 4) * TC_ROWS;
+  #pragma unroll
+          for (int j = 0; j < CW; j += 4)
+            o[(size_t)((c0 + j) >> 2) * TC_ROWS + r] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+        REGT_TS(6)
+        ++dbg_n;
+      }
+      tc_fence_before();
     }
-    tc_fence_before();
   } else if (warp == WARP_MMA) {
     // ================= MMA issuer (one elected lane) =================
     const uint32_t idesc_zr = make_idesc(FMT, 128, 2 * HH, 0, 0), idesc_c = make_idesc(FMT, 128, HH, 0, 0);
-    const uint32_t ah = smem_u32(Ah), smf = smem_u32(SMf), w = smem_u32(W);
+    const uint32_t ah = smem_u32(Ah), ah2 = smem_u32(Ah2), smf = smem_u32(SMf), w = smem_u32(W);
     constexpr int XU = Cfg::SMF_XU_CHUNK * TC_ROWS * 16;             // offset of the X | U chunks
     if (S > 0) {  // the loader has built step 0's tile: h_pre of step 0
-      mbar_wait(&bar_x, 0);
+      mbar_wait(&bar_x[0], 0);
       tc_fence_after();
       if (lane == 0 && hmma) {
         issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
@@ -599,13 +714,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
       mbar_wait(&bar_a2, ph);
       tc_fence_after();
       if (lane == 0) {
-        issue_gate_mma<FMT, HH>(tmem + 2 * HH, ah, as, w + Cfg::WZR_H + Cfg::WZR_S,
+        issue_gate_mma<FMT, HH>(tmem + 2 * HH, ah2, as, w + Cfg::WZR_H + Cfg::WZR_S,
                                 w + Cfg::WZR_H + Cfg::WZR_S + Cfg::WC_H, HH, idesc_c);
         umma_commit(&bar_c);
+        umma_commit(&bar_free[s % NBUF]);
       }
       __syncwarp();
       if (s + 1 < S) {  // next period's small tile (built by the loader warp) -> its h_pre
-        mbar_wait(&bar_x, (s + 1) & 1);
+        mbar_wait(&bar_x[(s + 1) % NBUF], (uint32_t)(((s + 1) / NBUF) & 1));
         tc_fence_after();
         if (lane == 0 && hmma) {
           issue_h_mma<FMT, HH>(tmem + 3 * HH, smf + ((s + 1) % NBUF) * SMB + XU, Cfg::SMF_TILE, w + Cfg::OFF_W0, Cfg::FWD_SPLIT);
@@ -628,14 +744,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
       float sv[4][8], xv[4][8], uv[4][8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) load_feats(a, ri[k].valid, ri[k].q, ri[k].b, ri[k].s0, ri[k].s1, it.t, sv[k], xv[k], uv[k]);
-      // buffer s % NBUF was last read by the MMAs of step s - NBUF (gate MMAs complete at bar_c)
-      if (s >= NBUF) mbar_wait(&bar_c, (uint32_t)((s - NBUF) & 1));
+      // buffer s % NBUF was last read by the MMAs of step s - NBUF: use number s / NBUF - 1 of that buffer
+      if (s >= NBUF) mbar_wait(&bar_free[s % NBUF], (uint32_t)((s / NBUF - 1) & 1));
       uint8_t* sm = SMf + (s % NBUF) * SMB;
 #pragma unroll
       for (int k = 0; k < 4; ++k) write_small_fwd<FMT, HH>(sm, lane + 32 * k, sv[k], xv[k], uv[k]);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_x);
+      if (lane == 0) mbar_arrive(&bar_x[s % NBUF]);
     }
   }
   if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[241] = clock64();
@@ -644,13 +760,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   if (warp == WARP_MMA) tmem_dealloc(tmem, 256);
 }
 
-// out_hidden[q][j] = sum over the t-chunks of the per-item partial attention sums
-__global__ void k_hid_reduce(const float* __restrict__ part, int ntc, long long count, float* __restrict__ out) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i * 4 >= count) return;
+// out_hidden[q][j] = sum over the t-chunks of the per-item partial attention sums (tiled partials, see above)
+__global__ void k_hid_reduce(const float* __restrict__ part, int ntc, int nqt, int HH, long long BN, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // one float4 of out
+  const int h4 = HH >> 2;
+  if (i >= BN * h4) return;
+  const long long q = i / h4;
+  const int c4 = (int)(i - q * h4);
+  const size_t tile = (size_t)h4 * TC_ROWS;   // float4 per (chunk, qt) tile
+  const float4* p = reinterpret_cast<const float4*>(part) + (size_t)(q >> 7) * tile + (size_t)c4 * TC_ROWS + (q & 127);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = 0; c < ntc; ++c) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)c * count) + i);
+    const float4 v = __ldg(p + (size_t)c * nqt * tile);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   reinterpret_cast<float4*>(out)[i] = s;
@@ -729,7 +850,7 @@ static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st, bool
   if (forked && join_side(st)) return -1;   // the feature builder ran beside the weight collapse
   const int slots = num_sms();
   TcArgs k = make_tcargs(a, L, slots);
-  const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + Cfg::NSPLIT * Cfg::A_TILE +
+  const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + (Cfg::PIPE ? 2 : 1) * Cfg::NSPLIT * Cfg::A_TILE +
                       (Cfg::PIPE ? 2 : 1) * Cfg::NSPLIT * Cfg::SMF_TILE;
   REGT_CUDA(cudaFuncSetAttribute(k_cell_fwd_tc<FMT, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(slots, k.items);
@@ -737,7 +858,7 @@ static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st, bool
   REGT_LAUNCHED("k_cell_fwd_tc", st);
   if (!head_fusable(a)) {  // otherwise the fused head sums the partials while loading its tiles
     const long long count = (long long)k.BN * HH;
-    k_hid_reduce<<<cdiv(count / 4, 256), 256, 0, st>>>(L.hid_part, k.ntc, count, a->out_hidden);
+    k_hid_reduce<<<cdiv(count / 4, 256), 256, 0, st>>>(L.hid_part, k.ntc, k.nqt, HH, k.BN, a->out_hidden);
     REGT_LAUNCHED("k_hid_reduce", st);
   }
   return 0;
@@ -795,9 +916,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   uint8_t* SM = T_HR + TILE;                             // [2] small tiles (double-buffered)
   uint8_t* STG = SM + 2 * SMT;                           // staged Z | R | H~ tiles
   uint8_t* GS = STG + 3 * PT;                            // G tile of the current item
-  __shared__ uint64_t bar_stage, bar_g, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w, bar_img, bar_x, bar_h;
+  __shared__ uint64_t bar_stage, bar_g, bar_e0, bar_m1, bar_e1, bar_m2, bar_e2, bar_w, bar_img, bar_h;
+  // per small-tile buffer: tile written by the loader / tile consumed by the MMAs.  Per-buffer barriers keep
+  // every waiter within one phase of its barrier (a waiter two phases behind would block forever).
+  __shared__ uint64_t bar_x[2], bar_sfree[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[2][NEPI_WARPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[240] = clock64();
 
@@ -805,13 +928,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     mbar_init(&bar_img, 1);
     mbar_init(&bar_stage, 1);
     mbar_init(&bar_g, 1);
-    mbar_init(&bar_e0, NEPI);
+    mbar_init(&bar_e0, NEPI_WARPS);
     mbar_init(&bar_m1, 1);
-    mbar_init(&bar_e1, NEPI);
+    mbar_init(&bar_e1, NEPI_WARPS);
     mbar_init(&bar_m2, 1);
-    mbar_init(&bar_e2, NEPI);
+    mbar_init(&bar_e2, NEPI_WARPS);
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_x, 1);
+    mbar_init(&bar_x[0], 1);
+    mbar_init(&bar_x[1], 1);
+    mbar_init(&bar_sfree[0], 1);
+    mbar_init(&bar_sfree[1], 1);
     mbar_init(&bar_h, 1);
     fence_barrier_init();
     mbar_arrive_expect_tx(&bar_img, Cfg::BWD_IMG);
@@ -822,7 +948,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  mbar_wait(&bar_img, 0);
+  if (warp != WARP_LOAD) mbar_wait(&bar_img, 0);   // the loader warp does not read the weight image
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(W + Cfg::BWD_W);
   const bool hmma = a.hmma != 0;
@@ -836,29 +962,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     RowInfo ri;
     StepIt it;
+    float hn[CW];
+    float dpr0 = 0.f, dpr1 = 0.f;   // attention-gradient sums of periods lane and 32 + lane
+    // h of one step (recomputed, not saved): tensor-core h_pre (single regional list) or CUDA cores
+    auto make_h = [&](const StepIt& st_, uint32_t ph_, float (&h_)[CW]) {
+      if (hmma) {
+        mbar_wait(&bar_h, ph_);
+        tc_fence_after();
+        tmem_ld<CW>(tlane + 320 + c0, h_);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const float v = h_[j] + consts[Cfg::C_C0 + c0 + j];
+          h_[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
+        }
+      } else {
+        float sv[8];
+        compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, st_.t, c0, h_, sv);
+      }
+    };
+    if (S > 0) {
+      it.set(a, 0);
+      ri.set(a, it.item, r, !hmma);
+      make_h(it, 0u, hn);
+    }
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       it.set(a, s);
       const int qt = it.item / a.ntc;
       float h[CW], dh[CW], rr[CW];
-      REGT_TS(0)
-      if (it.ti == 0) {
-        ri.set(a, it.item, r, !hmma);
-        mbar_wait(&bar_g, (uint32_t)((s / a.tp) & 1));   // this item's G tile has landed in smem
-      }
-      if (hmma) {
-        mbar_wait(&bar_h, ph);
-        tc_fence_after();
-        tmem_ld<CW>(tlane + 320 + c0, h);
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          const float v = h[j] + consts[Cfg::C_C0 + c0 + j];
-          h[j] = (a.mode == REGT_MODE_REGIONAL) ? (v > 0.f ? v : 0.01f * v) : v;
-        }
-      } else {
-        float sv[8];
-        compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, it.t, c0, h, sv);
-      }
+      for (int j = 0; j < CW; ++j) h[j] = hn[j];
+      const bool row_valid = ri.valid;   // ri moves on to the next item before this step ends
+      REGT_TS(0)
+      if (it.ti == 0) mbar_wait(&bar_g, (uint32_t)((s / a.tp) & 1));   // this item's G tile has landed in smem
       const float pt = consts[Cfg::C_PROBS + it.t];
       float dp = 0.f;
       REGT_TS(1)
@@ -871,7 +1007,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
 #pragma unroll
         for (int j = 0; j < CW; j += 4) {
           float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);   // rows past B*N: the padded part of G is never written
-          if (ri.valid) g4 = reinterpret_cast<const float4*>(GS)[((c0 + j) / 4) * TC_ROWS + r];
+          if (row_valid) g4 = reinterpret_cast<const float4*>(GS)[((c0 + j) / 4) * TC_ROWS + r];
           const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -885,16 +1021,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
           }
         }
         if (s > 0) mbar_wait(&bar_w, (uint32_t)((s - 1) & 1));  // previous step's MMAs released the tiles
-        store_operand<FMT, HH>(T_DZ, r, c0, z);
         store_operand<FMT, HH>(T_DH, r, c0, hc);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive_warp(&bar_e0);        // M1 needs Dh only: it runs under the remaining tile stores
+        store_operand<FMT, HH>(T_DZ, r, c0, z);
 #pragma unroll
         for (int j = 0; j < CW; ++j) z[j] = h[j] * rr[j];
         store_operand<FMT, HH>(T_HR, r, c0, z);
-        store_operand<FMT, HH>(T_H, r, c0, h);
+        store_operand<FMT, HH>(T_H, r, c0, h);   // made visible to the tensor core by the fence before bar_e1
       }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&bar_e0);
       REGT_TS(2)
 
       // ---- E1 ----
@@ -914,7 +1050,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_e1);
+      mbar_arrive_warp(&bar_e1);
+      if (s + 1 < S) {   // h of the next step, under M2 of this one (its h_pre MMA was issued right after M1)
+        StepIt nx;
+        nx.set(a, s + 1);
+        if (nx.ti == 0) ri.set(a, nx.item, r, !hmma);
+        make_h(nx, (uint32_t)((s + 1) & 1), hn);
+      }
       REGT_TS(4)
 
       // ---- E2 ----
@@ -935,22 +1077,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_e2);
+      mbar_arrive_warp(&bar_e2);
       REGT_TS(6)
 
       // ---- attention gradient partial: fixed-order block reduction ----
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) dp += __shfl_down_sync(0xffffffffu, dp, d);
-      if (lane == 0) red[s & 1][warp] = dp;
-      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
-      if (tid == 0) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int w8 = 0; w8 < NEPI_WARPS; ++w8) sacc += red[s & 1][w8];
-        a.dprobs_part[(size_t)qt * a.T + it.t] = sacc;
+      for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
+      // per-warp running sum of period t lives in a register of lane t % 32 (fixed order, no block
+      // barrier per step); combined once per CTA after the loop
+      if (lane == (it.t & 31)) {
+        if (it.t < 32) dpr0 += dp;
+        else dpr1 += dp;
       }
       REGT_TS(7)
       ++dbg_n;
+    }
+    // ---- attention-gradient partial of this CTA: fixed-order sum over the epilogue warps ----
+    {
+      float* dpacc = reinterpret_cast<float*>(STG);   // the plane staging area is free: every prefetch was consumed
+      dpacc[warp * 64 + lane] = dpr0;
+      dpacc[warp * 64 + 32 + lane] = dpr1;
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+      if (tid < a.T) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < NEPI_WARPS; ++w8) sacc += dpacc[w8 * 64 + tid];
+        a.dprobs_part[(size_t)blockIdx.x * a.T + tid] = sacc;
+      }
     }
     // ---- flush the persistent weight-gradient accumulators ----
     mbar_wait(&bar_w, (uint32_t)((S - 1) & 1));
@@ -1000,7 +1153,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
         prefetch(it);
         fetch_g(it.item);
       }
-      mbar_wait(&bar_x, 0);
+      mbar_wait(&bar_x[0], 0);
       tc_fence_after();
       if (lane == 0 && hmma) {
         issue_h_mma<FMT, HH>(tmem + 320, sm0 + XU, 0, w + 3 * Cfg::BT, 0);
@@ -1018,19 +1171,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       mbar_wait(&bar_e0, ph);
       tc_fence_after();
       if (lane == 0) {
-        // this step's staged planes (and, on its last period, the item's G tile) are consumed
-        if (more) {
-          prefetch(nx);
-          if (nx.ti == 0) fetch_g(nx.item);
-        }
         // M1: dHR = Dh . B_h
 #pragma unroll
         for (int k = 0; k < HH / 16; ++k)
           umma<FMT>(tmem, make_desc(tdh + k * 32, 16, 1024, LAYOUT_SW128),
                     make_desc(w + 2 * Cfg::BT + k * 32, 16, 1024, LAYOUT_SW128), id_dg, k > 0 ? 1u : 0u);
         umma_commit(&bar_m1);
+        // this step's staged planes (and, on its last period, the item's G tile) are consumed
+        if (more) {
+          prefetch(nx);
+          if (nx.ti == 0) fetch_g(nx.item);
+        }
       }
       __syncwarp();
+      if (more) {  // next period's h_pre from the tile the loader warp has built (read by the epilogue under M2)
+        mbar_wait(&bar_x[(s + 1) & 1], (uint32_t)(((s + 1) >> 1) & 1));
+        tc_fence_after();
+        if (lane == 0 && hmma) {
+          issue_h_mma<FMT, HH>(tmem + 320, sm0 + ((s + 1) & 1) * SMT + XU, 0, w + 3 * Cfg::BT, 0);
+          umma_commit(&bar_h);
+        }
+        __syncwarp();
+      }
       mbar_wait(&bar_e1, ph);
       tc_fence_after();
       if (lane == 0) {
@@ -1046,15 +1208,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
         umma_commit(&bar_m2);
       }
       __syncwarp();
-      if (more) {  // next period's h_pre from the tile the loader warp has built
-        mbar_wait(&bar_x, (uint32_t)((s + 1) & 1));
-        tc_fence_after();
-        if (lane == 0 && hmma) {
-          issue_h_mma<FMT, HH>(tmem + 320, sm0 + ((s + 1) & 1) * SMT + XU, 0, w + 3 * Cfg::BT, 0);
-          umma_commit(&bar_h);
-        }
-        __syncwarp();
-      }
       if (lane == 0) {
         // W1 / W1s: [Dz|Dr]^T . h , [Dz|Dr]^T . [S|X|U|1]   (contraction over the 128 rows)
 #pragma unroll
@@ -1076,6 +1229,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
           umma<FMT>(tmem + 288, da, make_desc(sm + k * 256, 128, TC_ROWS * 16, LAYOUT_NONE), id_ws, (k > 0) ? 1u : accw);
         }
         umma_commit(&bar_w);
+        umma_commit(&bar_sfree[s & 1]);
       }
       __syncwarp();
     }
@@ -1093,7 +1247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       float sv[4][8], xv[4][8], uv[4][8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) load_feats(a, ri[k].valid, ri[k].q, ri[k].b, ri[k].s0, ri[k].s1, it.t, sv[k], xv[k], uv[k]);
-      if (s >= 2) mbar_wait(&bar_w, (uint32_t)((s - 2) & 1));   // W1s / W2s of step s-2 were the last readers
+      if (s >= 2) mbar_wait(&bar_sfree[s & 1], (uint32_t)(((s >> 1) - 1) & 1));   // W1s / W2s of step s-2 were the last readers
       uint8_t* sm = SM + (s & 1) * SMT;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -1105,7 +1259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_x);
+      if (lane == 0) mbar_arrive(&bar_x[s & 1]);
     }
   }
   if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[241] = clock64();
@@ -1215,7 +1369,7 @@ int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
   if (side && join_side(st)) return -1;
   const int R = a->plan.R;
   k_tc_wreduce<<<cdiv(TC_ROWS * WP_COLS + a->T, 32), dim3(32, 8), 0, st>>>(L.tc_wpart, grid, HH, R, L.dB, L.dP, L.dcg, L.dM0, L.dM1,
-                                                                     L.dc0, L.tc_dpp, k.nqt, a->T, L.dprobs);
+                                                                     L.dc0, L.tc_dpp, grid, a->T, L.dprobs);
   REGT_LAUNCHED("k_tc_wreduce", st);
   if (a->mode == REGT_MODE_REGIONAL && R > 1) {
     const int zs = (int)max(1ll, min(64ll, 1024ll / R));

@@ -54,12 +54,12 @@ struct TcArgs {
   const float* M1t;        // [R][F][H] fp32 (global; region 0 is also in the image)
   const uint8_t* img;      // weight image
   float *Zp, *Rp, *Hcp;    // saved planes, tile layout [T][nqt][H/4][128][4]
-  float* hid_part;         // [ntc][BN][H]
+  float* hid_part;         // [ntc][nqt][H/4][128][4] per-chunk partial attention sums (tiled like G)
   // backward
   const float* G;          // [BN][H]
   float* dhp;              // d h_pre plane [T][nqt][H/4][128][4] (regional wgrad of M1)
   float* wpart;            // [grid][...] per-CTA weight-gradient partials
-  float* dprobs_part;      // [items][tp]
+  float* dprobs_part;      // [grid][T]
   long long* dbg;          // optional phase timestamps (REGT_TC_DEBUG)
 };
 

@@ -114,7 +114,7 @@ struct Layout {
   unsigned char* tc_img_b;   // backward weight image
   float *Zp, *Rp, *Hcp, *dhp_p;  // [T][nqt][H/4][128][4]
   float* Xt;                 // [T][BN][F] period-major copy of x (S and U are period-major too)
-  float* hid_part;           // [T (max t-chunks)][BN][H]
+  float* hid_part;           // [T (max t-chunks)][nqt][H/4][128][4]
   float* tc_wpart;           // [TC_MAX_CTAS][TC_WPART_FLOATS]
   float* tc_dpp;             // [T * nqt] attention-gradient partials
   size_t total;

@@ -15,8 +15,8 @@ struct HeadK {
   const float *w1, *w2;                        // natural layouts for the data gradients
   const float* d_hidden;
   float *a1, *out, *d_out, *loss_part, *d_a1, *G;
-  const float* hid_part;  // tensor-core cell: [ntc][BN][H] partial attention sums (NULL: hid is final)
-  int ntc;
+  const float* hid_part;  // tensor-core cell: [ntc][nqt][H/4][128][4] partial attention sums (NULL: hid is final)
+  int ntc, nqt;
   float* hid_out;         // where the summed out_hidden goes when hid_part is used
   int g_tiled;            // 1: G is written as [qt][H/4][128][4] tiles (tensor-core backward), 0: row-major
 };
@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(256, 1) k_head_fused(HeadK a, float* __restric
       if (q0 + rl < a.BN) {
         if (a.hid_part) {  // sum the per-chunk attention partials of the tensor-core cell (fixed order)
           for (int c = 0; c < a.ntc; ++c) {
-            const float4 p = __ldg(reinterpret_cast<const float4*>(a.hid_part + ((size_t)c * a.BN + q0 + rl) * H) + c4);
+            const long long q = q0 + rl;   // tiled partials [chunk][qt][H/4][128][4]
+            const float4 p = __ldg(reinterpret_cast<const float4*>(a.hid_part) +
+                                   (((size_t)c * a.nqt + (size_t)(q >> 7)) * (H / 4) + c4) * 128 + (q & 127));
             v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
           }
           reinterpret_cast<float4*>(a.hid_out + (q0 + rl) * H)[c4] = v;
@@ -437,6 +439,7 @@ static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* 
   if (a->precision != REGT_PREC_FP32 && head_fusable(a)) {  // the cell left per-chunk partials (see cell_tc.cu)
     k.hid_part = L.hid_part;
     k.ntc = tc_num_chunks(a);
+    k.nqt = (int)((k.BN + 127) / 128);
   }
   return k;
 }

@@ -45,7 +45,7 @@ struct HeadTcArgs {
   int O, ntc, nqt;
   float scale;
   const float *w1, *w2, *b1, *b2;        // linear1.weight [128][64], linear2.weight [O][128]
-  const float* hid_part;                 // [ntc][BN][64] attention partials of the cell (NULL: hid_in is final)
+  const float* hid_part;                 // [ntc][nqt][16][128][4] attention partials of the cell (NULL: hid_in is final)
   const float* hid_in;
   float* hid_out;                        // out_hidden [BN][64]
   const float* y;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
   const int O = a.O;
 
   if (tid == 0) {
-    mbar_init(&bar_a0, NEPI); mbar_init(&bar_a1, NEPI); mbar_init(&bar_a2, NEPI); mbar_init(&bar_a3, NEPI);
+    mbar_init(&bar_a0, NEPI_WARPS); mbar_init(&bar_a1, NEPI_WARPS); mbar_init(&bar_a2, NEPI_WARPS); mbar_init(&bar_a3, NEPI_WARPS);
     mbar_init(&bar_m1, 1); mbar_init(&bar_m2, 1); mbar_init(&bar_m3, 1); mbar_init(&bar_m4, 1); mbar_init(&bar_w, 1);
     fence_barrier_init();
   }
@@ -121,11 +121,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
         if (valid) {
           if (a.hid_part) {
-            for (int c = 0; c < a.ntc; ++c) {   // fixed order: deterministic
-              const float4* p = reinterpret_cast<const float4*>(a.hid_part + ((size_t)c * a.BN + q) * HH + ch * 32);
+            for (int c = 0; c < a.ntc; ++c) {   // fixed order: deterministic; tiled partials [chunk][qt][HH/4][128][4]
+              const float4* p = reinterpret_cast<const float4*>(a.hid_part) +
+                                (((size_t)c * a.nqt + qt) * (HH / 4) + ch * 8) * TC_ROWS + r;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg(p + j);
+                const float4 t = __ldg(p + (size_t)j * TC_ROWS);
                 v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
               }
             }
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_a0);
+      mbar_arrive_warp(&bar_a0);
 
       // ---- P1: a1 = relu(a1_pre + b1), 64 columns ----
       uint32_t amask[2];
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_a1);
+      mbar_arrive_warp(&bar_a1);
 
       // ---- P2: out, loss, d_out (8 of the 16 padded outputs per thread) ----
       mbar_wait(&bar_m2, ph);
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_a2);
+      mbar_arrive_warp(&bar_a2);
 
       // ---- P3: d a1 = da1_pre * (a1 > 0), 64 columns ----
       mbar_wait(&bar_m3, ph);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bar_a3);
+      mbar_arrive_warp(&bar_a3);
 
       // ---- P4: G = G_pre * (hid > 0) (+ d_hidden), 32 columns, tiled layout [qt][HH/4][128][4] ----
       mbar_wait(&bar_m4, ph);

@@ -56,6 +56,27 @@ __global__ void __launch_bounds__(256) k_spmm_rows(const int32_t* __restrict__ r
   }
 }
 
+// NB neighbour rows of one batch: lane metadata (column, weight) is broadcast by shuffle; slots past
+// the end of the row re-read the row's last neighbour with weight 0 (acc + 0*v leaves acc unchanged),
+// so the loads are unconditional and issue back to back.  Sums stay in sequential CSR order.
+template <int NB>
+__device__ __forceinline__ void gather_batch(const float4* __restrict__ xb, int W4, int c, int mycol, float myval, int j,
+                                             float4& acc) {
+  float4 v[NB];
+  float wv[NB];
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    const int cu = __shfl_sync(0xffffffffu, mycol, (j + u) & 31);
+    wv[u] = __shfl_sync(0xffffffffu, myval, (j + u) & 31);
+    v[u] = __ldg(xb + (size_t)cu * W4 + c);
+  }
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    acc.x = fmaf(wv[u], v[u].x, acc.x); acc.y = fmaf(wv[u], v[u].y, acc.y);
+    acc.z = fmaf(wv[u], v[u].z, acc.z); acc.w = fmaf(wv[u], v[u].w, acc.w);
+  }
+}
+
 // Feature builder of the tensor-core path: the same warp-per-row gather, but the results are written
 // period-major so that one (tile, period) of the cell kernels reads contiguous 32-byte rows:
 //   Xt[t][q][F] = x[q][:, t]      St[t][q][F] = (A_hat x)[q][:, t]      Ut[t][b*nseg+s][F] = (L_hat_r x) per segment
@@ -82,31 +103,35 @@ __global__ void __launch_bounds__(256) k_feat_tc(const int32_t* __restrict__ g_r
   const int e0 = rowptr[r], e1 = rowptr[r + 1];
   const long long plane_rows = is_seg ? BS : BN;
   float* dst = is_seg ? Ut : St;
-  for (int c = lane; c < W4; c += 32) {   // lane c owns float4 #c of the F*T-wide row (coalesced 128-bit gathers)
+  // lane c owns float4 #c of the F*T-wide row (coalesced 128-bit gathers).  The row's edge metadata is
+  // read ONCE, 32 entries per coalesced load, and broadcast by shuffle, so that all neighbour gathers of
+  // a batch are in flight together (two dependent memory rounds per row instead of one per 4 edges).
+  for (int cb = 0; cb < W4; cb += 32) {   // warp-uniform trip count (the shuffles need every lane)
+    const bool live = cb + lane < W4;
+    const int c = live ? cb + lane : W4 - 1;          // idle lanes shadow the last float4 (loads stay unconditional)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int e = e0;
-    for (; e + 4 <= e1; e += 4) {
-      float4 v[4];
-      float wv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        wv[u] = __ldg(val + e + u);
-        v[u] = __ldg(xb + (size_t)__ldg(col + e + u) * W4 + c);
+    float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!is_seg) self = __ldg(xb + (size_t)r * W4 + c);
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int n = min(32, e1 - eb);
+      const int mycol = __ldg(col + eb + min(lane, n - 1));
+      const float myval = lane < n ? __ldg(val + eb + lane) : 0.f;   // weight 0 past the end of the row
+      int j = 0;
+      while (j < n) {   // batches of 8 (or a final 4): every gather of a batch is in flight at once
+        if (n - j > 4) {
+          gather_batch<8>(xb, W4, c, mycol, myval, j, acc);
+          j += 8;
+        } else {
+          gather_batch<4>(xb, W4, c, mycol, myval, j, acc);
+          j += 4;
+        }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc.x = fmaf(wv[u], v[u].x, acc.x); acc.y = fmaf(wv[u], v[u].y, acc.y);
-        acc.z = fmaf(wv[u], v[u].z, acc.z); acc.w = fmaf(wv[u], v[u].w, acc.w);
-      }
-    }
-    for (; e < e1; ++e) {
-      const float wv = __ldg(val + e);
-      const float4 v = __ldg(xb + (size_t)__ldg(col + e) * W4 + c);
-      acc.x = fmaf(wv, v.x, acc.x); acc.y = fmaf(wv, v.y, acc.y); acc.z = fmaf(wv, v.z, acc.z); acc.w = fmaf(wv, v.w, acc.w);
     }
     // stage the row in shared memory so that the period-major write is one 32-byte row per lane
-    reinterpret_cast<float4*>(stage)[c] = acc;
-    if (!is_seg) reinterpret_cast<float4*>(stage + W)[c] = __ldg(xb + (size_t)r * W4 + c);
+    if (live) {
+      reinterpret_cast<float4*>(stage)[c] = acc;
+      if (!is_seg) reinterpret_cast<float4*>(stage + W)[c] = self;
+    }
   }
   __syncwarp();
   for (int t = lane; t < T; t += 32) {   // lane t gathers its 8 features (stride T) and writes 2 x float4

@@ -1,0 +1,104 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol
+that include/regt_b200.h declares (no compute calls), the ctypes structs mirror the header, the host-side
+argument checks fail loudly, and the product package never imports the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "regt_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(regt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from regt_b200 import _lib
+    lib = _lib.load()                      # builds with nvcc if missing; dlopen needs no GPU
+    names = _declared_functions()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/regt_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= set(names)
+    assert lib.regt_version() == 100
+    assert lib.regt_last_error() is not None
+
+
+def test_ctypes_structs_mirror_header():
+    from regt_b200 import _lib
+    src = open(HEADER).read()
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                name = re.sub(r"\[.*?\]", "", part.strip().split()[-1].lstrip("*"))
+                out.append(name)
+        return out
+    assert fields("regt_graph_plan") == [f[0] for f in _lib.GraphPlan._fields_]
+    assert fields("regt_params") == [f[0] for f in _lib.Params._fields_]
+    assert fields("regt_args") == [f[0] for f in _lib.Args._fields_]
+    # layout: 12 leading int32, then the plan (8-byte aligned)
+    assert _lib.Args.plan.offset == 48 and C.sizeof(_lib.GraphPlan) == 24 + 13 * 8
+
+
+def test_null_args_and_missing_workspace_are_rejected_without_a_gpu():
+    from regt_b200 import _lib
+    lib = _lib.load()
+    assert lib.regt_cell_forward(None) != 0
+    assert b"NULL" in lib.regt_last_error()
+    a = _lib.Args()
+    a.B, a.N, a.T, a.H, a.O = 1, 4, 2, 8, 1
+    a.plan.N = 4
+    assert lib.regt_cell_forward(C.byref(a)) != 0           # no workspace: refused before any launch
+    assert b"workspace" in lib.regt_last_error()
+    a.H = 7
+    assert lib.regt_cell_forward(C.byref(a)) != 0 and b"multiple of 8" in lib.regt_last_error()
+    assert lib.regt_workspace_bytes(C.byref(a)) > 0
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from models import TemporalGCN
+    m = TemporalGCN(8, 3, 2, hidden=16)
+    x = torch.rand(5, 8, 3)
+    ei = torch.tensor([[0, 1, 2], [1, 2, 3]])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(x, ei, torch.ones(3))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "regt-gcn_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)
+
+
+def test_reference_state_dict_keys():
+    """the 26 keys of the shipped checkpoints, on the drop-in module."""
+    from models import RegionalTemporalGCN
+    m = RegionalTemporalGCN(8, 104, 6, 1)
+    keys = set(m.state_dict().keys())
+    want = {"tgnn._attention", "tgnn._weight_att1", "tgnn._weight_att2", "tgnn._bias_att1", "tgnn._bias_att2",
+            "tgnn.conv.bias", "tgnn.conv.lins.0.weight", "tgnn.conv.lins.1.weight", "tgnn.linear.weight", "tgnn.linear.bias",
+            "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"}
+    for g in "zrh":
+        want |= {f"tgnn._base_tgcn.conv_{g}.bias", f"tgnn._base_tgcn.conv_{g}.lin.weight",
+                 f"tgnn._base_tgcn.linear_{g}.weight", f"tgnn._base_tgcn.linear_{g}.bias"}
+    assert keys == want and len(keys) == 26
+    assert tuple(m.state_dict()["tgnn.linear.weight"].shape) == (256, 1280)
+    ref = "/root/reference/pretrained/occrate/RegionalTemporalGCN/model_in6_out1_epoch50.pt"
+    if os.path.exists(ref):
+        m.load_state_dict(torch.load(ref, map_location="cpu"), strict=True)
