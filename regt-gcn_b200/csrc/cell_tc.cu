@@ -17,10 +17,25 @@
 #include "cell_tc.cuh"
 #include "gemm_simt.cuh"
 
+// build-time switches of the pipeline experiments (tools/build_variants.py + tools/gpu_ab.sh; measured on
+// B200 at config 2, profiles/r01_ab_variants.txt; defaults = the fastest measured)
+#ifndef REGT_FWD_PIPE
+#define REGT_FWD_PIPE 0      // 1: software-pipelined forward epilogue (bf16), 0: one phase after the other (A/B: 38 vs 46 us)
+#endif
+#ifndef REGT_BWD_H_UNDER_M2
+#define REGT_BWD_H_UNDER_M2 0  // 1: h of step s+1 is produced while M2 of step s runs (A/B: no gain)
+#endif
+#ifndef REGT_BWD_EARLY_E0
+#define REGT_BWD_EARLY_E0 1  // 1: M1 starts as soon as the Dh tile is stored (A/B: 62.7 vs 65.5 us)
+#endif
+#ifndef REGT_CW
+#define REGT_CW 32
+#endif
+
 namespace regt {
 using namespace tc;
 constexpr int F = REGT_F;
-constexpr int CW = 32;                    // columns owned by one epilogue thread
+constexpr int CW = REGT_CW;                    // columns owned by one epilogue thread
 constexpr int NEPI_WARPS = 4 * (64 / CW);  // 4 lane quarters x column groups (hidden = 64)
 constexpr int NEPI = NEPI_WARPS * 32;      // epilogue threads
 constexpr int WARP_MMA = NEPI_WARPS;       // issues every tcgen05.mma (one elected lane) + bulk prefetches
@@ -448,7 +463,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* W = smem;                                   // weight image (tiles + consts)
   uint8_t* Ah = W + ((Cfg::FWD_IMG + 1023) & ~1023);   // [NSPLIT][128 x HH]
-  uint8_t* Ah2 = Cfg::PIPE ? Ah + Cfg::NSPLIT * Cfg::A_TILE : Ah;   // h*R operand tile (own buffer when pipelined)
+  constexpr bool PIPE2 = Cfg::PIPE && REGT_FWD_PIPE;   // software-pipelined epilogue: h and h*R tiles are separate
+  uint8_t* Ah2 = PIPE2 ? Ah + Cfg::NSPLIT * Cfg::A_TILE : Ah;   // h*R operand tile (own buffer when pipelined)
   uint8_t* SMf = Ah2 + Cfg::NSPLIT * Cfg::A_TILE;      // [NBUF] small tiles  S(+pad) | X | U
   __shared__ uint64_t bar_a, bar_zr, bar_a2, bar_c, bar_img, bar_h;
   __shared__ uint64_t bar_x[2];   // per small-tile buffer, like bar_free: tile written / tile consumed
@@ -463,9 +479,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
   if (tid == 0) {
     mbar_init(&bar_free[0], 1);
     mbar_init(&bar_free[1], 1);
-    mbar_init(&bar_a, NEPI_WARPS);
+    mbar_init(&bar_a, NEPI_WARPS * ARRIVALS_PER_WARP);
     mbar_init(&bar_zr, 1);
-    mbar_init(&bar_a2, NEPI_WARPS);
+    mbar_init(&bar_a2, NEPI_WARPS * ARRIVALS_PER_WARP);
     mbar_init(&bar_c, 1);
     mbar_init(&bar_img, 1);
     mbar_init(&bar_x[0], 1);
@@ -514,7 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_fwd_tc(TcArgs a) {
         compute_h<HH>(a, consts, ri.valid, ri.q, ri.b, ri.s0, ri.s1, st_.t, c0, h_, sv);
       }
     };
-    if constexpr (Cfg::PIPE) {
+    if constexpr (PIPE2) {
       // Software-pipelined order (two operand tiles: Ah = h, Ah2 = h*R).  Per step s:
       //   E1r  r gate -> R plane, h*R tile -> M2(s) starts        E1z  z gate -> Z plane (under M2)
       //   P    h of step s+1 -> h tile -> M1(s+1) starts          E2   candidate, blend (under M1(s+1))
@@ -850,7 +866,7 @@ static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st, bool
   if (forked && join_side(st)) return -1;   // the feature builder ran beside the weight collapse
   const int slots = num_sms();
   TcArgs k = make_tcargs(a, L, slots);
-  const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + (Cfg::PIPE ? 2 : 1) * Cfg::NSPLIT * Cfg::A_TILE +
+  const size_t smem = 1024 + ((Cfg::FWD_IMG + 1023) & ~1023) + ((Cfg::PIPE && REGT_FWD_PIPE) ? 2 : 1) * Cfg::NSPLIT * Cfg::A_TILE +
                       (Cfg::PIPE ? 2 : 1) * Cfg::NSPLIT * Cfg::SMF_TILE;
   REGT_CUDA(cudaFuncSetAttribute(k_cell_fwd_tc<FMT, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(slots, k.items);
@@ -928,11 +944,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     mbar_init(&bar_img, 1);
     mbar_init(&bar_stage, 1);
     mbar_init(&bar_g, 1);
-    mbar_init(&bar_e0, NEPI_WARPS);
+    mbar_init(&bar_e0, NEPI_WARPS * ARRIVALS_PER_WARP);
     mbar_init(&bar_m1, 1);
-    mbar_init(&bar_e1, NEPI_WARPS);
+    mbar_init(&bar_e1, NEPI_WARPS * ARRIVALS_PER_WARP);
     mbar_init(&bar_m2, 1);
-    mbar_init(&bar_e2, NEPI_WARPS);
+    mbar_init(&bar_e2, NEPI_WARPS * ARRIVALS_PER_WARP);
     mbar_init(&bar_w, 1);
     mbar_init(&bar_x[0], 1);
     mbar_init(&bar_x[1], 1);
@@ -983,15 +999,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
     if (S > 0) {
       it.set(a, 0);
       ri.set(a, it.item, r, !hmma);
-      make_h(it, 0u, hn);
+      if (REGT_BWD_H_UNDER_M2) make_h(it, 0u, hn);
     }
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       it.set(a, s);
       const int qt = it.item / a.ntc;
       float h[CW], dh[CW], rr[CW];
+      if (REGT_BWD_H_UNDER_M2) {
 #pragma unroll
-      for (int j = 0; j < CW; ++j) h[j] = hn[j];
+        for (int j = 0; j < CW; ++j) h[j] = hn[j];
+      } else {
+        if (it.ti == 0 && s > 0) ri.set(a, it.item, r, !hmma);
+        make_h(it, ph, h);
+      }
       const bool row_valid = ri.valid;   // ri moves on to the next item before this step ends
       REGT_TS(0)
       if (it.ti == 0) mbar_wait(&bar_g, (uint32_t)((s / a.tp) & 1));   // this item's G tile has landed in smem
@@ -1022,14 +1043,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
         }
         if (s > 0) mbar_wait(&bar_w, (uint32_t)((s - 1) & 1));  // previous step's MMAs released the tiles
         store_operand<FMT, HH>(T_DH, r, c0, hc);
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive_warp(&bar_e0);        // M1 needs Dh only: it runs under the remaining tile stores
+        if (REGT_BWD_EARLY_E0) {
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive_warp(&bar_e0);        // M1 needs Dh only: it runs under the remaining tile stores
+        }
         store_operand<FMT, HH>(T_DZ, r, c0, z);
 #pragma unroll
         for (int j = 0; j < CW; ++j) z[j] = h[j] * rr[j];
         store_operand<FMT, HH>(T_HR, r, c0, z);
         store_operand<FMT, HH>(T_H, r, c0, h);   // made visible to the tensor core by the fence before bar_e1
+        if (!REGT_BWD_EARLY_E0) {
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive_warp(&bar_e0);
+        }
       }
       REGT_TS(2)
 
@@ -1051,7 +1079,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_cell_bwd_tc(TcArgs a) {
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive_warp(&bar_e1);
-      if (s + 1 < S) {   // h of the next step, under M2 of this one (its h_pre MMA was issued right after M1)
+      if (REGT_BWD_H_UNDER_M2 && s + 1 < S) {   // h of the next step, under M2 of this one (its h_pre MMA was issued right after M1)
         StepIt nx;
         nx.set(a, s + 1);
         if (nx.ti == 0) ri.set(a, nx.item, r, !hmma);

@@ -1,0 +1,303 @@
+// Generic fp32 GEMMs on the sm_100a tensor cores with fp32-equivalent accuracy (3xTF32: every contraction is
+// evaluated as hi*hi + lo*hi + hi*lo with a = hi + lo, hi = tf32(a)), for hidden widths the fused cell
+// kernels are not built for.  Operands live in global memory as plain fp32 row-major arrays; the loader
+// warps split them into tf32 (hi, lo) pairs and write the UMMA shared-memory layouts by hand
+// (tc_common.cuh); accumulators live in TMEM.
+//
+//   gemm_nt : C[M][N]  = A[M][K] . Bt[N][K]^T             (K-major operands, SWIZZLE_128B)
+//             used for the H x H gate contractions  [rows, H] x [H, 2H | H]  and the data gradients.
+//   gemm_tn : Cp[s][M][N] = sum_{r in split s} A[r][M] . B[r][N]   (MN-major operands, contraction over rows,
+//             128-byte swizzle with 32-byte atoms), split over the rows; the partials are summed by
+//             k_reduce_splits.  Used for the weight gradients  D^T . [h | h*R | S | X | 1].
+#include "cell_tc.cuh"
+
+namespace regt {
+using namespace tc;
+
+namespace {
+constexpr int GT_ROWS = 128;         // M tile = UMMA M = TMEM lanes
+constexpr int GT_KC = 32;            // K chunk: 32 fp32 = one 128-byte swizzle row
+constexpr int GT_NS = 3;             // pipeline stages
+constexpr int GT_TILE = GT_ROWS * 128;               // one [128][128 B] operand tile (16 KB)
+constexpr int GT_STAGE = 4 * GT_TILE;                // A hi | A lo | B hi | B lo
+constexpr int GT_LOADERS = 128;                      // loader / epilogue threads (4 warps = the 4 TMEM lane quarters)
+constexpr int GT_THREADS = GT_LOADERS + 32;          // + the MMA issuer warp
+
+__device__ __forceinline__ uint32_t tf32_rn(float a) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
+  return u;
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(tf32_rn(v.x)); hi.y = __uint_as_float(tf32_rn(v.y));
+  hi.z = __uint_as_float(tf32_rn(v.z)); hi.w = __uint_as_float(tf32_rn(v.w));
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+
+struct GemmArgs {
+  const float *A, *B;
+  float* C;
+  long long M;          // nt: rows of A / C.   tn: rows contracted over
+  int N, K;             // nt: C is [M][N], K = contraction.   tn: C is [K][N] (K = columns of A used as output rows)
+  long long lda, ldb, ldc;
+  long long chunk;      // tn: rows per split
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C[M][N] = A[M][K] . Bt[N][K]^T      grid (ceil(M/128), ceil(N/128))
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_nt_tf32x3(GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_full[GT_NS], bar_empty[GT_NS], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * GT_ROWS;
+  const int n0 = blockIdx.y * 128;
+  const int nt = min(128, a.N - n0);            // width of this N tile (multiple of 16)
+  const int nchunks = (a.K + GT_KC - 1) / GT_KC;
+  if (tid == 0) {
+    for (int s = 0; s < GT_NS; ++s) {
+      mbar_init(&bar_full[s], GT_LOADERS);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 4) {
+    // ---- loaders: thread r owns row r of the A tile and row r of the Bt tile ----
+    const long long arow = m0 + tid;
+    const bool a_ok = arow < a.M;
+    const bool b_ok = tid < nt;
+    const float* ap = a.A + (a_ok ? arow : 0) * a.lda;
+    const float* bp = a.B + (size_t)(b_ok ? n0 + tid : 0) * a.ldb;
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % GT_NS;
+      const int k0 = kc * GT_KC;
+      float4 av[8], bv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = k0 + 4 * c;
+        av[c] = (a_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(ap + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bv[c] = (b_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(bp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (kc >= GT_NS) mbar_wait(&bar_empty[s], (uint32_t)((kc / GT_NS - 1) & 1));
+      uint8_t* st = sm + s * GT_STAGE;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 hi, lo;
+        const uint32_t off = sw128_off(tid, c * 16, GT_ROWS);
+        split4(av[c], hi, lo);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + GT_TILE + off) = lo;
+        split4(bv[c], hi, lo);
+        *reinterpret_cast<float4*>(st + 2 * GT_TILE + off) = hi;
+        *reinterpret_cast<float4*>(st + 3 * GT_TILE + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&bar_full[s]);
+    }
+    // ---- epilogue: TMEM -> registers -> C (thread = row) ----
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    float* cp = a.C + (a_ok ? arow : 0) * a.ldc + n0;
+    for (int c0 = 0; c0 < nt; c0 += 16) {
+      float v[16];
+      tmem_ld16(tlane + c0, v);
+      if (a_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---- MMA issuer ----
+    const uint32_t idesc = make_idesc(FMT_TF32, 128, nt, 0, 0);
+    const uint32_t base = smem_u32(sm);
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % GT_NS;
+      mbar_wait(&bar_full[s], (uint32_t)((kc / GT_NS) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + s * GT_STAGE;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {   // hi*hi, lo*hi, hi*lo
+          const uint32_t at = st + (p == 1 ? GT_TILE : 0), bt = st + 2 * GT_TILE + (p == 2 ? GT_TILE : 0);
+#pragma unroll
+          for (int k = 0; k < GT_KC / 8; ++k)
+            umma<FMT_TF32>(tmem, make_desc(at + k * 32, 16, 1024, LAYOUT_SW128), make_desc(bt + k * 32, 16, 1024, LAYOUT_SW128),
+                           idesc, (kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_empty[s]);
+        if (kc + 1 == nchunks) umma_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------
+// Cp[z][K][N] = sum_{r in rows of split z} A[r][k0 .. k0+128) ^T . B[r][n0 .. n0+128)
+// grid (ceil(K/128), ceil(N/128), splits)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_full[GT_NS], bar_empty[GT_NS], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int kt = min(128, a.K - k0), nt = min(128, a.N - n0);     // output tile: kt rows (multiple of 32) x nt cols
+  const long long r0 = (long long)blockIdx.z * a.chunk, r1 = min(a.M, r0 + a.chunk);
+  const int nchunks = (int)((r1 - r0 + GT_KC - 1) / GT_KC);
+  if (tid == 0) {
+    for (int s = 0; s < GT_NS; ++s) {
+      mbar_init(&bar_full[s], GT_LOADERS);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  // operand tiles: [block of 32 columns][32 rows][128 B], 32-byte-atom swizzle; A: 4 blocks, B: 4 blocks
+  constexpr int BLK = GT_KC * 128;   // 4 KB
+
+  if (warp < 4) {
+    // ---- loaders: warp w owns column block w (32 floats = 128 B), lane = row of the chunk ----
+    const bool a_ok = warp * 32 < kt, b_ok = warp * 32 < nt;
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % GT_NS;
+      const long long r = r0 + (long long)kc * GT_KC + lane;
+      const bool r_ok = r < r1;
+      float4 av[8], bv[8];
+      const float4* ap = reinterpret_cast<const float4*>(a.A + (r_ok ? r : 0) * a.lda + k0 + warp * 32);
+      const float4* bp = reinterpret_cast<const float4*>(a.B + (r_ok ? r : 0) * a.ldb + n0 + warp * 32);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        av[c] = (r_ok && a_ok) ? __ldg(ap + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bv[c] = (r_ok && b_ok) ? __ldg(bp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (kc >= GT_NS) mbar_wait(&bar_empty[s], (uint32_t)((kc / GT_NS - 1) & 1));
+      uint8_t* st = sm + s * GT_STAGE;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 hi, lo;
+        const uint32_t off = warp * BLK + sw128b32_off(lane, c * 16, GT_KC);
+        split4(av[c], hi, lo);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + GT_TILE + off) = lo;
+        split4(bv[c], hi, lo);
+        *reinterpret_cast<float4*>(st + 2 * GT_TILE + off) = hi;
+        *reinterpret_cast<float4*>(st + 3 * GT_TILE + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&bar_full[s]);
+    }
+    // ---- epilogue: partial tile -> Cp[z] (thread = output row) ----
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const bool row_ok = tid < kt;
+    float* cp = a.C + ((size_t)blockIdx.z * a.K + k0 + (row_ok ? tid : 0)) * a.ldc + n0;
+    for (int c0 = 0; c0 < nt; c0 += 16) {
+      float v[16];
+      tmem_ld16(tlane + c0, v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    tc_fence_before();
+  } else {
+    const uint32_t idesc = make_idesc(FMT_TF32, 128, nt, 1, 1);
+    const uint32_t base = smem_u32(sm);
+    if (nchunks == 0 && lane == 0) {
+      // empty split: nothing to contract -- the epilogue must still see zeros
+    }
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % GT_NS;
+      mbar_wait(&bar_full[s], (uint32_t)((kc / GT_NS) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + s * GT_STAGE;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t at = st + (p == 1 ? GT_TILE : 0), bt = st + 2 * GT_TILE + (p == 2 ? GT_TILE : 0);
+#pragma unroll
+          for (int k = 0; k < GT_KC / 8; ++k)   // 8 rows of the chunk per MMA: 1 KB down the tile
+            umma<FMT_TF32>(tmem, make_desc(at + k * 1024, BLK, 1024, LAYOUT_SW128_B32),
+                           make_desc(bt + k * 1024, BLK, 1024, LAYOUT_SW128_B32), idesc, (kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_empty[s]);
+        if (kc + 1 == nchunks) umma_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+static int gemm_check(const float* A, const float* B, const float* C, long long lda, long long ldb, long long ldc, const char* who) {
+  REGT_CHECK(A && B && C, "%s: NULL operand", who);
+  REGT_CHECK(lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, "%s: leading dimensions must be multiples of 4 floats", who);
+  REGT_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0), "%s: operands must be 16-byte aligned", who);
+  return 0;
+}
+
+// C[M][N] = A[M][K] . Bt[N][K]^T ; N multiple of 16, K multiple of 4
+int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M,
+                          int N, int K, cudaStream_t st) {
+  if (gemm_check(A, Bt, C, lda, ldb, ldc, "gemm_nt")) return -1;
+  REGT_CHECK(N % 16 == 0 && K % 4 == 0 && N > 0 && K > 0, "gemm_nt: N=%d must be a multiple of 16 and K=%d of 4", N, K);
+  if (M == 0) return 0;
+  GemmArgs a{A, Bt, C, M, N, K, lda, ldb, ldc, 0};
+  const size_t smem = (size_t)GT_NS * GT_STAGE + 1024;
+  REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gemm_nt_tf32x3<<<dim3(cdiv(M, GT_ROWS), cdiv(N, 128)), GT_THREADS, smem, st>>>(a);
+  REGT_LAUNCHED("k_gemm_nt_tf32x3", st);
+  return 0;
+}
+
+// Cp[z][K][N] (z < splits) = partial sums over row chunks of A[M][K]^T . B[M][N] ; K multiple of 32, N of 16
+int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
+                          int splits, cudaStream_t st) {
+  if (gemm_check(A, B, Cp, lda, ldb, N, "gemm_tn")) return -1;
+  REGT_CHECK(K % 32 == 0 && N % 16 == 0 && K > 0 && N > 0 && splits > 0, "gemm_tn: K=%d must be a multiple of 32 and N=%d of 16", K, N);
+  long long chunk = (M + splits - 1) / splits;
+  chunk = (chunk + GT_KC - 1) / GT_KC * GT_KC;
+  GemmArgs a{A, B, Cp, M, N, K, lda, ldb, N, chunk};
+  const size_t smem = (size_t)GT_NS * GT_STAGE + 1024;
+  REGT_CUDA(cudaFuncSetAttribute(k_gemm_tn_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gemm_tn_tf32x3<<<dim3(cdiv(K, 128), cdiv(N, 128), splits), GT_THREADS, smem, st>>>(a);
+  REGT_LAUNCHED("k_gemm_tn_tf32x3", st);
+  return 0;
+}
+
+}  // namespace regt
+
+// debug entry points (not part of the reference-facing ABI): tests/test_gpu_gemm.py
+extern "C" int regt_debug_gemm_nt(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                                  int32_t N, int32_t K, regt_stream_t stream) {
+  return regt::launch_gemm_nt_tf32x3(A, lda, Bt, ldb, C, ldc, M, N, K, (cudaStream_t)stream);
+}
+extern "C" int regt_debug_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* Cp, int64_t M, int32_t K,
+                                  int32_t N, int32_t splits, regt_stream_t stream) {
+  return regt::launch_gemm_tn_tf32x3(A, lda, B, ldb, Cp, M, K, N, splits, (cudaStream_t)stream);
+}

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(HeadTcArgs a) {
   const int O = a.O;
 
   if (tid == 0) {
-    mbar_init(&bar_a0, NEPI_WARPS); mbar_init(&bar_a1, NEPI_WARPS); mbar_init(&bar_a2, NEPI_WARPS); mbar_init(&bar_a3, NEPI_WARPS);
+    mbar_init(&bar_a0, NEPI_WARPS * ARRIVALS_PER_WARP); mbar_init(&bar_a1, NEPI_WARPS * ARRIVALS_PER_WARP); mbar_init(&bar_a2, NEPI_WARPS * ARRIVALS_PER_WARP); mbar_init(&bar_a3, NEPI_WARPS * ARRIVALS_PER_WARP);
     mbar_init(&bar_m1, 1); mbar_init(&bar_m2, 1); mbar_init(&bar_m3, 1); mbar_init(&bar_m4, 1); mbar_init(&bar_w, 1);
     fence_barrier_init();
   }

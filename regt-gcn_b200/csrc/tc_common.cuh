@@ -30,9 +30,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // one arrival per WARP: every lane has fenced its own writes; lane 0 arrives after the warp converges.
 // (hundreds of per-thread arrivals on one mbarrier serialise on the same shared-memory word)
+#ifndef REGT_WARP_ARRIVE
+#define REGT_WARP_ARRIVE 0   // A/B on B200: per-thread arrivals are not slower (159.5 vs 160.8 us per step)
+#endif
+constexpr int ARRIVALS_PER_WARP = REGT_WARP_ARRIVE ? 1 : 32;   // mbar_init count = warps * ARRIVALS_PER_WARP
 __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+#if REGT_WARP_ARRIVE
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+  mbar_arrive(bar);
+#endif
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
@@ -127,7 +135,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)layout << 61;  // 0 = no swizzle (interleave), 2 = SWIZZLE_128B
   return d;
 }
-constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128 = 2;
+constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128 = 2, LAYOUT_SW128_B32 = 1;   // B32: 128-byte swizzle with 32-byte atoms
 
 // instruction descriptor: fp32 accumulate, A/B format (1 = bf16, 2 = tf32), majors (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
@@ -170,6 +178,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 __device__ __forceinline__ uint32_t sw128_off(int row, int kb, int rows) {
   const int blk = kb >> 7, inb = kb & 127;
   return (uint32_t)(blk * rows * 128 + row * 128 + ((((inb >> 4) ^ (row & 7)) << 4) | (inb & 15)));
+}
+// 128-byte swizzle with 32-byte atoms (MN-major operands of 32-bit elements): the 32-byte unit index
+// is XORed with (row & 3)
+__device__ __forceinline__ uint32_t sw128b32_off(int row, int kb, int rows) {
+  const int blk = kb >> 7, inb = kb & 127;
+  return (uint32_t)(blk * rows * 128 + row * 128 + ((((inb >> 5) ^ (row & 3)) << 5) | (inb & 31)));
 }
 // byte offset inside a chunk tile [chunk][row][16 B]
 __device__ __forceinline__ uint32_t chunk_off(int row, int chunk, int rows) { return (uint32_t)((chunk * rows + row) * 16); }

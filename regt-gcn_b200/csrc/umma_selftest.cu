@@ -11,6 +11,7 @@ using namespace tc;
 // variant 1: K-major chunk   A[128][K], B[N][K]          (K = one MMA k-step: 8 tf32 / 16 bf16)
 // variant 2: MN-major SW128  A[K][128], B[K][N]          (contraction over the tile rows)
 // variant 3: MN-major: A SW128 [K][128], B chunk tile [K][N]
+// variant 4: MN-major SW128 with 32-byte swizzle atoms (descriptor layout 1)  A[K][128], B[K][N]   (32-bit elements)
 template <int FMT>
 __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ D, int variant, int N, int K) {
@@ -25,11 +26,13 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
   const int a_rows = mn ? K : 128, a_cols = mn ? 128 : K;   // tile rows / extent along the 128-byte direction
   const int b_rows = mn ? K : N, b_cols = mn ? N : K;
   const bool a_chunk = (variant == 1), b_chunk = (variant == 1 || variant == 3);
+  const bool b32 = (variant == 4);
   uint8_t* As = smem;
   uint8_t* Bs = smem + 64 * 1024;
 
   auto put = [&](uint8_t* base, bool chunk, int rows, int r, int c, float v) {
-    uint32_t off = chunk ? chunk_off(r, (c * ES) >> 4, rows) + ((c * ES) & 15) : sw128_off(r, c * ES, rows);
+    uint32_t off = chunk ? chunk_off(r, (c * ES) >> 4, rows) + ((c * ES) & 15)
+                         : (b32 ? sw128b32_off(r, c * ES, rows) : sw128_off(r, c * ES, rows));
     if constexpr (FMT == FMT_TF32) *reinterpret_cast<float*>(base + off) = v;
     else *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(v);
   };
@@ -59,9 +62,10 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
         db = b_chunk ? make_desc(b0 + s * 2 * b_rows * 16, b_rows * 16, 128, LAYOUT_NONE)
                      : make_desc(b0 + (kb >> 7) * b_rows * 128 + (kb & 127), 16, 1024, LAYOUT_SW128);
       } else {
-        da = make_desc(a0 + s * UK * 128, a_rows * 128, 1024, LAYOUT_SW128);
+        const uint32_t lay = b32 ? LAYOUT_SW128_B32 : LAYOUT_SW128;
+        da = make_desc(a0 + s * UK * 128, a_rows * 128, 1024, lay);
         db = b_chunk ? make_desc(b0 + s * UK * 16, 128, b_rows * 16, LAYOUT_NONE)
-                     : make_desc(b0 + s * UK * 128, b_rows * 128, 1024, LAYOUT_SW128);
+                     : make_desc(b0 + s * UK * 128, b_rows * 128, 1024, lay);
       }
       umma<FMT>(tmem, da, db, idesc, s > 0 ? 1u : 0u);
     }
@@ -87,7 +91,7 @@ extern "C" int regt_debug_umma_selftest(int fmt, int variant, const float* A, co
   using namespace regt;
   cudaStream_t st = (cudaStream_t)stream;
   REGT_CHECK(fmt == 1 || fmt == 2, "selftest: fmt must be 1 (bf16) or 2 (tf32)");
-  REGT_CHECK(variant >= 0 && variant <= 3 && N % 32 == 0 && N >= 32 && N <= 128, "selftest: bad variant/N");
+  REGT_CHECK(variant >= 0 && variant <= 4 && N % 32 == 0 && N >= 32 && N <= 128, "selftest: bad variant/N");
   const size_t smem = 129 * 1024;
   if (fmt == 2) {
     REGT_CUDA(cudaFuncSetAttribute(k_umma_selftest<tc::FMT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

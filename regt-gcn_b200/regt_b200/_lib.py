@@ -56,6 +56,9 @@ _lib = None
 
 
 def lib_path() -> str:
+    alt = os.environ.get("REGT_B200_LIB")   # experiment builds (csrc/build.py build_variant)
+    if alt:
+        return alt
     return os.path.normpath(os.path.join(_HERE, "..", "lib", "libregt_b200.so"))
 
 
@@ -101,6 +104,10 @@ def load() -> C.CDLL:
     lib.regt_profile_begin.argtypes = [vp]
     lib.regt_profile_read.restype = C.c_int
     lib.regt_profile_read.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
+    lib.regt_debug_gemm_nt.restype = C.c_int
+    lib.regt_debug_gemm_nt.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp]
+    lib.regt_debug_gemm_tn.restype = C.c_int
+    lib.regt_debug_gemm_tn.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.regt_debug_umma_selftest.restype = C.c_int
     lib.regt_debug_umma_selftest.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = lib

@@ -12,13 +12,16 @@ def _ints(shape, seed):
 
 
 @pytest.mark.parametrize("fmt", [1, 2], ids=["bf16", "tf32"])
-@pytest.mark.parametrize("variant,N,K", [(0, 128, 64), (0, 64, 128), (1, 64, 0), (2, 64, 128), (2, 128, 64), (3, 32, 128)])
+@pytest.mark.parametrize("variant,N,K", [(0, 128, 64), (0, 64, 128), (1, 64, 0), (2, 64, 128), (2, 128, 64), (3, 32, 128),
+                                         (4, 64, 32), (4, 128, 64)])
 def test_umma_layout_roles(fmt, variant, N, K):
     from regt_b200 import _lib
     lib = _lib.load()
     uk = 8 if fmt == 2 else 16
-    if fmt == 2 and variant >= 2:
-        pytest.skip("tf32 MN-major operands need the SW128_32B layout; the kernels only use bf16 MN-major tiles")
+    if fmt == 2 and variant in (2, 3):
+        pytest.skip("tf32 MN-major operands need the 32-byte-atom swizzle (variant 4)")
+    if fmt == 1 and variant == 4:
+        pytest.skip("the 32-byte-atom swizzle is the MN-major layout of 32-bit elements")
     if variant == 1:
         K = uk
     if variant >= 2:

@@ -1,0 +1,27 @@
+"""builds experiment variants of libregt_b200.so (extra -D switches) under regt-gcn_b200/lib/variants/."""
+import concurrent.futures as cf
+import importlib.util
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("regt_build", os.path.join(ROOT, "regt-gcn_b200", "csrc", "build.py"))
+B = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(B)
+
+NOPIPE = ["REGT_FWD_PIPE=0", "REGT_BWD_H_UNDER_M2=0", "REGT_BWD_EARLY_E0=0"]
+VARIANTS = {
+    "base": [],
+    "nopipe": NOPIPE,
+    "nopipe_thrarrive": NOPIPE + ["REGT_WARP_ARRIVE=0"],
+    "fwdpipe_only": ["REGT_BWD_H_UNDER_M2=0", "REGT_BWD_EARLY_E0=0"],
+    "bwd_early_only": ["REGT_FWD_PIPE=0", "REGT_BWD_H_UNDER_M2=0"],
+    "cw16": ["REGT_CW=16"],
+    "cw16_nopipe": ["REGT_CW=16"] + NOPIPE,
+}
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(VARIANTS)
+    B.build()
+    with cf.ThreadPoolExecutor(4) as ex:
+        for n, p in zip(names, ex.map(lambda n: B.build_variant(n, VARIANTS[n]), names)):
+            print(n, p)
