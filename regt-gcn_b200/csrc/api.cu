@@ -11,6 +11,8 @@ int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st);
 int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st);
 int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st);
 int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st);
 
 Layout make_layout(const regt_args* a, void* base) {
   Layout L{};
@@ -29,7 +31,7 @@ Layout make_layout(const regt_args* a, void* base) {
   L.probs = c.take<float>(T);
   L.S = c.take<float>(BN * F * T);
   L.U = c.take<float>((size_t)a->B * (nseg ? nseg : 1) * F * T);
-  const bool tcp = a->precision != REGT_PREC_FP32;
+  const bool tcp = a->precision == REGT_PREC_BF16;   // fused tcgen05 kernels (tile-layout planes); tf32x3 uses the fp32 planes
   if (!tcp) {
     L.h = c.take<float>(rows * H);
     L.Z = c.take<float>(rows * H);
@@ -104,6 +106,10 @@ extern "C" int regt_cell_forward(const regt_args* a) {
   cudaStream_t st = (cudaStream_t)a->stream;
   prof_mark("<begin>", st);
   if (a->precision == REGT_PREC_FP32) return cell_forward_fp32(a, L, st);
+  if (a->precision == REGT_PREC_TF32X3) {
+    REGT_CHECK(a->H % 32 == 0, "precision tf32x3 needs hidden %% 32 == 0 (got %d); use precision fp32", a->H);
+    return cell_forward_g(a, L, st);
+  }
   return cell_forward_tc(a, L, st);
 }
 
@@ -113,6 +119,10 @@ extern "C" int regt_cell_backward(const regt_args* a) {
   cudaStream_t st = (cudaStream_t)a->stream;
   prof_mark("<begin>", st);
   if (a->precision == REGT_PREC_FP32) return cell_backward_fp32(a, L, st);
+  if (a->precision == REGT_PREC_TF32X3) {
+    REGT_CHECK(a->H % 32 == 0, "precision tf32x3 needs hidden %% 32 == 0 (got %d); use precision fp32", a->H);
+    return cell_backward_g(a, L, st);
+  }
   return cell_backward_tc(a, L, st);
 }
 

@@ -503,6 +503,39 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
   return 0;
 }
 
+// F-wide weight gradients (dP_g = D_g^T S, dM0 = D_3^T X, biases = column sums, dM1 per region) -- shared with cell_g.cu
+int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st) {
+  const int H = a->H, T = a->T, R = a->plan.R;
+  const long long rows = (long long)a->B * a->N * T;
+  float* part = L.part;
+  const int ncol = (a->mode == REGT_MODE_TGCN) ? 3 * H : 4 * H;
+  long long chunk = (rows + splits - 1) / splits;
+  k_wgrad_skinny<<<dim3(cdiv(ncol, 128), splits), 128, 0, st>>>(L.D, L.S, a->x, a->N, a->x_rows > 0 ? a->x_rows : a->N, H, T, rows, ncol, chunk, part);
+  REGT_LAUNCHED("k_wgrad_skinny", st);
+  k_skinny_reduce<<<cdiv((long long)ncol * (F + 1), 256), 256, 0, st>>>(part, splits, H, ncol, L.dP, L.dcg, L.dM0, L.dc0);
+  REGT_LAUNCHED("k_skinny_reduce", st);
+  if (a->mode != REGT_MODE_TGCN) {
+    const int zs = (int)max(1ll, min(64ll, 1024ll / ((long long)R * cdiv(H, 128))));
+    k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
+                                                        a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
+    REGT_LAUNCHED("k_wgrad_m1", st);
+    if (launch_reduce_splits(part, L.dM1, (long long)R * H * F, zs, 0, st)) return -1;
+  }
+  return 0;
+}
+
+int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st) {
+  k_attn_accum<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(Hn, probs, T, H, BN, out_hidden);
+  REGT_LAUNCHED("k_attn_accum", st);
+  return 0;
+}
+int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st) {
+  const int nblk = 128;
+  k_dprobs<<<nblk, 256, 0, st>>>(G, Hn, T, H, BN, part);
+  REGT_LAUNCHED("k_dprobs", st);
+  return launch_reduce_splits(part, dprobs, T, nblk, 0, st);
+}
+
 int cell_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, T = a->T;
   const long long BN = (long long)a->B * a->N;
@@ -553,20 +586,7 @@ int cell_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   if (launch_wgrad_tn(tb, rows, splits, st)) return -1;
   for (int g = 0; g < 3; ++g)
     if (launch_reduce_splits(tb.p[g].part, L.dB + (size_t)g * H * H, (long long)H * H, splits, 0, st)) return -1;
-  // F-wide weight gradients
-  const int ncol = (a->mode == REGT_MODE_TGCN) ? 3 * H : 4 * H;
-  long long chunk = (rows + splits - 1) / splits;
-  k_wgrad_skinny<<<dim3(cdiv(ncol, 128), splits), 128, 0, st>>>(L.D, L.S, a->x, a->N, a->x_rows > 0 ? a->x_rows : a->N, H, T, rows, ncol, chunk, part);
-  REGT_LAUNCHED("k_wgrad_skinny", st);
-  k_skinny_reduce<<<cdiv((long long)ncol * (F + 1), 256), 256, 0, st>>>(part, splits, H, ncol, L.dP, L.dcg, L.dM0, L.dc0);
-  REGT_LAUNCHED("k_skinny_reduce", st);
-  if (a->mode != REGT_MODE_TGCN) {
-    const int zs = (int)max(1ll, min(64ll, 1024ll / ((long long)R * cdiv(H, 128))));
-    k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
-                                                        a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
-    REGT_LAUNCHED("k_wgrad_m1", st);
-    if (launch_reduce_splits(part, L.dM1, (long long)R * H * F, zs, 0, st)) return -1;
-  }
+  if (launch_fwide_wgrads(a, L, splits, st)) return -1;
   return launch_chain(a, L, st);
 }
 

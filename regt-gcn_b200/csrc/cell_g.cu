@@ -1,0 +1,295 @@
+// REGT_PREC_TF32X3 for any hidden width that is a multiple of 32: the regional temporal GCN cell with
+// every H x H contraction on the sm_100a tensor cores through the generic 3xTF32 GEMMs of gemm_tc.cu
+// (fp32-equivalent accuracy), forward AND backward.  Unlike the fused H = 64 kernels of cell_tc.cu the
+// gate pre-activations make one round trip through HBM, which is what lets the same code serve H = 128
+// (configs 4, 5) and H = 256 (configs 1, 3): no weight set has to fit one SM's shared memory or TMEM.
+//
+// Planes are the fp32 path's (row = (b*N+n)*T + t; cell.cu), so the F-wide weight gradients, the
+// attention kernels and the chain rule are shared with it.  Reference arithmetic replaced:
+// models/utils.py:163-203, models/RegionalTemporalGCN.py:134-148, models/TemporalGCN.py:84-90.
+//
+//   forward   h   = act(X M0 + U M1 + c0)                          k_g_h        (F-wide, CUDA cores)
+//             Pzr = h . [B_z | B_r]^T                              gemm_nt x2   (tensor cores; B_g = linear_g.weight[:, H:])
+//             Z,R = sigmoid(Pzr + S Pzr_s + czr), hR = h*R          k_g_zr
+//             Pc  = hR . B_h^T                                      gemm_nt
+//             H~  = tanh(Pc + S Pc_s + cc), H' = Z h + (1-Z) H~     k_g_c  -> k_attn_accum
+//   backward  Dz, Dh from G, probs, saved planes                    k_g_b1
+//             dHR = Dh . B_h                                        gemm_nt (B_h^T packed by k_g_pack_bt)
+//             Dr  = dHR h R (1-R)                                   k_g_b2
+//             dhg = [Dz | Dr] . [B_z ; B_r]                         gemm_nt
+//             dhp = act'(h) (probs G Z + dHR R + dhg)               k_g_b3
+//             dB_z, dB_r = [Dz|Dr]^T h ;  dB_h = Dh^T hR            gemm_tn (row contraction, split over rows)
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace regt {
+
+constexpr int F = REGT_F;
+
+int launch_prep(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_chain(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y, int B,
+                     int n_out, int n_in, int width, cudaStream_t st);
+int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M,
+                          int N, int K, cudaStream_t st);
+int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
+                          int splits, cudaStream_t st);
+int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st);
+int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st);
+int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st);
+
+namespace {
+struct GK {
+  long long rows;
+  int N, xN, T, H, nseg, mode;
+  const float *x, *S, *U, *h_ext;
+  const int32_t *seg_ptr, *seg_reg;
+  const float *M0t, *M1t, *c0, *Wzr, *Wc, *czr, *cc, *probs, *G;
+  float *h, *Z, *Rg, *Hc, *hR, *Hn, *D;
+  float* d_h_ext;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+// one thread = (row, 4 consecutive columns)
+__device__ __forceinline__ bool rowcol(const GK& a, long long& row, int& j) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int H4 = a.H >> 2;
+  row = i / H4;
+  j = (int)(i - row * H4) * 4;
+  return row < a.rows;
+}
+__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// h = act(X_t M0 + sum_seg U_seg,t M1[region] + c0)      (regional combine on the F-wide features)
+__global__ void __launch_bounds__(256) k_g_h(GK a) {
+  long long row; int j;
+  if (!rowcol(a, row, j)) return;
+  const int H = a.H, T = a.T;
+  float v[4];
+  if (a.mode == REGT_MODE_TGCN) {
+    const float4 e = a.h_ext ? ld4(a.h_ext + row * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    st4(a.h + row * H + j, e.x, e.y, e.z, e.w);
+    return;
+  }
+  const long long q = row / T;
+  const int t = (int)(row - q * T);
+  const int b = (int)(q / a.N), n = (int)(q - (long long)b * a.N);
+  const float* xr = a.x + ((size_t)b * a.xN + n) * F * T + t;
+  const float4 c = ld4(a.c0 + j);
+  v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const float xv = __ldg(xr + f * T);
+    const float4 w = ld4(a.M0t + f * H + j);
+    v[0] = fmaf(xv, w.x, v[0]); v[1] = fmaf(xv, w.y, v[1]); v[2] = fmaf(xv, w.z, v[2]); v[3] = fmaf(xv, w.w, v[3]);
+  }
+  for (int s = a.seg_ptr[n]; s < a.seg_ptr[n + 1]; ++s) {
+    const float* ur = a.U + ((size_t)b * a.nseg + s) * F * T + t;
+    const float* m = a.M1t + (size_t)a.seg_reg[s] * F * H + j;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const float uv = __ldg(ur + f * T);
+      const float4 w = ld4(m + f * H);
+      v[0] = fmaf(uv, w.x, v[0]); v[1] = fmaf(uv, w.y, v[1]); v[2] = fmaf(uv, w.z, v[2]); v[3] = fmaf(uv, w.w, v[3]);
+    }
+  }
+  if (a.mode == REGT_MODE_REGIONAL) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.01f * v[e];   // F.leaky_relu
+  }
+  st4(a.h + row * H + j, v[0], v[1], v[2], v[3]);
+}
+
+// the F-wide part of a gate pre-activation: sum_f S[q][f][t] * W[f][n0 + e] for 4 columns
+__device__ __forceinline__ void s_part(const float* __restrict__ S, long long q, int t, int T, const float* __restrict__ W, int ldw,
+                                       int n, float (&v)[4]) {
+  const float* sr = S + q * F * T + t;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const float sv = __ldg(sr + f * T);
+    const float4 w = ld4(W + (size_t)f * ldw + n);
+    v[0] = fmaf(sv, w.x, v[0]); v[1] = fmaf(sv, w.y, v[1]); v[2] = fmaf(sv, w.z, v[2]); v[3] = fmaf(sv, w.w, v[3]);
+  }
+}
+
+// Z, R = sigmoid(Pzr + S Wzr_s + czr) ; hR = h * R         Pzr = D[:, 0:2H]
+__global__ void __launch_bounds__(256) k_g_zr(GK a) {
+  long long row; int j;
+  if (!rowcol(a, row, j)) return;
+  const int H = a.H, T = a.T;
+  const long long q = row / T;
+  const int t = (int)(row - q * T);
+  const float4 pz = ld4(a.D + row * 4 * H + j), pr = ld4(a.D + row * 4 * H + H + j);
+  const float4 bz = ld4(a.czr + j), br = ld4(a.czr + H + j);
+  float z[4] = {pz.x + bz.x, pz.y + bz.y, pz.z + bz.z, pz.w + bz.w};
+  float r[4] = {pr.x + br.x, pr.y + br.y, pr.z + br.z, pr.w + br.w};
+  s_part(a.S, q, t, T, a.Wzr, 2 * H, j, z);
+  s_part(a.S, q, t, T, a.Wzr, 2 * H, H + j, r);
+  const float4 hv = ld4(a.h + row * H + j);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { z[e] = sigm(z[e]); r[e] = sigm(r[e]); }
+  st4(a.Z + row * H + j, z[0], z[1], z[2], z[3]);
+  st4(a.Rg + row * H + j, r[0], r[1], r[2], r[3]);
+  st4(a.hR + row * H + j, hv.x * r[0], hv.y * r[1], hv.z * r[2], hv.w * r[3]);
+}
+
+// H~ = tanh(Pc + S Wc_s + cc) ; H' = Z h + (1 - Z) H~       Pc = D[:, 2H:3H]
+__global__ void __launch_bounds__(256) k_g_c(GK a) {
+  long long row; int j;
+  if (!rowcol(a, row, j)) return;
+  const int H = a.H, T = a.T;
+  const long long q = row / T;
+  const int t = (int)(row - q * T);
+  const float4 pc = ld4(a.D + row * 4 * H + 2 * H + j), bc = ld4(a.cc + j);
+  float c[4] = {pc.x + bc.x, pc.y + bc.y, pc.z + bc.z, pc.w + bc.w};
+  s_part(a.S, q, t, T, a.Wc, H, j, c);
+  const float4 hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j);
+  const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w};
+  float hn[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    c[e] = tanhf(c[e]);
+    hn[e] = z[e] * h[e] + (1.0f - z[e]) * c[e];
+  }
+  st4(a.Hc + row * H + j, c[0], c[1], c[2], c[3]);
+  st4(a.Hn + row * H + j, hn[0], hn[1], hn[2], hn[3]);
+}
+
+// Dz -> D[:, 0:H], Dh -> D[:, 2H:3H]
+__global__ void __launch_bounds__(256) k_g_b1(GK a) {
+  long long row; int j;
+  if (!rowcol(a, row, j)) return;
+  const int H = a.H, T = a.T;
+  const long long q = row / T;
+  const int t = (int)(row - q * T);
+  const float p = __ldg(a.probs + t);
+  const float4 g = ld4(a.G + q * H + j), hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j), cv = ld4(a.Hc + row * H + j);
+  const float gg[4] = {p * g.x, p * g.y, p * g.z, p * g.w};     // dH' = probs[t] * d out_hidden
+  const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w}, c[4] = {cv.x, cv.y, cv.z, cv.w};
+  float dz[4], dh[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    dz[e] = gg[e] * (h[e] - c[e]) * z[e] * (1.0f - z[e]);
+    dh[e] = gg[e] * (1.0f - z[e]) * (1.0f - c[e] * c[e]);
+  }
+  st4(a.D + row * 4 * H + j, dz[0], dz[1], dz[2], dz[3]);
+  st4(a.D + row * 4 * H + 2 * H + j, dh[0], dh[1], dh[2], dh[3]);
+}
+
+// Dr = dHR * h * R (1 - R) -> D[:, H:2H]                   dHR = Hn plane (reused)
+__global__ void __launch_bounds__(256) k_g_b2(GK a) {
+  long long row; int j;
+  if (!rowcol(a, row, j)) return;
+  const int H = a.H;
+  const float4 d = ld4(a.Hn + row * H + j), hv = ld4(a.h + row * H + j), rv = ld4(a.Rg + row * H + j);
+  st4(a.D + row * 4 * H + H + j, d.x * hv.x * rv.x * (1.0f - rv.x), d.y * hv.y * rv.y * (1.0f - rv.y),
+      d.z * hv.z * rv.z * (1.0f - rv.z), d.w * hv.w * rv.w * (1.0f - rv.w));
+}
+
+// d h = probs G Z + dHR R + dhg ; through the regional combine's activation -> D[:, 3H:4H] (in place over dhg)
+__global__ void __launch_bounds__(256) k_g_b3(GK a) {
+  long long row; int j;
+  if (!rowcol(a, row, j)) return;
+  const int H = a.H, T = a.T;
+  const long long q = row / T;
+  const int t = (int)(row - q * T);
+  const float p = __ldg(a.probs + t);
+  const float4 g = ld4(a.G + q * H + j), zv = ld4(a.Z + row * H + j), d = ld4(a.Hn + row * H + j), rv = ld4(a.Rg + row * H + j);
+  const float4 dg = ld4(a.D + row * 4 * H + 3 * H + j);
+  float v[4] = {fmaf(d.x, rv.x, p * g.x * zv.x) + dg.x, fmaf(d.y, rv.y, p * g.y * zv.y) + dg.y,
+                fmaf(d.z, rv.z, p * g.z * zv.z) + dg.z, fmaf(d.w, rv.w, p * g.w * zv.w) + dg.w};
+  if (a.mode == REGT_MODE_TGCN) {
+    if (a.d_h_ext) st4(a.d_h_ext + row * H + j, v[0], v[1], v[2], v[3]);
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+  } else if (a.mode == REGT_MODE_REGIONAL) {
+    const float4 hv = ld4(a.h + row * H + j);
+    v[0] *= hv.x > 0.f ? 1.0f : 0.01f; v[1] *= hv.y > 0.f ? 1.0f : 0.01f;
+    v[2] *= hv.z > 0.f ? 1.0f : 0.01f; v[3] *= hv.w > 0.f ? 1.0f : 0.01f;
+  }
+  st4(a.D + row * 4 * H + 3 * H + j, v[0], v[1], v[2], v[3]);
+}
+
+// K-major B operands of the data-gradient GEMMs: BhT[k][n] = B_h[n][k], BzrT[k][g*H + n] = B_g[n][k]
+__global__ void k_g_pack_bt(const float* __restrict__ lw0, const float* __restrict__ lw1, const float* __restrict__ lw2, int H,
+                            float* __restrict__ BhT, float* __restrict__ BzrT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * H * H) return;
+  const int g = i / (H * H), rem = i % (H * H), k = rem / H, n = rem % H;   // n fastest: coalesced writes
+  const float* lw = g == 0 ? lw0 : (g == 1 ? lw1 : lw2);
+  const float v = __ldg(lw + (size_t)n * 2 * H + H + k);
+  if (g == 2) BhT[(size_t)k * H + n] = v;
+  else BzrT[(size_t)k * 2 * H + g * H + n] = v;
+}
+
+GK make_gk(const regt_args* a, const Layout& L) {
+  GK k{};
+  k.rows = (long long)a->B * a->N * a->T;
+  k.N = a->N; k.xN = a->x_rows > 0 ? a->x_rows : a->N; k.T = a->T; k.H = a->H; k.nseg = a->plan.nseg; k.mode = a->mode;
+  k.x = a->x; k.S = L.S; k.U = L.U; k.h_ext = a->h_ext;
+  k.seg_ptr = a->plan.seg_ptr; k.seg_reg = a->plan.seg_reg;
+  k.M0t = L.M0t; k.M1t = L.M1t; k.c0 = L.c0; k.Wzr = L.Wzr; k.Wc = L.Wc; k.czr = L.czr; k.cc = L.cc; k.probs = L.probs;
+  k.G = L.G;
+  k.h = L.h; k.Z = L.Z; k.Rg = L.Rg; k.Hc = L.Hc; k.hR = L.hR; k.Hn = L.Hn; k.D = L.D;
+  k.d_h_ext = a->d_h_ext;
+  return k;
+}
+#define G_LAUNCH(kern, name)                                                      \
+  do {                                                                            \
+    kern<<<cdiv(k.rows * (H / 4), 256), 256, 0, st>>>(k);                         \
+    REGT_LAUNCHED(name, st);                                                      \
+  } while (0)
+}  // namespace
+
+bool cell_g_usable(const regt_args* a) { return a->precision == REGT_PREC_TF32X3 && a->H % 32 == 0; }
+
+int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int H = a->H, T = a->T;
+  const long long BN = (long long)a->B * a->N;
+  const int xN = a->x_rows > 0 ? a->x_rows : a->N;
+  if (launch_prep(a, L, st)) return -1;
+  if (launch_spmm_rows(a->plan.g_rowptr, a->plan.g_col, a->plan.g_val, a->x, L.S, a->B, a->N, xN, F * T, st)) return -1;
+  if (a->mode != REGT_MODE_TGCN && a->plan.nseg > 0) {
+    if (launch_spmm_rows(a->plan.seg_eptr, a->plan.c_col, a->plan.c_val, a->x, L.U, a->B, a->plan.nseg, xN, F * T, st))
+      return -1;
+  }
+  GK k = make_gk(a, L);
+  G_LAUNCH(k_g_h, "k_g_h");
+  // Pzr = h . [B_z | B_r]^T : the K-major B operand is the reference parameter itself (linear_g.weight[:, H:])
+  for (int g = 0; g < 2; ++g)
+    if (launch_gemm_nt_tf32x3(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, st)) return -1;
+  G_LAUNCH(k_g_zr, "k_g_zr");
+  if (launch_gemm_nt_tf32x3(L.hR, H, a->p.lin_w[2] + H, 2 * H, L.D + 2 * H, 4 * H, k.rows, H, H, st)) return -1;
+  G_LAUNCH(k_g_c, "k_g_c");
+  return launch_attn_accum(L.Hn, L.probs, T, H, BN, a->out_hidden, st);
+}
+
+int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int H = a->H, T = a->T;
+  const long long BN = (long long)a->B * a->N, rows = BN * T;
+  GK k = make_gk(a, L);
+  float* part = L.part;
+  // attention gradient first: it reads H' (the Hn plane), which then becomes the dHR scratch
+  if (launch_dprobs(L.G, L.Hn, T, H, BN, part, L.dprobs, st)) return -1;
+  float* BhT = part;                       // [H][H]   scratch until the weight-gradient partials take over
+  float* BzrT = part + (size_t)H * H;      // [H][2H]
+  k_g_pack_bt<<<cdiv(3ll * H * H, 256), 256, 0, st>>>(a->p.lin_w[0], a->p.lin_w[1], a->p.lin_w[2], H, BhT, BzrT);
+  REGT_LAUNCHED("k_g_pack_bt", st);
+  G_LAUNCH(k_g_b1, "k_g_b1");
+  if (launch_gemm_nt_tf32x3(L.D + 2 * H, 4 * H, BhT, H, L.Hn, H, rows, H, H, st)) return -1;            // dHR = Dh . B_h
+  G_LAUNCH(k_g_b2, "k_g_b2");
+  if (launch_gemm_nt_tf32x3(L.D, 4 * H, BzrT, 2 * H, L.D + 3 * H, 4 * H, rows, H, 2 * H, st)) return -1;   // dhg
+  G_LAUNCH(k_g_b3, "k_g_b3");
+  // H x H weight gradients on the tensor cores (contraction over the rows)
+  const int splits = (int)max(1ll, min((long long)WGRAD_SPLITS, rows / 512));
+  if (launch_gemm_tn_tf32x3(L.D, 4 * H, L.h, H, part, rows, 2 * H, H, splits, st)) return -1;              // dB_z | dB_r
+  if (launch_gemm_tn_tf32x3(L.D + 2 * H, 4 * H, L.hR, H, part + (size_t)splits * 2 * H * H, rows, H, H, splits, st)) return -1;
+  if (launch_reduce_splits(part, L.dB, 2ll * H * H, splits, 0, st)) return -1;
+  if (launch_reduce_splits(part + (size_t)splits * 2 * H * H, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
+  if (launch_fwide_wgrads(a, L, splits, st)) return -1;
+  return launch_chain(a, L, st);
+}
+
+}  // namespace regt

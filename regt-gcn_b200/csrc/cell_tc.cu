@@ -881,14 +881,13 @@ static int run_fwd_tc(const regt_args* a, const Layout& L, cudaStream_t st, bool
 }
 
 int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st) {
-  REGT_CHECK(a->H == 64, "tensor-core precisions are built for hidden=64 (got %d); use precision fp32", a->H);
+  REGT_CHECK(a->H == 64, "the fused bf16 tensor-core kernels are built for hidden=64 (got %d); use precision tf32x3 or fp32", a->H);
   REGT_CHECK(a->mode != REGT_MODE_TGCN, "tensor-core precisions do not cover the bare TGCN cell; use precision fp32");
   REGT_CHECK(a->T <= 64, "tensor-core path supports up to 64 periods");
   // features (graph + x) and collapsed weights (parameters) are independent: two streams
   cudaStream_t side = fork_side(st);
   if (launch_feat_tc(a->plan, a->x, a->B, a->x_rows > 0 ? a->x_rows : a->N, a->T, L.Xt, L.S, L.U, side ? side : st)) return -1;
   if (launch_prep(a, L, st)) return -1;
-  if (a->precision == REGT_PREC_TF32X3) return run_fwd_tc<FMT_TF32, 64>(a, L, st, side != nullptr);
   return run_fwd_tc<FMT_BF16, 64>(a, L, st, side != nullptr);
 }
 

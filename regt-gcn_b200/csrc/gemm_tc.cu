@@ -6,8 +6,8 @@
 //
 //   gemm_nt : C[M][N]  = A[M][K] . Bt[N][K]^T             (K-major operands, SWIZZLE_128B)
 //             used for the H x H gate contractions  [rows, H] x [H, 2H | H]  and the data gradients.
-//   gemm_tn : Cp[s][M][N] = sum_{r in split s} A[r][M] . B[r][N]   (MN-major operands, contraction over rows,
-//             128-byte swizzle with 32-byte atoms), split over the rows; the partials are summed by
+//   gemm_tn : Cp[s][M][N] = sum_{r in split s} A[r][M] . B[r][N]   (contraction over rows: the loaders transpose
+//             into the same K-major tiles), split over the rows; the partials are summed by
 //             k_reduce_splits.  Used for the weight gradients  D^T . [h | h*R | S | X | 1].
 #include "cell_tc.cuh"
 
@@ -174,11 +174,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  // operand tiles: [block of 32 columns][32 rows][128 B], 32-byte-atom swizzle; A: 4 blocks, B: 4 blocks
-  constexpr int BLK = GT_KC * 128;   // 4 KB
-
+  // The contraction runs over the ROWS of A and B, so the loaders transpose on the way into shared memory:
+  // element (row r of the chunk, column m) goes to K-major tile row m, K position r.  The tiles are then
+  // ordinary K-major SWIZZLE_128B operands ([128 columns][32 rows of the chunk = 128 B]), exactly as in gemm_nt.
   if (warp < 4) {
-    // ---- loaders: warp w owns column block w (32 floats = 128 B), lane = row of the chunk ----
+    // ---- loaders: warp w owns column block w (32 floats = 128 B of every row), lane = row of the chunk.
+    //      A lane's 4-byte stores of one (c, e) hit 32 different banks (the swizzle spreads lane >> 2). ----
     const bool a_ok = warp * 32 < kt, b_ok = warp * 32 < nt;
     for (int kc = 0; kc < nchunks; ++kc) {
       const int s = kc % GT_NS;
@@ -190,33 +191,45 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         av[c] = (r_ok && a_ok) ? __ldg(ap + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bv[c] = (r_ok && b_ok) ? __ldg(bp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bv[c] = (r_ok && b_ok && warp * 32 + 4 * c < nt) ? __ldg(bp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (kc >= GT_NS) mbar_wait(&bar_empty[s], (uint32_t)((kc / GT_NS - 1) & 1));
       uint8_t* st = sm + s * GT_STAGE;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float4 hi, lo;
-        const uint32_t off = warp * BLK + sw128b32_off(lane, c * 16, GT_KC);
         split4(av[c], hi, lo);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + GT_TILE + off) = lo;
+        const float ah[4] = {hi.x, hi.y, hi.z, hi.w}, al[4] = {lo.x, lo.y, lo.z, lo.w};
         split4(bv[c], hi, lo);
-        *reinterpret_cast<float4*>(st + 2 * GT_TILE + off) = hi;
-        *reinterpret_cast<float4*>(st + 3 * GT_TILE + off) = lo;
+        const float bh[4] = {hi.x, hi.y, hi.z, hi.w}, bl[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t off = sw128_off(warp * 32 + 4 * c + e, lane * 4, GT_ROWS);
+          *reinterpret_cast<float*>(st + off) = ah[e];
+          *reinterpret_cast<float*>(st + GT_TILE + off) = al[e];
+          *reinterpret_cast<float*>(st + 2 * GT_TILE + off) = bh[e];
+          *reinterpret_cast<float*>(st + 3 * GT_TILE + off) = bl[e];
+        }
       }
       fence_proxy_async();
       mbar_arrive(&bar_full[s]);
     }
     // ---- epilogue: partial tile -> Cp[z] (thread = output row) ----
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
+    if (nchunks > 0) {   // an empty split (more splits than row chunks) contributes zeros
+      mbar_wait(&bar_done, 0);
+      tc_fence_after();
+    }
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     const bool row_ok = tid < kt;
     float* cp = a.C + ((size_t)blockIdx.z * a.K + k0 + (row_ok ? tid : 0)) * a.ldc + n0;
     for (int c0 = 0; c0 < nt; c0 += 16) {
       float v[16];
-      tmem_ld16(tlane + c0, v);
+      if (nchunks > 0) {
+        tmem_ld16(tlane + c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
       if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -224,11 +237,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
     }
     tc_fence_before();
   } else {
-    const uint32_t idesc = make_idesc(FMT_TF32, 128, nt, 1, 1);
+    const uint32_t idesc = make_idesc(FMT_TF32, 128, nt, 0, 0);
     const uint32_t base = smem_u32(sm);
-    if (nchunks == 0 && lane == 0) {
-      // empty split: nothing to contract -- the epilogue must still see zeros
-    }
     for (int kc = 0; kc < nchunks; ++kc) {
       const int s = kc % GT_NS;
       mbar_wait(&bar_full[s], (uint32_t)((kc / GT_NS) & 1));
@@ -239,9 +249,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
         for (int p = 0; p < 3; ++p) {
           const uint32_t at = st + (p == 1 ? GT_TILE : 0), bt = st + 2 * GT_TILE + (p == 2 ? GT_TILE : 0);
 #pragma unroll
-          for (int k = 0; k < GT_KC / 8; ++k)   // 8 rows of the chunk per MMA: 1 KB down the tile
-            umma<FMT_TF32>(tmem, make_desc(at + k * 1024, BLK, 1024, LAYOUT_SW128_B32),
-                           make_desc(bt + k * 1024, BLK, 1024, LAYOUT_SW128_B32), idesc, (kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < GT_KC / 8; ++k)
+            umma<FMT_TF32>(tmem, make_desc(at + k * 32, 16, 1024, LAYOUT_SW128), make_desc(bt + k * 32, 16, 1024, LAYOUT_SW128),
+                           idesc, (kc > 0 || p > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&bar_empty[s]);
         if (kc + 1 == nchunks) umma_commit(&bar_done);

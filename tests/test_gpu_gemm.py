@@ -24,7 +24,7 @@ def test_gemm_nt_tf32x3(M, N, K, pad):
     rc = lib.regt_debug_gemm_nt(A.data_ptr(), K + pad, Bt.data_ptr(), K + pad, C.data_ptr(), N + pad, M, N, K, _st())
     _lib.check(rc, "regt_debug_gemm_nt")
     ref = A[:, :K].double() @ Bt[:, :K].double().t()
-    assert relerr(C[:, :N], ref) <= 2e-6
+    assert relerr(C[:, :N], ref) <= 1e-5
     if pad:
         assert torch.isnan(C[:, N:]).all()      # nothing written outside the N columns
 
@@ -41,4 +41,4 @@ def test_gemm_tn_tf32x3(M, K, N, splits):
     rc = lib.regt_debug_gemm_tn(A.data_ptr(), K + 4, B.data_ptr(), N + 8, Cp.data_ptr(), M, K, N, splits, _st())
     _lib.check(rc, "regt_debug_gemm_tn")
     ref = A[:, :K].double().t() @ B[:, :N].double()
-    assert relerr(Cp.double().sum(0), ref) <= 2e-6
+    assert relerr(Cp.double().sum(0), ref) <= 1e-5

@@ -12,16 +12,14 @@ def _ints(shape, seed):
 
 
 @pytest.mark.parametrize("fmt", [1, 2], ids=["bf16", "tf32"])
-@pytest.mark.parametrize("variant,N,K", [(0, 128, 64), (0, 64, 128), (1, 64, 0), (2, 64, 128), (2, 128, 64), (3, 32, 128),
-                                         (4, 64, 32), (4, 128, 64)])
+@pytest.mark.parametrize("variant,N,K", [(0, 128, 64), (0, 64, 128), (1, 64, 0), (2, 64, 128), (2, 128, 64), (3, 32, 128)])
 def test_umma_layout_roles(fmt, variant, N, K):
     from regt_b200 import _lib
     lib = _lib.load()
     uk = 8 if fmt == 2 else 16
-    if fmt == 2 and variant in (2, 3):
-        pytest.skip("tf32 MN-major operands need the 32-byte-atom swizzle (variant 4)")
-    if fmt == 1 and variant == 4:
-        pytest.skip("the 32-byte-atom swizzle is the MN-major layout of 32-bit elements")
+    if fmt == 2 and variant >= 2:
+        pytest.skip("MN-major tiles are only used with bf16 operands; the 3xTF32 row contraction (gemm_tn) transposes "
+                    "into K-major tiles instead (a first guess at the 32-byte-atom swizzle did not reproduce the GEMM)")
     if variant == 1:
         K = uk
     if variant >= 2:
