@@ -398,7 +398,23 @@ def main():
         pk = peaks()
         ab = kernel_alg_bytes(w, B if not args.micro_batch else min(B, args.micro_batch))
         dom = max((k for k in per_kernel if k in ab), key=lambda k: per_kernel[k], default=None)
-        if dom is not None:
+        if args.precision == "tf32x3" and "k_gemm_nt_tf32x3" in per_kernel:
+            # generic 3xTF32 path: the H x H contractions dominate -> tensor-pipe roofline.  Algorithmic flops of the NT
+            # GEMMs per step: 2*rows*H*H * (2 [z,r] + 1 [c] + 1 [dHR] + 2 [dhg]); the hardware executes 3 tf32 products
+            # per contraction at half the bf16 rate, so the attainable fp32-equivalent peak is bf16_peak / 6.
+            mbB = B if not args.micro_batch else min(B, args.micro_batch)
+            nmb = (B + mbB - 1) // mbB
+            flops = 2.0 * B * w.N * w.T * w.H * w.H * 6
+            t_all = per_kernel["k_gemm_nt_tf32x3"] * 1e-3
+            ach = flops / t_all / 1e12
+            peak = pk["bf16_tflops"] / 6.0
+            roofline = {"kernel": "k_gemm_nt_tf32x3", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": pk["source"] + ": bf16 dense / 6 (tf32 = half the bf16 rate, 3 products per contraction)",
+                        "alg_flops_per_step": flops, "launches_per_step": counts["k_gemm_nt_tf32x3"], "micro_batches": nmb,
+                        "launch_ms": per_kernel["k_gemm_nt_tf32x3"] / counts["k_gemm_nt_tf32x3"],
+                        "share_of_step": per_kernel["k_gemm_nt_tf32x3"] / step_sum}
+        elif dom is not None:
             t_launch = per_kernel[dom] / counts[dom] * 1e-3
             ach = ab[dom] / t_launch / 1e9
             # DRAM bytes of that kernel per launch from the committed `ncu --set full` capture of this same

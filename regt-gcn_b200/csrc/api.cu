@@ -40,6 +40,7 @@ Layout make_layout(const regt_args* a, void* base) {
     L.hR = c.take<float>(rows * H);
     L.Hn = c.take<float>(rows * H);
     L.D = c.take<float>(rows * 4 * H);
+    L.Feat = c.take<float>(a->precision == REGT_PREC_TF32X3 ? rows * 32 : 4);
   } else {
     const size_t nqt = (BN + 127) / 128, plane = T * nqt * 128 * H;
     L.tc_img_f = c.take<unsigned char>(TC_IMG_BYTES);
@@ -64,7 +65,8 @@ Layout make_layout(const regt_args* a, void* base) {
   L.dc0 = c.take<float>(H);
   L.dprobs = c.take<float>(T);
   size_t pf = (size_t)3 * WGRAD_SPLITS * H * H;                    // H x H split-K partials
-  pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * (F + 1));             // F-wide partials
+  pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * 32);                  // F-wide partials ([4H][F+1] fp32 path, [4H][32] tf32x3 GEMM)
+  pf = max(pf, (size_t)3 * H * H + 1024 * 64);                      // tf32x3: packed B^T operands + attention partials
   pf = max(pf, (size_t)64 * R * H * F);                             // per-region partials (<= 64 z-splits)
   pf = max(pf, (size_t)128 * T);                                    // attention partials
   pf = max(pf, (size_t)32 * (O * HEAD_HID + HEAD_HID * H));         // head split-K partials

@@ -503,7 +503,18 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
   return 0;
 }
 
-// F-wide weight gradients (dP_g = D_g^T S, dM0 = D_3^T X, biases = column sums, dM1 per region) -- shared with cell_g.cu
+// dM1[r] = sum over the (node, region r) segments of D_3^T U  -- shared with cell_g.cu
+int launch_wgrad_m1(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int H = a->H, T = a->T, R = a->plan.R;
+  float* part = L.part;
+  const int zs = (int)max(1ll, min(64ll, 1024ll / ((long long)R * cdiv(H, 128))));
+  k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
+                                                      a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
+  REGT_LAUNCHED("k_wgrad_m1", st);
+  return launch_reduce_splits(part, L.dM1, (long long)R * H * F, zs, 0, st);
+}
+
+// F-wide weight gradients (dP_g = D_g^T S, dM0 = D_3^T X, biases = column sums, dM1 per region)
 int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st) {
   const int H = a->H, T = a->T, R = a->plan.R;
   const long long rows = (long long)a->B * a->N * T;
@@ -514,13 +525,7 @@ int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStr
   REGT_LAUNCHED("k_wgrad_skinny", st);
   k_skinny_reduce<<<cdiv((long long)ncol * (F + 1), 256), 256, 0, st>>>(part, splits, H, ncol, L.dP, L.dcg, L.dM0, L.dc0);
   REGT_LAUNCHED("k_skinny_reduce", st);
-  if (a->mode != REGT_MODE_TGCN) {
-    const int zs = (int)max(1ll, min(64ll, 1024ll / ((long long)R * cdiv(H, 128))));
-    k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
-                                                        a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
-    REGT_LAUNCHED("k_wgrad_m1", st);
-    if (launch_reduce_splits(part, L.dM1, (long long)R * H * F, zs, 0, st)) return -1;
-  }
+  if (a->mode != REGT_MODE_TGCN && launch_wgrad_m1(a, L, st)) return -1;
   return 0;
 }
 

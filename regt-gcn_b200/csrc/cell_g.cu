@@ -12,13 +12,15 @@
 //             Pzr = h . [B_z | B_r]^T                              gemm_nt x2   (tensor cores; B_g = linear_g.weight[:, H:])
 //             Z,R = sigmoid(Pzr + S Pzr_s + czr), hR = h*R          k_g_zr
 //             Pc  = hR . B_h^T                                      gemm_nt
-//             H~  = tanh(Pc + S Pc_s + cc), H' = Z h + (1-Z) H~     k_g_c  -> k_attn_accum
-//   backward  Dz, Dh from G, probs, saved planes                    k_g_b1
+//             H~  = tanh(Pc + S Pc_s + cc), H' = Z h + (1-Z) H~,    k_g_c  (period-attention sum in registers)
+//             out_hidden = sum_t probs[t] H'
+//   backward  Dz, Dh from G, probs, saved planes; d probs         k_g_b1
 //             dHR = Dh . B_h                                        gemm_nt (B_h^T packed by k_g_pack_bt)
 //             Dr  = dHR h R (1-R)                                   k_g_b2
 //             dhg = [Dz | Dr] . [B_z ; B_r]                         gemm_nt
 //             dhp = act'(h) (probs G Z + dHR R + dhg)               k_g_b3
 //             dB_z, dB_r = [Dz|Dr]^T h ;  dB_h = Dh^T hR            gemm_tn (row contraction, split over rows)
+//             dP_g, dc_g, dM0, dc0 = D^T [S | X | 1]                gemm_tn on the 32-wide feature plane (k_g_feat)
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
@@ -37,6 +39,7 @@ int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long lo
 int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st);
 int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st);
 int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st);
+int launch_wgrad_m1(const regt_args* a, const Layout& L, cudaStream_t st);
 
 namespace {
 struct GK {
@@ -47,6 +50,10 @@ struct GK {
   const float *M0t, *M1t, *c0, *Wzr, *Wc, *czr, *cc, *probs, *G;
   float *h, *Z, *Rg, *Hc, *hR, *Hn, *D;
   float* d_h_ext;
+  float* Feat;        // [rows][32]: S_t (8) | X_t (8) | 1 | 0...   B operand of the F-wide weight-gradient GEMM
+  float* out_hidden;  // [BN][H]
+  float* dp_part;     // [gridDim.x][T] attention-gradient partials
+  long long BN;
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -136,47 +143,108 @@ __global__ void __launch_bounds__(256) k_g_zr(GK a) {
   st4(a.hR + row * H + j, hv.x * r[0], hv.y * r[1], hv.z * r[2], hv.w * r[3]);
 }
 
-// H~ = tanh(Pc + S Wc_s + cc) ; H' = Z h + (1 - Z) H~       Pc = D[:, 2H:3H]
-__global__ void __launch_bounds__(256) k_g_c(GK a) {
-  long long row; int j;
-  if (!rowcol(a, row, j)) return;
-  const int H = a.H, T = a.T;
-  const long long q = row / T;
-  const int t = (int)(row - q * T);
-  const float4 pc = ld4(a.D + row * 4 * H + 2 * H + j), bc = ld4(a.cc + j);
-  float c[4] = {pc.x + bc.x, pc.y + bc.y, pc.z + bc.z, pc.w + bc.w};
-  s_part(a.S, q, t, T, a.Wc, H, j, c);
-  const float4 hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j);
-  const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w};
-  float hn[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    c[e] = tanhf(c[e]);
-    hn[e] = z[e] * h[e] + (1.0f - z[e]) * c[e];
-  }
-  st4(a.Hc + row * H + j, c[0], c[1], c[2], c[3]);
-  st4(a.Hn + row * H + j, hn[0], hn[1], hn[2], hn[3]);
+// one thread = (q = b*N+n, 4 consecutive columns), walking the T periods of the row block
+__device__ __forceinline__ bool qcol(const GK& a, long long i, long long& q, int& j) {
+  const int H4 = a.H >> 2;
+  q = i / H4;
+  j = (int)(i - q * H4) * 4;
+  return q < a.BN;
 }
 
-// Dz -> D[:, 0:H], Dh -> D[:, 2H:3H]
-__global__ void __launch_bounds__(256) k_g_b1(GK a) {
-  long long row; int j;
-  if (!rowcol(a, row, j)) return;
+// H~ = tanh(Pc + S Wc_s + cc) ; H' = Z h + (1 - Z) H~ ; out_hidden = sum_t probs[t] H'      Pc = D[:, 2H:3H]
+// (the period-attention sum of models/RegionalTemporalGCN.py:134,146 stays in registers: no H' plane)
+__global__ void __launch_bounds__(256) k_g_c(GK a) {
+  long long q; int j;
+  if (!qcol(a, blockIdx.x * (long long)blockDim.x + threadIdx.x, q, j)) return;
   const int H = a.H, T = a.T;
+  const float4 bc = ld4(a.cc + j);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < T; ++t) {
+    const long long row = q * T + t;
+    const float4 pc = ld4(a.D + row * 4 * H + 2 * H + j);
+    float c[4] = {pc.x + bc.x, pc.y + bc.y, pc.z + bc.z, pc.w + bc.w};
+    s_part(a.S, q, t, T, a.Wc, H, j, c);
+    const float4 hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j);
+    const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w};
+    const float p = __ldg(a.probs + t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      c[e] = tanhf(c[e]);
+      acc[e] = fmaf(p, z[e] * h[e] + (1.0f - z[e]) * c[e], acc[e]);
+    }
+    st4(a.Hc + row * H + j, c[0], c[1], c[2], c[3]);
+  }
+  st4(a.out_hidden + q * H + j, acc[0], acc[1], acc[2], acc[3]);
+}
+
+// Feat[row] = S_t | X_t | 1 | 0   (32 floats per row)
+__global__ void __launch_bounds__(256) k_g_feat(GK a) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = i >> 3;
+  if (row >= a.rows) return;
+  const int c4 = (int)(i & 7), T = a.T;
   const long long q = row / T;
   const int t = (int)(row - q * T);
-  const float p = __ldg(a.probs + t);
-  const float4 g = ld4(a.G + q * H + j), hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j), cv = ld4(a.Hc + row * H + j);
-  const float gg[4] = {p * g.x, p * g.y, p * g.z, p * g.w};     // dH' = probs[t] * d out_hidden
-  const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w}, c[4] = {cv.x, cv.y, cv.z, cv.w};
-  float dz[4], dh[4];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c4 < 2) {
+    const float* sr = a.S + q * F * T + (4 * c4) * T + t;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    dz[e] = gg[e] * (h[e] - c[e]) * z[e] * (1.0f - z[e]);
-    dh[e] = gg[e] * (1.0f - z[e]) * (1.0f - c[e] * c[e]);
+    for (int e = 0; e < 4; ++e) v[e] = __ldg(sr + e * T);
+  } else if (c4 < 4) {
+    const int b = (int)(q / a.N), n = (int)(q - (long long)b * a.N);
+    const float* xr = a.x + ((size_t)b * a.xN + n) * F * T + (4 * (c4 - 2)) * T + t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = __ldg(xr + e * T);
+  } else if (c4 == 4) {
+    v[0] = 1.0f;
   }
-  st4(a.D + row * 4 * H + j, dz[0], dz[1], dz[2], dz[3]);
-  st4(a.D + row * 4 * H + 2 * H + j, dh[0], dh[1], dh[2], dh[3]);
+  st4(a.Feat + row * 32 + 4 * c4, v[0], v[1], v[2], v[3]);
+}
+
+// Dz -> D[:, 0:H], Dh -> D[:, 2H:3H]; attention gradient partials d probs[t] = sum G * H'_t (H' recomputed)
+__global__ void __launch_bounds__(256) k_g_b1(GK a) {
+  __shared__ float red[8][64];
+  const int H = a.H, T = a.T, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = a.BN * (H >> 2);
+  for (int t = threadIdx.x; t < 8 * 64; t += 256) (&red[0][0])[t] = 0.f;
+  __syncthreads();
+  // grid-stride over (q, 4 columns); trip counts are warp-uniform up to the tail (idle lanes add zeros)
+  for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    long long q; int j;
+    const bool live = qcol(a, base + threadIdx.x, q, j);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) g = ld4(a.G + q * H + j);
+    const float gr[4] = {g.x, g.y, g.z, g.w};
+    for (int t = 0; t < T; ++t) {
+      float dp = 0.f;
+      if (live) {
+        const long long row = q * T + t;
+        const float p = __ldg(a.probs + t);
+        const float4 hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j), cv = ld4(a.Hc + row * H + j);
+        const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w}, c[4] = {cv.x, cv.y, cv.z, cv.w};
+        float dz[4], dh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float gg = p * gr[e];                       // dH' = probs[t] * d out_hidden
+          dp = fmaf(gr[e], z[e] * h[e] + (1.0f - z[e]) * c[e], dp);
+          dz[e] = gg * (h[e] - c[e]) * z[e] * (1.0f - z[e]);
+          dh[e] = gg * (1.0f - z[e]) * (1.0f - c[e] * c[e]);
+        }
+        st4(a.D + row * 4 * H + j, dz[0], dz[1], dz[2], dz[3]);
+        st4(a.D + row * 4 * H + 2 * H + j, dh[0], dh[1], dh[2], dh[3]);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
+      if (lane == 0) red[warp][t] += dp;     // only this warp's lane 0 touches red[warp][*]: fixed order
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < T) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    a.dp_part[(size_t)blockIdx.x * T + threadIdx.x] = s;
+  }
 }
 
 // Dr = dHR * h * R (1 - R) -> D[:, H:2H]                   dHR = Hn plane (reused)
@@ -224,6 +292,32 @@ __global__ void k_g_pack_bt(const float* __restrict__ lw0, const float* __restri
   else BzrT[(size_t)k * 2 * H + g * H + n] = v;
 }
 
+// out[i] = sum over nparts of part[p * stride + i]   (fixed order; 32 outputs x 8 partial subsets per block)
+__global__ void __launch_bounds__(256) k_g_sum_parts(const float* __restrict__ part, int stride, int nparts, int n, float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const float s = sum_parts_32x8(part, (size_t)stride, nparts, i, i < n, red);
+  if (threadIdx.y == 0 && i < n) out[i] = s;
+}
+// Cp[split][4H][32] = D^T . Feat  ->  dP_g = D_g^T S, dc_g, dM0 = dhp^T X, dc0      (what k_skinny_reduce writes)
+__global__ void __launch_bounds__(256) k_g_fw_scatter(const float* __restrict__ Cp, int splits, int H, float* __restrict__ dP,
+                                                      float* __restrict__ dcg, float* __restrict__ dM0, float* __restrict__ dc0) {
+  __shared__ float red[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;       // (c, col) with col = i & 31
+  const int n = 4 * H * 32;
+  const float s = sum_parts_32x8(Cp, (size_t)n, splits, i, i < n, red);
+  if (threadIdx.y != 0 || i >= n) return;
+  const int c = i >> 5, col = i & 31;
+  if (c < 3 * H) {
+    if (col < F) dP[(size_t)c * F + col] = s;
+    else if (col == 16) dcg[c] = s;
+  } else {
+    const int m = c - 3 * H;
+    if (col >= 8 && col < 16) dM0[(size_t)m * F + col - 8] = s;
+    else if (col == 16) dc0[m] = s;
+  }
+}
+
 GK make_gk(const regt_args* a, const Layout& L) {
   GK k{};
   k.rows = (long long)a->B * a->N * a->T;
@@ -234,6 +328,7 @@ GK make_gk(const regt_args* a, const Layout& L) {
   k.G = L.G;
   k.h = L.h; k.Z = L.Z; k.Rg = L.Rg; k.Hc = L.Hc; k.hR = L.hR; k.Hn = L.Hn; k.D = L.D;
   k.d_h_ext = a->d_h_ext;
+  k.Feat = L.Feat; k.out_hidden = a->out_hidden; k.BN = (long long)a->B * a->N;
   return k;
 }
 #define G_LAUNCH(kern, name)                                                      \
@@ -249,6 +344,7 @@ int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, T = a->T;
   const long long BN = (long long)a->B * a->N;
   const int xN = a->x_rows > 0 ? a->x_rows : a->N;
+  REGT_CHECK(T <= 64, "precision tf32x3 supports up to 64 periods (got %d)", T);
   if (launch_prep(a, L, st)) return -1;
   if (launch_spmm_rows(a->plan.g_rowptr, a->plan.g_col, a->plan.g_val, a->x, L.S, a->B, a->N, xN, F * T, st)) return -1;
   if (a->mode != REGT_MODE_TGCN && a->plan.nseg > 0) {
@@ -262,8 +358,9 @@ int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
     if (launch_gemm_nt_tf32x3(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, st)) return -1;
   G_LAUNCH(k_g_zr, "k_g_zr");
   if (launch_gemm_nt_tf32x3(L.hR, H, a->p.lin_w[2] + H, 2 * H, L.D + 2 * H, 4 * H, k.rows, H, H, st)) return -1;
-  G_LAUNCH(k_g_c, "k_g_c");
-  return launch_attn_accum(L.Hn, L.probs, T, H, BN, a->out_hidden, st);
+  k_g_c<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(k);
+  REGT_LAUNCHED("k_g_c", st);
+  return 0;
 }
 
 int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
@@ -271,13 +368,17 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   const long long BN = (long long)a->B * a->N, rows = BN * T;
   GK k = make_gk(a, L);
   float* part = L.part;
-  // attention gradient first: it reads H' (the Hn plane), which then becomes the dHR scratch
-  if (launch_dprobs(L.G, L.Hn, T, H, BN, part, L.dprobs, st)) return -1;
   float* BhT = part;                       // [H][H]   scratch until the weight-gradient partials take over
   float* BzrT = part + (size_t)H * H;      // [H][2H]
+  float* dpp = part + (size_t)3 * H * H;   // [nb1][T] attention-gradient partials
   k_g_pack_bt<<<cdiv(3ll * H * H, 256), 256, 0, st>>>(a->p.lin_w[0], a->p.lin_w[1], a->p.lin_w[2], H, BhT, BzrT);
   REGT_LAUNCHED("k_g_pack_bt", st);
-  G_LAUNCH(k_g_b1, "k_g_b1");
+  const int nb1 = (int)min(1024ll, (long long)cdiv(BN * (H / 4), 256));
+  k.dp_part = dpp;
+  k_g_b1<<<nb1, 256, 0, st>>>(k);
+  REGT_LAUNCHED("k_g_b1", st);
+  k_g_sum_parts<<<cdiv(T, 32), dim3(32, 8), 0, st>>>(dpp, T, nb1, T, L.dprobs);
+  REGT_LAUNCHED("k_g_sum_parts", st);
   if (launch_gemm_nt_tf32x3(L.D + 2 * H, 4 * H, BhT, H, L.Hn, H, rows, H, H, st)) return -1;            // dHR = Dh . B_h
   G_LAUNCH(k_g_b2, "k_g_b2");
   if (launch_gemm_nt_tf32x3(L.D, 4 * H, BzrT, 2 * H, L.D + 3 * H, 4 * H, rows, H, 2 * H, st)) return -1;   // dhg
@@ -288,7 +389,15 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   if (launch_gemm_tn_tf32x3(L.D + 2 * H, 4 * H, L.hR, H, part + (size_t)splits * 2 * H * H, rows, H, H, splits, st)) return -1;
   if (launch_reduce_splits(part, L.dB, 2ll * H * H, splits, 0, st)) return -1;
   if (launch_reduce_splits(part + (size_t)splits * 2 * H * H, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
-  if (launch_fwide_wgrads(a, L, splits, st)) return -1;
+  // F-wide weight gradients and biases: one more row contraction, D^T . [S | X | 1]
+  k_g_feat<<<cdiv(rows * 8, 256), 256, 0, st>>>(k);
+  REGT_LAUNCHED("k_g_feat", st);
+  if (launch_gemm_tn_tf32x3(L.D, 4 * H, L.Feat, 32, part, rows, 4 * H, 32, splits, st)) return -1;
+  k_g_fw_scatter<<<cdiv(4ll * H * 32, 32), dim3(32, 8), 0, st>>>(part, splits, H, L.dP, L.dcg, L.dM0, L.dc0);
+  REGT_LAUNCHED("k_g_fw_scatter", st);
+  if (a->mode != REGT_MODE_TGCN) {   // dM1[r]: per-region sums over the (node, region) segments
+    if (launch_wgrad_m1(a, L, st)) return -1;
+  }
   return launch_chain(a, L, st);
 }
 

@@ -98,6 +98,7 @@ struct Layout {
   float* d_a1;   // [B*N][128]
   // backward planes
   float* D;      // [rows][4H]  d_pre_z | d_pre_r | d_pre_h | d_hpre
+  float* Feat;   // [rows][32]  S_t | X_t | 1 | 0  (tf32x3: B operand of the F-wide weight-gradient GEMM)
   // collapsed-weight gradients
   float* dB;     // [3][H][H]   dB_z, dB_r, dB_h
   float* dP;     // [3][H][F]

@@ -20,7 +20,8 @@ constexpr int GT_KC = 32;            // K chunk: 32 fp32 = one 128-byte swizzle 
 constexpr int GT_NS = 3;             // pipeline stages
 constexpr int GT_TILE = GT_ROWS * 128;               // one [128][128 B] operand tile (16 KB)
 constexpr int GT_STAGE = 4 * GT_TILE;                // A hi | A lo | B hi | B lo
-constexpr int GT_LOADERS = 128;                      // loader / epilogue threads (4 warps = the 4 TMEM lane quarters)
+constexpr int GT_LOADERS = 256;                      // loader / epilogue threads: 8 warps, two per TMEM lane quarter
+constexpr int GT_LW = GT_LOADERS / 32;               // loader warps; warp GT_LW issues the MMAs
 constexpr int GT_THREADS = GT_LOADERS + 32;          // + the MMA issuer warp
 
 __device__ __forceinline__ uint32_t tf32_rn(float a) {
@@ -65,35 +66,40 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_nt_tf32x3(GemmArgs a) {
     mbar_init(&bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_base_s, 128);
+  if (warp == GT_LW) tmem_alloc(&tmem_base_s, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < 4) {
-    // ---- loaders: thread r owns row r of the A tile and row r of the Bt tile ----
-    const long long arow = m0 + tid;
+  if (warp < GT_LW) {
+    // ---- loaders: thread (r, half) owns 64 bytes (4 float4) of row r of the A tile and of the Bt tile.
+    //      The global loads of chunk kc+1 are issued before chunk kc is written to shared memory. ----
+    const int r = tid & 127, half = tid >> 7;
+    const long long arow = m0 + r;
     const bool a_ok = arow < a.M;
-    const bool b_ok = tid < nt;
-    const float* ap = a.A + (a_ok ? arow : 0) * a.lda;
-    const float* bp = a.B + (size_t)(b_ok ? n0 + tid : 0) * a.ldb;
+    const bool b_ok = r < nt;
+    const float* ap = a.A + (a_ok ? arow : 0) * a.lda + half * 16;
+    const float* bp = a.B + (size_t)(b_ok ? n0 + r : 0) * a.ldb + half * 16;
+    float4 av[4], bv[4], an[4], bn[4];
+    auto load = [&](int kc, float4 (&x)[4], float4 (&y)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = kc * GT_KC + half * 16 + 4 * c;
+        x[c] = (a_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(ap + kc * GT_KC + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[c] = (b_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(bp + kc * GT_KC + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (nchunks > 0) load(0, av, bv);
     for (int kc = 0; kc < nchunks; ++kc) {
       const int s = kc % GT_NS;
-      const int k0 = kc * GT_KC;
-      float4 av[8], bv[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int k = k0 + 4 * c;
-        av[c] = (a_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(ap + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bv[c] = (b_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(bp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      if (kc + 1 < nchunks) load(kc + 1, an, bn);
       if (kc >= GT_NS) mbar_wait(&bar_empty[s], (uint32_t)((kc / GT_NS - 1) & 1));
       uint8_t* st = sm + s * GT_STAGE;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float4 hi, lo;
-        const uint32_t off = sw128_off(tid, c * 16, GT_ROWS);
+        const uint32_t off = sw128_off(r, (half * 4 + c) * 16, GT_ROWS);
         split4(av[c], hi, lo);
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + GT_TILE + off) = lo;
@@ -103,13 +109,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_nt_tf32x3(GemmArgs a) {
       }
       fence_proxy_async();
       mbar_arrive(&bar_full[s]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { av[c] = an[c]; bv[c] = bn[c]; }
     }
-    // ---- epilogue: TMEM -> registers -> C (thread = row) ----
+    // ---- epilogue: TMEM -> registers -> C (thread = row; the two warps of a lane quarter alternate 16-column groups) ----
     mbar_wait(&bar_done, 0);
     tc_fence_after();
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* cp = a.C + (a_ok ? arow : 0) * a.ldc + n0;
-    for (int c0 = 0; c0 < nt; c0 += 16) {
+    for (int c0 = half * 16; c0 < nt; c0 += 32) {
       float v[16];
       tmem_ld16(tlane + c0, v);
       if (a_ok) {
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_nt_tf32x3(GemmArgs a) {
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == GT_LW) tmem_dealloc(tmem, 128);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
     mbar_init(&bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_base_s, 128);
+  if (warp == GT_LW) tmem_alloc(&tmem_base_s, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -177,26 +185,32 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
   // The contraction runs over the ROWS of A and B, so the loaders transpose on the way into shared memory:
   // element (row r of the chunk, column m) goes to K-major tile row m, K position r.  The tiles are then
   // ordinary K-major SWIZZLE_128B operands ([128 columns][32 rows of the chunk = 128 B]), exactly as in gemm_nt.
-  if (warp < 4) {
-    // ---- loaders: warp w owns column block w (32 floats = 128 B of every row), lane = row of the chunk.
-    //      A lane's 4-byte stores of one (c, e) hit 32 different banks (the swizzle spreads lane >> 2). ----
-    const bool a_ok = warp * 32 < kt, b_ok = warp * 32 < nt;
-    for (int kc = 0; kc < nchunks; ++kc) {
-      const int s = kc % GT_NS;
+  if (warp < GT_LW) {
+    // ---- loaders: warp (w & 3) owns column block w & 3 (32 floats = 128 B of every row), its half w >> 2 the
+    //      float4s 4*half .. 4*half+3 of that block; lane = row of the chunk.  A lane's 4-byte stores of one
+    //      (c, e) hit 32 different banks (the swizzle spreads lane >> 2).  Loads run one chunk ahead. ----
+    const int blk = warp & 3, half = warp >> 2;
+    const bool a_ok = blk * 32 < kt, b_ok = blk * 32 < nt;
+    float4 av[4], bv[4], an[4], bn[4];
+    auto load = [&](int kc, float4 (&x)[4], float4 (&y)[4]) {
       const long long r = r0 + (long long)kc * GT_KC + lane;
       const bool r_ok = r < r1;
-      float4 av[8], bv[8];
-      const float4* ap = reinterpret_cast<const float4*>(a.A + (r_ok ? r : 0) * a.lda + k0 + warp * 32);
-      const float4* bp = reinterpret_cast<const float4*>(a.B + (r_ok ? r : 0) * a.ldb + n0 + warp * 32);
+      const float4* ap = reinterpret_cast<const float4*>(a.A + (r_ok ? r : 0) * a.lda + k0 + blk * 32) + half * 4;
+      const float4* bp = reinterpret_cast<const float4*>(a.B + (r_ok ? r : 0) * a.ldb + n0 + blk * 32) + half * 4;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        av[c] = (r_ok && a_ok) ? __ldg(ap + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bv[c] = (r_ok && b_ok && warp * 32 + 4 * c < nt) ? __ldg(bp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 4; ++c) {
+        x[c] = (r_ok && a_ok) ? __ldg(ap + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[c] = (r_ok && b_ok && blk * 32 + 16 * half + 4 * c < nt) ? __ldg(bp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    if (nchunks > 0) load(0, av, bv);
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % GT_NS;
+      if (kc + 1 < nchunks) load(kc + 1, an, bn);
       if (kc >= GT_NS) mbar_wait(&bar_empty[s], (uint32_t)((kc / GT_NS - 1) & 1));
       uint8_t* st = sm + s * GT_STAGE;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float4 hi, lo;
         split4(av[c], hi, lo);
         const float ah[4] = {hi.x, hi.y, hi.z, hi.w}, al[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
         const float bh[4] = {hi.x, hi.y, hi.z, hi.w}, bl[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint32_t off = sw128_off(warp * 32 + 4 * c + e, lane * 4, GT_ROWS);
+          const uint32_t off = sw128_off(blk * 32 + 16 * half + 4 * c + e, lane * 4, GT_ROWS);
           *reinterpret_cast<float*>(st + off) = ah[e];
           *reinterpret_cast<float*>(st + GT_TILE + off) = al[e];
           *reinterpret_cast<float*>(st + 2 * GT_TILE + off) = bh[e];
@@ -213,16 +227,19 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
       }
       fence_proxy_async();
       mbar_arrive(&bar_full[s]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { av[c] = an[c]; bv[c] = bn[c]; }
     }
-    // ---- epilogue: partial tile -> Cp[z] (thread = output row) ----
+    // ---- epilogue: partial tile -> Cp[z] (thread = output row; the two warps of a lane quarter alternate 16-column groups) ----
     if (nchunks > 0) {   // an empty split (more splits than row chunks) contributes zeros
       mbar_wait(&bar_done, 0);
       tc_fence_after();
     }
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    const bool row_ok = tid < kt;
-    float* cp = a.C + ((size_t)blockIdx.z * a.K + k0 + (row_ok ? tid : 0)) * a.ldc + n0;
-    for (int c0 = 0; c0 < nt; c0 += 16) {
+    const int orow = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool row_ok = orow < kt;
+    float* cp = a.C + ((size_t)blockIdx.z * a.K + k0 + (row_ok ? orow : 0)) * a.ldc + n0;
+    for (int c0 = half * 16; c0 < nt; c0 += 32) {
       float v[16];
       if (nchunks > 0) {
         tmem_ld16(tlane + c0, v);
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == GT_LW) tmem_dealloc(tmem, 128);
 }
 
 static int gemm_check(const float* A, const float* B, const float* C, long long lda, long long ldb, long long ldc, const char* who) {
