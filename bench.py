@@ -434,7 +434,7 @@ def main():
 
     # ---------------- the fp32 (1e-5 parity) mode of the same step, same inputs, same run ----------------
     fp32_mode = None
-    if rank == 0 and world == 1 and args.precision != "fp32":
+    if rank == 0 and world == 1 and args.precision != "fp32" and str(args.workload) == "2":   # small config only: a second workspace
         m32 = (TemporalGCN(8, w.T, w.O, hidden=w.H, precision="fp32") if w.model == "TemporalGCN"
                else RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R, precision="fp32"))
         W.init_params_synthetic(m32, 1234)

@@ -197,9 +197,7 @@ __global__ void k_chain(regt_params p, regt_params g, int H, int R, int T, int m
       if (which == 0) {
         for (int j = 0; j < H; ++j) v += (double)Lsum[(size_t)j * H + m] * (double)dM0[(size_t)j * F + f];
       } else {
-        for (int r = 0; r < R; ++r)
-          for (int j = 0; j < H; ++j)
-            v += (double)p.comb_w[(size_t)j * R * H + (size_t)r * H + m] * (double)dM1[((size_t)r * H + j) * F + f];
+        return;   // R*H-long contraction: one block per output (k_chain_w1)
       }
     } else {
       v = which == 0 ? dM0[(size_t)m * F + f] : dM1[(size_t)m * F + f];
@@ -240,6 +238,25 @@ __global__ void k_chain(regt_params p, regt_params g, int H, int R, int T, int m
   }
 }
 
+// cheb lins.1 weight of the regional model: d W1[m][f] = sum_r sum_j L_r[j][m] * dM1[r][j][f]  (R*H terms per output)
+__global__ void __launch_bounds__(256) k_chain_w1(const float* __restrict__ comb_w, const float* __restrict__ dM1, int H, int R,
+                                                  int acc, float* __restrict__ g_w1) {
+  __shared__ double red[256];
+  const int m = blockIdx.x / F, f = blockIdx.x % F;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < R * H; i += 256) {   // i = r*H + j ; fixed strided order, then a fixed tree
+    const int r = i / H, j = i - r * H;
+    v += (double)__ldg(comb_w + (size_t)j * R * H + (size_t)r * H + m) * (double)__ldg(dM1 + ((size_t)r * H + j) * F + f);
+  }
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && g_w1) g_w1[(size_t)m * F + f] = acc ? g_w1[(size_t)m * F + f] + (float)red[0] : (float)red[0];
+}
+
 int launch_chain(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, R = a->plan.R;
   long long n = (long long)3 * H * 2 * H + 3 * H + (long long)3 * H * F + 3 * H + a->T + 2ll * H * F + H + H +
@@ -247,6 +264,10 @@ int launch_chain(const regt_args* a, const Layout& L, cudaStream_t st) {
   k_chain<<<cdiv(n, 256), 256, 0, st>>>(a->p, a->g, H, R, a->T, a->mode, a->accumulate, L.Lsum, L.probs, L.dB, L.dP,
                                        L.dcg, L.dM0, L.dM1, L.dc0, L.dprobs);
   REGT_LAUNCHED("k_chain", st);
+  if (a->mode == REGT_MODE_REGIONAL) {
+    k_chain_w1<<<H * F, 256, 0, st>>>(a->p.comb_w, L.dM1, H, R, a->accumulate, a->g.cheb_w1);
+    REGT_LAUNCHED("k_chain_w1", st);
+  }
   return 0;
 }
 
