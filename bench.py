@@ -276,19 +276,51 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = lib.regt_launch_count(1) // max(3, args.warmup)
 
-    graphs, graph_loss = None, [None, None]
-    if not args.no_graph:
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            raw_step()
-        torch.cuda.current_stream().wait_stream(s)
+    def exchange(loss):
+        """the exchange step: shared-weight gradients + loss, ONE NCCL all-reduce of the flat buffer"""
+        if not sharded:
+            ex.add_loss(loss)
+        return ex.sync()
+
+    def full_step(b=0):
+        loss = raw_step(b)
+        return exchange(loss) if dist is not None else loss
+
+    if dist is not None:          # NCCL communicator warm-up before any capture
+        for _ in range(2):
+            loss_d = full_step()
         torch.cuda.synchronize()
-        graphs = [torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()]   # one per input buffer
-        for b in (0, 1):
-            with torch.cuda.graph(graphs[b]):
-                graph_loss[b] = raw_step(b)
+
+    graphs, graph_loss, graph_has_exchange = None, [None, None], False
+    if not args.no_graph:
+        def capture(fn):
+            gs, ls = [torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()], [None, None]   # one per input buffer
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn()
+            torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
+            for b in (0, 1):
+                with torch.cuda.graph(gs[b]):
+                    ls[b] = fn(b)
+                torch.cuda.synchronize()
+            return gs, ls
+        if dist is not None:
+            # the all-reduce is captured INSIDE the step's graph (one replay = compute + exchange); if this NCCL
+            # build refuses capture on any rank, every rank falls back to replay + eager all-reduce
+            ok = torch.ones(1, device=dev)
+            try:
+                graphs, graph_loss = capture(full_step)
+            except Exception as e:  # noqa: BLE001
+                ok.zero_()
+                print(f"[rank {rank}] NCCL graph capture failed ({type(e).__name__}): eager exchange", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            graph_has_exchange = bool(ok.item())
+            if not graph_has_exchange:
+                graphs, graph_loss = capture(raw_step)
+        else:
+            graphs, graph_loss = capture(raw_step)
     graph = graphs[0] if graphs else None
 
     def step(b=0):
@@ -296,12 +328,10 @@ def main():
         if graphs is not None:
             graphs[b].replay()
             loss_d = graph_loss[b]
+            if dist is not None and not graph_has_exchange:
+                loss_d = exchange(loss_d)
         else:
-            loss_d = raw_step(b)
-        if dist is not None:
-            if not sharded:
-                ex.add_loss(loss_d)
-            loss_d = ex.sync()   # the exchange step: shared-weight gradients + loss, one NCCL all-reduce
+            loss_d = full_step(b)
 
     for _ in range(3):
         step()
@@ -471,7 +501,7 @@ def main():
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor cores)", "bf16": "bf16 operands, f32 accumulate (f32 inputs, outputs, loss, gradients)"}[args.precision],
             "data": "synthetic",
             "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, l2="flushed between timed steps (256 MiB memset)",
-                           cuda_graph=graph is not None, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
+                           cuda_graph=graph is not None, exchange_in_graph=graph_has_exchange, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
                            parallelism=("single GPU" if world == 1 else
                                         f"region-sharded x{world} (LPT regions->ranks, halo rows of x read locally), NCCL all-reduce of the flat gradient buffer"
                                         if sharded else
@@ -484,10 +514,15 @@ def main():
             "roofline": roofline, "roofline_step": step_roof, "kernels": breakdown, "cpu_baseline": cpu,
             "fp32_parity_mode": fp32_mode,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if dist is not None:
+        # CUDA graphs that captured NCCL kernels are still alive: a regular communicator teardown can wait on them
+        # forever.  Everything is measured and printed; leave without the teardown.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
