@@ -36,6 +36,7 @@ for p in (ROOT, PKG):
 
 import torch  # noqa: E402
 
+_REAL_STDOUT = None
 METRIC = "regt_gcn_fwd_bwd_samples_per_s"
 UNIT = "samples/s"
 
@@ -211,6 +212,12 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to stdout) are sent
+    # to stderr by pointing fd 1 there; the line is written to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -514,7 +521,8 @@ def main():
             "roofline": roofline, "roofline_step": step_roof, "kernels": breakdown, "cpu_baseline": cpu,
             "fp32_parity_mode": fp32_mode,
         }
-        print(json.dumps(out), flush=True)
+        _REAL_STDOUT.write(json.dumps(out) + "\n")
+        _REAL_STDOUT.flush()
     if dist is not None:
         # CUDA graphs that captured NCCL kernels are still alive: a regular communicator teardown can wait on them
         # forever.  Everything is measured and printed; leave without the teardown.

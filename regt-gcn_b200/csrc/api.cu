@@ -67,6 +67,7 @@ Layout make_layout(const regt_args* a, void* base) {
   size_t pf = (size_t)3 * WGRAD_SPLITS * H * H;                    // H x H split-K partials
   pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * 32);                  // F-wide partials ([4H][F+1] fp32 path, [4H][32] tf32x3 GEMM)
   pf = max(pf, (size_t)3 * H * H + 1024 * 64);                      // tf32x3: packed B^T operands + attention partials
+  pf = max(pf, (size_t)WGRAD_SPLITS * (3 * H * H + 4 * H * 32));    // tf32x3: H x H and F-wide weight-gradient partials side by side
   pf = max(pf, (size_t)64 * R * H * F);                             // per-region partials (<= 64 z-splits)
   pf = max(pf, (size_t)128 * T);                                    // attention partials
   pf = max(pf, (size_t)32 * (O * HEAD_HID + HEAD_HID * H));         // head split-K partials

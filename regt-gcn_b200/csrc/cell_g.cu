@@ -35,7 +35,8 @@ int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val
 int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M,
                           int N, int K, cudaStream_t st);
 int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
-                          int splits, cudaStream_t st);
+                          int splits, cudaStream_t st, const float* B2 = nullptr, long long ldb2 = 0, float* Cp2 = nullptr,
+                          long long c2_split = 0);
 int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st);
 int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st);
 int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st);
@@ -385,15 +386,19 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   G_LAUNCH(k_g_b3, "k_g_b3");
   // H x H weight gradients on the tensor cores (contraction over the rows)
   const int splits = (int)max(1ll, min((long long)WGRAD_SPLITS, rows / 512));
-  if (launch_gemm_tn_tf32x3(L.D, 4 * H, L.h, H, part, rows, 2 * H, H, splits, st)) return -1;              // dB_z | dB_r
-  if (launch_gemm_tn_tf32x3(L.D + 2 * H, 4 * H, L.hR, H, part + (size_t)splits * 2 * H * H, rows, H, H, splits, st)) return -1;
-  if (launch_reduce_splits(part, L.dB, 2ll * H * H, splits, 0, st)) return -1;
-  if (launch_reduce_splits(part + (size_t)splits * 2 * H * H, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
-  // F-wide weight gradients and biases: one more row contraction, D^T . [S | X | 1]
+  // ... and, in the SAME pass over D, the F-wide gradients and biases D^T . [S | X | 1] (second, 32-column operand)
   k_g_feat<<<cdiv(rows * 8, 256), 256, 0, st>>>(k);
   REGT_LAUNCHED("k_g_feat", st);
-  if (launch_gemm_tn_tf32x3(L.D, 4 * H, L.Feat, 32, part, rows, 4 * H, 32, splits, st)) return -1;
-  k_g_fw_scatter<<<cdiv(4ll * H * 32, 32), dim3(32, 8), 0, st>>>(part, splits, H, L.dP, L.dcg, L.dM0, L.dc0);
+  float* pB = part;                                          // [splits][2H][H]  dB_z | dB_r
+  float* pBh = pB + (size_t)splits * 2 * H * H;              // [splits][H][H]   dB_h
+  float* pF = pBh + (size_t)splits * H * H;                  // [splits][4H][32] D^T Feat
+  const long long fsplit = 4ll * H * 32;
+  if (launch_gemm_tn_tf32x3(L.D, 4 * H, L.h, H, pB, rows, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit)) return -1;
+  if (launch_gemm_tn_tf32x3(L.D + 2 * H, 4 * H, L.hR, H, pBh, rows, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit)) return -1;
+  if (launch_gemm_tn_tf32x3(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rows, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit)) return -1;
+  if (launch_reduce_splits(pB, L.dB, 2ll * H * H, splits, 0, st)) return -1;
+  if (launch_reduce_splits(pBh, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
+  k_g_fw_scatter<<<cdiv(4ll * H * 32, 32), dim3(32, 8), 0, st>>>(pF, splits, H, L.dP, L.dcg, L.dM0, L.dc0);
   REGT_LAUNCHED("k_g_fw_scatter", st);
   if (a->mode != REGT_MODE_TGCN) {   // dM1[r]: per-region sums over the (node, region) segments
     if (launch_wgrad_m1(a, L, st)) return -1;

@@ -108,6 +108,9 @@ def load() -> C.CDLL:
     lib.regt_debug_gemm_nt.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp]
     lib.regt_debug_gemm_tn.restype = C.c_int
     lib.regt_debug_gemm_tn.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.regt_debug_gemm_tn2.restype = C.c_int
+    lib.regt_debug_gemm_tn2.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                        vp, C.c_int64, vp, vp]
     lib.regt_debug_umma_selftest.restype = C.c_int
     lib.regt_debug_umma_selftest.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = lib

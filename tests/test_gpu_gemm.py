@@ -42,3 +42,22 @@ def test_gemm_tn_tf32x3(M, K, N, splits):
     _lib.check(rc, "regt_debug_gemm_tn")
     ref = A[:, :K].double().t() @ B[:, :N].double()
     assert relerr(Cp.double().sum(0), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("M,K,N,splits", [(1000, 256, 128, 4), (3000, 128, 256, 3), (777, 64, 0, 2)])
+def test_gemm_tn_with_second_operand(M, K, N, splits):
+    """one pass over A contracts it with B [M,N] AND with a 32-column plane B2 (the F-wide weight gradients)."""
+    from regt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.rand(M, K + 4, generator=g) - 0.5).cuda()
+    B = (torch.rand(M, max(N, 4), generator=g) - 0.5).cuda()
+    B2 = (torch.rand(M, 32, generator=g) - 0.5).cuda()
+    Cp = torch.full((splits, K, max(N, 1)), float("nan"), device="cuda")
+    Cp2 = torch.full((splits, K, 32), float("nan"), device="cuda")
+    rc = lib.regt_debug_gemm_tn2(A.data_ptr(), K + 4, B.data_ptr() if N else None, max(N, 4), Cp.data_ptr() if N else None, M, K, N,
+                                 splits, B2.data_ptr(), 32, Cp2.data_ptr(), _st())
+    _lib.check(rc, "regt_debug_gemm_tn2")
+    if N:
+        assert relerr(Cp.double().sum(0), A[:, :K].double().t() @ B[:, :N].double()) <= 1e-5
+    assert relerr(Cp2.double().sum(0), A[:, :K].double().t() @ B2.double()) <= 1e-5
