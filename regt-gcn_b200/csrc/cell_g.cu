@@ -36,7 +36,7 @@ int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long l
                           int N, int K, cudaStream_t st);
 int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
                           int splits, cudaStream_t st, const float* B2 = nullptr, long long ldb2 = 0, float* Cp2 = nullptr,
-                          long long c2_split = 0);
+                          long long c2_split = 0, int relu_b = 0);
 int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st);
 int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st);
 int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st);
@@ -71,44 +71,65 @@ __device__ __forceinline__ bool rowcol(const GK& a, long long& row, int& j) {
 }
 __device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// one thread = (q = b*N+n, 4 consecutive columns), walking the T periods of the row block: the F-wide weight
+// columns it needs are loaded ONCE into registers, the x / S / U values of a period are warp-uniform broadcasts
+__device__ __forceinline__ bool qcol(const GK& a, long long i, long long& q, int& j) {
+  const int H4 = a.H >> 2;
+  q = i / H4;
+  j = (int)(i - q * H4) * 4;
+  return q < a.BN;
+}
+__device__ __forceinline__ void fma4(float s, const float4& w, float (&v)[4]) {
+  v[0] = fmaf(s, w.x, v[0]); v[1] = fmaf(s, w.y, v[1]); v[2] = fmaf(s, w.z, v[2]); v[3] = fmaf(s, w.w, v[3]);
+}
+
 // h = act(X_t M0 + sum_seg U_seg,t M1[region] + c0)      (regional combine on the F-wide features)
 __global__ void __launch_bounds__(256) k_g_h(GK a) {
-  long long row; int j;
-  if (!rowcol(a, row, j)) return;
+  long long q; int j;
+  if (!qcol(a, blockIdx.x * (long long)blockDim.x + threadIdx.x, q, j)) return;
   const int H = a.H, T = a.T;
-  float v[4];
   if (a.mode == REGT_MODE_TGCN) {
-    const float4 e = a.h_ext ? ld4(a.h_ext + row * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    st4(a.h + row * H + j, e.x, e.y, e.z, e.w);
+    for (int t = 0; t < T; ++t) {
+      const long long row = q * T + t;
+      const float4 e = a.h_ext ? ld4(a.h_ext + row * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      st4(a.h + row * H + j, e.x, e.y, e.z, e.w);
+    }
     return;
   }
-  const long long q = row / T;
-  const int t = (int)(row - q * T);
   const int b = (int)(q / a.N), n = (int)(q - (long long)b * a.N);
-  const float* xr = a.x + ((size_t)b * a.xN + n) * F * T + t;
+  const float* xr = a.x + ((size_t)b * a.xN + n) * F * T;
   const float4 c = ld4(a.c0 + j);
-  v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
+  float4 w0[F], w1[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) {
-    const float xv = __ldg(xr + f * T);
-    const float4 w = ld4(a.M0t + f * H + j);
-    v[0] = fmaf(xv, w.x, v[0]); v[1] = fmaf(xv, w.y, v[1]); v[2] = fmaf(xv, w.z, v[2]); v[3] = fmaf(xv, w.w, v[3]);
+  for (int f = 0; f < F; ++f) w0[f] = ld4(a.M0t + f * H + j);
+  const int s0 = a.seg_ptr[n], s1 = a.seg_ptr[n + 1];
+  const float* u0 = nullptr;
+  if (s1 > s0) {   // the node's first (normally only) regional segment: its M1 block stays in registers too
+    u0 = a.U + ((size_t)b * a.nseg + s0) * F * T;
+    const float* m = a.M1t + (size_t)a.seg_reg[s0] * F * H + j;
+#pragma unroll
+    for (int f = 0; f < F; ++f) w1[f] = ld4(m + f * H);
   }
-  for (int s = a.seg_ptr[n]; s < a.seg_ptr[n + 1]; ++s) {
-    const float* ur = a.U + ((size_t)b * a.nseg + s) * F * T + t;
-    const float* m = a.M1t + (size_t)a.seg_reg[s] * F * H + j;
+  for (int t = 0; t < T; ++t) {
+    float v[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-      const float uv = __ldg(ur + f * T);
-      const float4 w = ld4(m + f * H);
-      v[0] = fmaf(uv, w.x, v[0]); v[1] = fmaf(uv, w.y, v[1]); v[2] = fmaf(uv, w.z, v[2]); v[3] = fmaf(uv, w.w, v[3]);
+    for (int f = 0; f < F; ++f) fma4(__ldg(xr + f * T + t), w0[f], v);
+    if (u0) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) fma4(__ldg(u0 + f * T + t), w1[f], v);
     }
-  }
-  if (a.mode == REGT_MODE_REGIONAL) {
+    for (int s = s0 + 1; s < s1; ++s) {   // a node that appears in several regional lists (random decomposition)
+      const float* ur = a.U + ((size_t)b * a.nseg + s) * F * T + t;
+      const float* m = a.M1t + (size_t)a.seg_reg[s] * F * H + j;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.01f * v[e];   // F.leaky_relu
+      for (int f = 0; f < F; ++f) fma4(__ldg(ur + f * T), ld4(m + f * H), v);
+    }
+    if (a.mode == REGT_MODE_REGIONAL) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.01f * v[e];   // F.leaky_relu
+    }
+    st4(a.h + (q * T + t) * H + j, v[0], v[1], v[2], v[3]);
   }
-  st4(a.h + row * H + j, v[0], v[1], v[2], v[3]);
 }
 
 // the F-wide part of a gate pre-activation: sum_f S[q][f][t] * W[f][n0 + e] for 4 columns
@@ -144,14 +165,6 @@ __global__ void __launch_bounds__(256) k_g_zr(GK a) {
   st4(a.hR + row * H + j, hv.x * r[0], hv.y * r[1], hv.z * r[2], hv.w * r[3]);
 }
 
-// one thread = (q = b*N+n, 4 consecutive columns), walking the T periods of the row block
-__device__ __forceinline__ bool qcol(const GK& a, long long i, long long& q, int& j) {
-  const int H4 = a.H >> 2;
-  q = i / H4;
-  j = (int)(i - q * H4) * 4;
-  return q < a.BN;
-}
-
 // H~ = tanh(Pc + S Wc_s + cc) ; H' = Z h + (1 - Z) H~ ; out_hidden = sum_t probs[t] H'      Pc = D[:, 2H:3H]
 // (the period-attention sum of models/RegionalTemporalGCN.py:134,146 stays in registers: no H' plane)
 __global__ void __launch_bounds__(256) k_g_c(GK a) {
@@ -159,12 +172,17 @@ __global__ void __launch_bounds__(256) k_g_c(GK a) {
   if (!qcol(a, blockIdx.x * (long long)blockDim.x + threadIdx.x, q, j)) return;
   const int H = a.H, T = a.T;
   const float4 bc = ld4(a.cc + j);
+  float4 wc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) wc[f] = ld4(a.Wc + (size_t)f * H + j);
+  const float* sr = a.S + q * F * T;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int t = 0; t < T; ++t) {
     const long long row = q * T + t;
     const float4 pc = ld4(a.D + row * 4 * H + 2 * H + j);
     float c[4] = {pc.x + bc.x, pc.y + bc.y, pc.z + bc.z, pc.w + bc.w};
-    s_part(a.S, q, t, T, a.Wc, H, j, c);
+#pragma unroll
+    for (int f = 0; f < F; ++f) fma4(__ldg(sr + f * T + t), wc[f], c);
     const float4 hv = ld4(a.h + row * H + j), zv = ld4(a.Z + row * H + j);
     const float h[4] = {hv.x, hv.y, hv.z, hv.w}, z[4] = {zv.x, zv.y, zv.z, zv.w};
     const float p = __ldg(a.probs + t);
@@ -353,7 +371,8 @@ int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
       return -1;
   }
   GK k = make_gk(a, L);
-  G_LAUNCH(k_g_h, "k_g_h");
+  k_g_h<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(k);
+  REGT_LAUNCHED("k_g_h", st);
   // Pzr = h . [B_z | B_r]^T : the K-major B operand is the reference parameter itself (linear_g.weight[:, H:])
   for (int g = 0; g < 2; ++g)
     if (launch_gemm_nt_tf32x3(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, st)) return -1;
@@ -361,6 +380,9 @@ int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   if (launch_gemm_nt_tf32x3(L.hR, H, a->p.lin_w[2] + H, 2 * H, L.D + 2 * H, 4 * H, k.rows, H, H, st)) return -1;
   k_g_c<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(k);
   REGT_LAUNCHED("k_g_c", st);
+  // feature plane [S | X | 1]: second operand of the weight-gradient contractions (cell and head backward)
+  k_g_feat<<<cdiv(k.rows * 8, 256), 256, 0, st>>>(k);
+  REGT_LAUNCHED("k_g_feat", st);
   return 0;
 }
 
@@ -386,9 +408,8 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   G_LAUNCH(k_g_b3, "k_g_b3");
   // H x H weight gradients on the tensor cores (contraction over the rows)
   const int splits = (int)max(1ll, min((long long)WGRAD_SPLITS, rows / 512));
-  // ... and, in the SAME pass over D, the F-wide gradients and biases D^T . [S | X | 1] (second, 32-column operand)
-  k_g_feat<<<cdiv(rows * 8, 256), 256, 0, st>>>(k);
-  REGT_LAUNCHED("k_g_feat", st);
+  // ... and, in the SAME pass over D, the F-wide gradients and biases D^T . [S | X | 1] (second, 32-column operand:
+  // the feature plane built in the forward)
   float* pB = part;                                          // [splits][2H][H]  dB_z | dB_r
   float* pBh = pB + (size_t)splits * 2 * H * H;              // [splits][H][H]   dB_h
   float* pF = pBh + (size_t)splits * H * H;                  // [splits][4H][32] D^T Feat

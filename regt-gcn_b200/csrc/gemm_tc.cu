@@ -51,6 +51,7 @@ struct GemmArgs {
   long long ldb2;
   int N2;
   long long c2_split;   // elements between the splits of C2 (its rows may be a window of a taller array)
+  int relu_b;           // tn: B is read through max(., 0)  (the head's relu(out_hidden))
 };
 }  // namespace
 
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tn_tf32x3(GemmArgs a) {
       for (int c = 0; c < 4; ++c) {
         x[c] = (r_ok && a_ok) ? __ldg(ap + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         y[c] = (r_ok && b_ok && blk * 32 + 16 * half + 4 * c < nt) ? __ldg(bp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.relu_b) y[c] = make_float4(fmaxf(y[c].x, 0.f), fmaxf(y[c].y, 0.f), fmaxf(y[c].z, 0.f), fmaxf(y[c].w, 0.f));
       }
       if (n2) f = r_ok ? __ldg(reinterpret_cast<const float4*>(a.B2 + r * a.ldb2) + warp) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -364,7 +366,7 @@ int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long l
   if (gemm_check(A, Bt, C, lda, ldb, ldc, "gemm_nt")) return -1;
   REGT_CHECK(N % 16 == 0 && K % 4 == 0 && N > 0 && K > 0, "gemm_nt: N=%d must be a multiple of 16 and K=%d of 4", N, K);
   if (M == 0) return 0;
-  GemmArgs a{A, Bt, C, M, N, K, lda, ldb, ldc, 0, nullptr, nullptr, 0, 0, 0};
+  GemmArgs a{A, Bt, C, M, N, K, lda, ldb, ldc, 0, nullptr, nullptr, 0, 0, 0, 0};
   const size_t smem = (size_t)GT_NS * GT_STAGE + 1024;
   REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static int sms = 0;
@@ -383,14 +385,14 @@ int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long l
 // Optional second operand B2 [M][32] (ldb2): Cp2[z][K][32] = partials of A^T . B2 in the same pass (N may then be 0).
 int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
                           int splits, cudaStream_t st, const float* B2 = nullptr, long long ldb2 = 0, float* Cp2 = nullptr,
-                          long long c2_split = 0) {
+                          long long c2_split = 0, int relu_b = 0) {
   if (N > 0 && gemm_check(A, B, Cp, lda, ldb, N, "gemm_tn")) return -1;
   REGT_CHECK(K % 32 == 0 && N % 16 == 0 && K > 0 && N >= 0 && splits > 0, "gemm_tn: K=%d must be a multiple of 32 and N=%d of 16", K, N);
   REGT_CHECK(N > 0 || B2, "gemm_tn: nothing to contract with");
   REGT_CHECK(!B2 || (Cp2 && ldb2 % 4 == 0 && (uintptr_t)B2 % 16 == 0 && (uintptr_t)Cp2 % 16 == 0), "gemm_tn: bad second operand");
   long long chunk = (M + splits - 1) / splits;
   chunk = (chunk + GT_KC - 1) / GT_KC * GT_KC;
-  GemmArgs a{A, N > 0 ? B : A, Cp, M, N, K, lda, N > 0 ? ldb : lda, N, chunk, B2, Cp2, ldb2, B2 ? 32 : 0, c2_split > 0 ? c2_split : (long long)K * 32};
+  GemmArgs a{A, N > 0 ? B : A, Cp, M, N, K, lda, N > 0 ? ldb : lda, N, chunk, B2, Cp2, ldb2, B2 ? 32 : 0, c2_split > 0 ? c2_split : (long long)K * 32, relu_b};
   const size_t smem = (size_t)GT_NS * GT_STAGE2 + 1024;
   REGT_CUDA(cudaFuncSetAttribute(k_gemm_tn_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_gemm_tn_tf32x3<<<dim3(cdiv(K, 128), max(1, cdiv(N, 128)), splits), GT_THREADS, smem, st>>>(a);

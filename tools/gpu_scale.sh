@@ -7,7 +7,7 @@ if [ "$N" = "1" ]; then
 else
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus $N > gpurun_out/b2_bf16_n$N.json 2> gpurun_out/b2_bf16_n$N.err; tail -2 gpurun_out/b2_bf16_n$N.err
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29622 bench.py --gpus $N --workload 5 --precision tf32x3 --steps 3 --warmup 3 --no-graph > gpurun_out/b5_tf32_n$N.json 2> gpurun_out/b5_tf32_n$N.err; tail -2 gpurun_out/b5_tf32_n$N.err
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29623 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/ref_n$N.json 2> gpurun_out/ref_n$N.err; tail -1 gpurun_out/ref_n$N.json | cut -c1-200
+  true
 fi
 python - <<'PY'
 import json,glob
