@@ -41,6 +41,7 @@ Layout make_layout(const regt_args* a, void* base) {
     L.Hn = c.take<float>(rows * H);
     L.D = c.take<float>(rows * 4 * H);
     L.Feat = c.take<float>(a->precision == REGT_PREC_TF32X3 ? rows * 32 : 4);
+    L.bsplit = c.take<float>(a->precision == REGT_PREC_TF32X3 ? gemm_nt_scratch_floats((int)H, 2 * (int)H) : 4);
   } else {
     const size_t nqt = (BN + 127) / 128, plane = T * nqt * 128 * H;
     L.tc_img_f = c.take<unsigned char>(TC_IMG_BYTES);

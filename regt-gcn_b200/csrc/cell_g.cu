@@ -37,6 +37,13 @@ int launch_gemm_nt_tf32x3(const float* A, long long lda, const float* Bt, long l
 int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
                           int splits, cudaStream_t st, const float* B2 = nullptr, long long ldb2 = 0, float* Cp2 = nullptr,
                           long long c2_split = 0, int relu_b = 0);
+int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M, int N,
+                       int K, float* scratch, cudaStream_t st);
+int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int nseg, const int* seg_k0, const int* seg_b,
+                       float* const* seg_C, const float* const* Bs, const long long* ldbs, int N, int splits, const float* B2,
+                       long long ldb2, float* C2, long long c2_split, cudaStream_t st);
+int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N, int splits,
+                        cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split);
 int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st);
 int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st);
 int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st);
@@ -375,9 +382,9 @@ int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   REGT_LAUNCHED("k_g_h", st);
   // Pzr = h . [B_z | B_r]^T : the K-major B operand is the reference parameter itself (linear_g.weight[:, H:])
   for (int g = 0; g < 2; ++g)
-    if (launch_gemm_nt_tf32x3(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, st)) return -1;
+    if (launch_gemm_nt_tma(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, L.bsplit, st)) return -1;
   G_LAUNCH(k_g_zr, "k_g_zr");
-  if (launch_gemm_nt_tf32x3(L.hR, H, a->p.lin_w[2] + H, 2 * H, L.D + 2 * H, 4 * H, k.rows, H, H, st)) return -1;
+  if (launch_gemm_nt_tma(L.hR, H, a->p.lin_w[2] + H, 2 * H, L.D + 2 * H, 4 * H, k.rows, H, H, L.bsplit, st)) return -1;
   k_g_c<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(k);
   REGT_LAUNCHED("k_g_c", st);
   // feature plane [S | X | 1]: second operand of the weight-gradient contractions (cell and head backward)
@@ -402,21 +409,33 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   REGT_LAUNCHED("k_g_b1", st);
   k_g_sum_parts<<<cdiv(T, 32), dim3(32, 8), 0, st>>>(dpp, T, nb1, T, L.dprobs);
   REGT_LAUNCHED("k_g_sum_parts", st);
-  if (launch_gemm_nt_tf32x3(L.D + 2 * H, 4 * H, BhT, H, L.Hn, H, rows, H, H, st)) return -1;            // dHR = Dh . B_h
+  if (launch_gemm_nt_tma(L.D + 2 * H, 4 * H, BhT, H, L.Hn, H, rows, H, H, L.bsplit, st)) return -1;            // dHR = Dh . B_h
   G_LAUNCH(k_g_b2, "k_g_b2");
-  if (launch_gemm_nt_tf32x3(L.D, 4 * H, BzrT, 2 * H, L.D + 3 * H, 4 * H, rows, H, 2 * H, st)) return -1;   // dhg
+  if (launch_gemm_nt_tma(L.D, 4 * H, BzrT, 2 * H, L.D + 3 * H, 4 * H, rows, H, 2 * H, L.bsplit, st)) return -1;   // dhg
   G_LAUNCH(k_g_b3, "k_g_b3");
   // H x H weight gradients on the tensor cores (contraction over the rows)
-  const int splits = (int)max(1ll, min((long long)WGRAD_SPLITS, rows / 512));
   // ... and, in the SAME pass over D, the F-wide gradients and biases D^T . [S | X | 1] (second, 32-column operand:
-  // the feature plane built in the forward)
+  // the feature plane built in the forward).  H % 128 == 0: ONE launch over all four gate blocks of D (z | r against h,
+  // h~ against h*R, h_pre against the feature plane only), split so that the grid fills the SMs once.
+  const bool merged = H % 128 == 0;
+  const int ctas_per_split = (4 * H / 128) * (H / 128);
+  const int splits = merged ? (int)max(1ll, min((long long)min(WGRAD_SPLITS, cdiv(148, ctas_per_split)), rows / 512))
+                            : (int)max(1ll, min((long long)WGRAD_SPLITS, rows / 512));
   float* pB = part;                                          // [splits][2H][H]  dB_z | dB_r
   float* pBh = pB + (size_t)splits * 2 * H * H;              // [splits][H][H]   dB_h
   float* pF = pBh + (size_t)splits * H * H;                  // [splits][4H][32] D^T Feat
   const long long fsplit = 4ll * H * 32;
-  if (launch_gemm_tn_tf32x3(L.D, 4 * H, L.h, H, pB, rows, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit)) return -1;
-  if (launch_gemm_tn_tf32x3(L.D + 2 * H, 4 * H, L.hR, H, pBh, rows, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit)) return -1;
-  if (launch_gemm_tn_tf32x3(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rows, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit)) return -1;
+  if (merged) {
+    const int k0[3] = {0, 2 * H, 3 * H}, sb[3] = {0, 1, -1};
+    float* cs[3] = {pB, pBh, nullptr};
+    const float* bs[2] = {L.h, L.hR};
+    const long long lds[2] = {H, H};
+    if (launch_gemm_tn_tma(L.D, 4 * H, rows, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, L.Feat, 32, pF, fsplit, st)) return -1;
+  } else {
+    if (launch_gemm_tn_auto(L.D, 4 * H, L.h, H, pB, rows, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit)) return -1;
+    if (launch_gemm_tn_auto(L.D + 2 * H, 4 * H, L.hR, H, pBh, rows, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit)) return -1;
+    if (launch_gemm_tn_auto(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rows, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit)) return -1;
+  }
   if (launch_reduce_splits(pB, L.dB, 2ll * H * H, splits, 0, st)) return -1;
   if (launch_reduce_splits(pBh, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
   k_g_fw_scatter<<<cdiv(4ll * H * 32, 32), dim3(32, 8), 0, st>>>(pF, splits, H, L.dP, L.dcg, L.dM0, L.dc0);

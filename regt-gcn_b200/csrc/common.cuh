@@ -99,6 +99,7 @@ struct Layout {
   // backward planes
   float* D;      // [rows][4H]  d_pre_z | d_pre_r | d_pre_h | d_hpre
   float* Feat;   // [rows][32]  S_t | X_t | 1 | 0  (tf32x3: B operand of the F-wide weight-gradient GEMM)
+  float* bsplit; // tf32x3: hi | lo images of the weight operand of the current gate GEMM (gemm_tma.cu)
   // collapsed-weight gradients
   float* dB;     // [3][H][H]   dB_z, dB_r, dB_h
   float* dP;     // [3][H][F]
@@ -124,6 +125,7 @@ constexpr int TC_MAX_CTAS = 160;
 constexpr int TC_IMG_BYTES = 160 * 1024;
 
 Layout make_layout(const regt_args* a, void* base);
+size_t gemm_nt_scratch_floats(int N, int K);
 
 constexpr int HEAD_HID = 128;  // hidden_dim of the decoder MLP (models/RegionalTemporalGCN.py:19)
 constexpr int WGRAD_SPLITS = 64;

@@ -111,6 +111,13 @@ def load() -> C.CDLL:
     lib.regt_debug_gemm_tn2.restype = C.c_int
     lib.regt_debug_gemm_tn2.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                         vp, C.c_int64, vp, vp]
+    lib.regt_debug_gemm_nt_tma.restype = C.c_int
+    lib.regt_debug_gemm_nt_tma.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp, vp]
+    lib.regt_debug_gemm_tn_tma.restype = C.c_int
+    lib.regt_debug_gemm_tn_tma.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           vp, C.c_int64, vp, vp]
+    lib.regt_debug_gemm_tn_multi.restype = C.c_int
+    lib.regt_debug_gemm_tn_multi.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp]
     lib.regt_debug_umma_selftest.restype = C.c_int
     lib.regt_debug_umma_selftest.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = lib
