@@ -71,7 +71,8 @@ Layout make_layout(const regt_args* a, void* base) {
   pf = max(pf, (size_t)WGRAD_SPLITS * (3 * H * H + 4 * H * 32));    // tf32x3: H x H and F-wide weight-gradient partials side by side
   pf = max(pf, (size_t)64 * R * H * F);                             // per-region partials (<= 64 z-splits)
   pf = max(pf, (size_t)128 * T);                                    // attention partials
-  pf = max(pf, (size_t)32 * (O * HEAD_HID + HEAD_HID * (H + 32)));  // head split-K partials (+ the 32-wide second operand, tf32x3)
+  pf = max(pf, (size_t)128 * (O * HEAD_HID + HEAD_HID * H));        // head split-K partials (<= 128 splits)
+  pf = max(pf, (size_t)152 * HEAD_HID * (H + 32));                  // head dW1 on the tensor cores (+ the 32-wide second operand, tf32x3)
   pf = max(pf, BN / 64 + 2);                                        // loss partials
   pf += H * HEAD_HID + HEAD_HID * O + 64;                           // transposed head weights (tail)
   L.hpart = c.take<float>((size_t)148 * (HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 8));

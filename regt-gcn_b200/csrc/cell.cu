@@ -449,18 +449,39 @@ int launch_reduce_splits(const float* part, float* out, long long count, int spl
   return 0;
 }
 
-__global__ void __launch_bounds__(128) k_colsum(const float* __restrict__ A, int lda, int C, long long rows,
-                                                long long chunk, float* __restrict__ part) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
+// part[split][c] = sum over the rows of the split of A[r][c].  256 threads = RS row lanes x CW column lanes
+// (CW = power of two >= min(C, 128)): independent loads in flight, then a fixed-order sum over the row lanes.
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int lda, int C, long long rows,
+                                                long long chunk, float* __restrict__ part, int CW) {
+  __shared__ float red[256];
+  const int RS = 256 / CW;
+  const int cl = threadIdx.x % CW, rl = threadIdx.x / CW;
+  const int c = blockIdx.x * CW + cl;
   const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += __ldg(A + r * lda + c);
-  part[(size_t)blockIdx.y * C + c] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    long long r = r0 + rl;
+    for (; r + 3ll * RS < r1; r += 4ll * RS) {
+      s0 += __ldg(A + r * lda + c);
+      s1 += __ldg(A + (r + RS) * lda + c);
+      s2 += __ldg(A + (r + 2ll * RS) * lda + c);
+      s3 += __ldg(A + (r + 3ll * RS) * lda + c);
+    }
+    for (; r < r1; r += RS) s0 += __ldg(A + r * lda + c);
+  }
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float s = 0.f;
+    for (int i = 0; i < RS; ++i) s += red[i * CW + cl];
+    part[(size_t)blockIdx.y * C + c] = s;
+  }
 }
 int launch_colsum(const float* A, int lda, int C, long long rows, int splits, float* part, cudaStream_t st) {
   long long chunk = (rows + splits - 1) / splits;
-  k_colsum<<<dim3(cdiv(C, 128), splits), 128, 0, st>>>(A, lda, C, rows, chunk, part);
+  int CW = 1;
+  while (CW < C && CW < 128) CW <<= 1;
+  k_colsum<<<dim3(cdiv(C, CW), splits), 256, 0, st>>>(A, lda, C, rows, chunk, part, CW);
   REGT_LAUNCHED("k_colsum", st);
   return 0;
 }

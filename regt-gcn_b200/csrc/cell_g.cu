@@ -41,9 +41,9 @@ int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long
                        int K, float* scratch, cudaStream_t st);
 int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int nseg, const int* seg_k0, const int* seg_b,
                        float* const* seg_C, const float* const* Bs, const long long* ldbs, int N, int splits, const float* B2,
-                       long long ldb2, float* C2, long long c2_split, cudaStream_t st);
+                       long long ldb2, float* C2, long long c2_split, cudaStream_t st, int relu_b);
 int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N, int splits,
-                        cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split);
+                        cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split, int relu_b);
 int launch_attn_accum(const float* Hn, const float* probs, int T, int H, long long BN, float* out_hidden, cudaStream_t st);
 int launch_dprobs(const float* G, const float* Hn, int T, int H, long long BN, float* part, float* dprobs, cudaStream_t st);
 int launch_fwide_wgrads(const regt_args* a, const Layout& L, int splits, cudaStream_t st);
@@ -430,11 +430,11 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
     float* cs[3] = {pB, pBh, nullptr};
     const float* bs[2] = {L.h, L.hR};
     const long long lds[2] = {H, H};
-    if (launch_gemm_tn_tma(L.D, 4 * H, rows, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, L.Feat, 32, pF, fsplit, st)) return -1;
+    if (launch_gemm_tn_tma(L.D, 4 * H, rows, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, L.Feat, 32, pF, fsplit, st, 0)) return -1;
   } else {
-    if (launch_gemm_tn_auto(L.D, 4 * H, L.h, H, pB, rows, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit)) return -1;
-    if (launch_gemm_tn_auto(L.D + 2 * H, 4 * H, L.hR, H, pBh, rows, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit)) return -1;
-    if (launch_gemm_tn_auto(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rows, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit)) return -1;
+    if (launch_gemm_tn_auto(L.D, 4 * H, L.h, H, pB, rows, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit, 0)) return -1;
+    if (launch_gemm_tn_auto(L.D + 2 * H, 4 * H, L.hR, H, pBh, rows, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit, 0)) return -1;
+    if (launch_gemm_tn_auto(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rows, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit, 0)) return -1;
   }
   if (launch_reduce_splits(pB, L.dB, 2ll * H * H, splits, 0, st)) return -1;
   if (launch_reduce_splits(pBh, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;

@@ -299,6 +299,7 @@ struct TnArgs {
   long long c2_split;
   long long M, chunk;          // rows contracted over; rows per split (multiple of 32)
   int N, N2;
+  int relu_b;                  // the B operands are read through max(., 0)
 };
 constexpr int TN_CONV = 256;                  // converter / epilogue threads (warps 0-7)
 constexpr int TN_W_MMA = TN_CONV / 32;
@@ -405,6 +406,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn_tma(const __grid_cons
         const uint32_t off = (uint32_t)(lane * 128 + (((half * 4 + c) ^ (lane & 7)) << 4));
         av[c] = a_ok ? *reinterpret_cast<const float4*>(rw + blk * TN_BOX + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         bv[c] = b_ok ? *reinterpret_cast<const float4*>(rw + (4 + blk) * TN_BOX + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (a.relu_b) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bv[c] = make_float4(fmaxf(bv[c].x, 0.f), fmaxf(bv[c].y, 0.f), fmaxf(bv[c].z, 0.f), fmaxf(bv[c].w, 0.f));
       }
       if (n2) fv = *reinterpret_cast<const float4*>(rw + 8 * TN_BOX + lane * 128 + ((warp ^ (lane & 7)) << 4));
 #if !defined(REGT_TN_LATE)
@@ -583,7 +588,7 @@ int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long
 // Segment boundaries must be multiples of 128 unless there is a single segment.
 int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int nseg, const int* seg_k0, const int* seg_b,
                        float* const* seg_C, const float* const* Bs, const long long* ldbs, int N, int splits, const float* B2,
-                       long long ldb2, float* C2, long long c2_split, cudaStream_t st) {
+                       long long ldb2, float* C2, long long c2_split, cudaStream_t st, int relu_b) {
   REGT_CHECK(A && nseg >= 1 && nseg <= 4 && Ktot % 32 == 0 && N % 32 == 0 && splits > 0 && M >= 32, "gemm_tn_tma: bad shape");
   REGT_CHECK(!B2 || (C2 && ldb2 % 4 == 0), "gemm_tn_tma: bad second operand");
   TnArgs a{};
@@ -613,6 +618,7 @@ int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int
   a.chunk = (chunk + KC - 1) / KC * KC;
   a.N = any_b ? N : 0;
   a.N2 = B2 ? 32 : 0;
+  a.relu_b = relu_b;
   const size_t smem = (size_t)TN_NR * TN_RAW + (size_t)TN_NC * TN_CV + 1024;
   REGT_CUDA(cudaFuncSetAttribute(k_gemm_tn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_gemm_tn_tma<<<dim3(cdiv(Ktot, 128), max(1, cdiv(a.N, 128)), splits), TN_THREADS, smem, st>>>(a);
@@ -622,15 +628,15 @@ int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int
 
 // drop-in for launch_gemm_tn_tf32x3 (single segment); falls back when the TMA preconditions do not hold
 int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N, int splits,
-                        cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split) {
+                        cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split, int relu_b) {
   const bool ok = !legacy_forced() && M >= 32 && K % 32 == 0 && N % 32 == 0 && lda % 4 == 0 && ((uintptr_t)A % 16) == 0 &&
                   (N == 0 || (ldb % 4 == 0 && ((uintptr_t)B % 16) == 0)) && (!B2 || ((uintptr_t)B2 % 16) == 0);
-  if (!ok) return launch_gemm_tn_tf32x3(A, lda, B, ldb, Cp, M, K, N, splits, st, B2, ldb2, Cp2, c2_split, 0);
+  if (!ok) return launch_gemm_tn_tf32x3(A, lda, B, ldb, Cp, M, K, N, splits, st, B2, ldb2, Cp2, c2_split, relu_b);
   const int k0 = 0, sb = N > 0 ? 0 : -1;
   float* cs[1] = {Cp};
   const float* bs[2] = {B, nullptr};
   const long long lds[2] = {ldb, 0};
-  return launch_gemm_tn_tma(A, lda, M, K, 1, &k0, &sb, cs, bs, lds, N, splits, B2, ldb2, Cp2, c2_split, st);
+  return launch_gemm_tn_tma(A, lda, M, K, 1, &k0, &sb, cs, bs, lds, N, splits, B2, ldb2, Cp2, c2_split, st, relu_b);
 }
 
 }  // namespace regt
@@ -642,7 +648,7 @@ extern "C" int regt_debug_gemm_nt_tma(const float* A, int64_t lda, const float* 
 }
 extern "C" int regt_debug_gemm_tn_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* Cp, int64_t M, int32_t K,
                                       int32_t N, int32_t splits, const float* B2, int64_t ldb2, float* Cp2, regt_stream_t stream) {
-  return regt::launch_gemm_tn_auto(A, lda, B, ldb, Cp, M, K, N, splits, (cudaStream_t)stream, B2, ldb2, Cp2, 0);
+  return regt::launch_gemm_tn_auto(A, lda, B, ldb, Cp, M, K, N, splits, (cudaStream_t)stream, B2, ldb2, Cp2, 0, 0);
 }
 // four-segment form used by the cell backward: A = D [M][4H]; segments z|r (B = h), h~ (B = hR), h_pre (B2 only)
 extern "C" int regt_debug_gemm_tn_multi(const float* A, int64_t lda, int64_t M, int32_t H, const float* B0, const float* B1,
@@ -651,5 +657,5 @@ extern "C" int regt_debug_gemm_tn_multi(const float* A, int64_t lda, int64_t M, 
   float* cs[3] = {C0, C1, nullptr};
   const float* bs[2] = {B0, B1};
   const long long lds[2] = {H, H};
-  return regt::launch_gemm_tn_tma(A, lda, M, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, B2, 32, C2, 0, (cudaStream_t)stream);
+  return regt::launch_gemm_tn_tma(A, lda, M, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, B2, 32, C2, 0, (cudaStream_t)stream, 0);
 }

@@ -481,8 +481,8 @@ int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   return 0;
 }
 
-int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N,
-                          int splits, cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split, int relu_b);
+int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N, int splits,
+                        cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split, int relu_b);
 // out[r] (+)= sum over splits of Cp2[s][r][col]   (one column of a [splits][rows][32] partial array)
 __global__ void k_pick_col(const float* __restrict__ Cp2, int splits, int rows, int col, int acc, float* __restrict__ out) {
   const int r = threadIdx.x;
@@ -522,16 +522,18 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   k_head_bwd<<<nblk, TMH * 4, smem, st>>>(k);
   REGT_LAUNCHED("k_head_bwd", st);
   // weight gradients: dW2 = d_out^T a1, dW1 = d_a1^T relu(hid); biases = column sums
-  const int splits = (int)max(1ll, min(32ll, BN / 128));
+  // split-K over the rows: enough splits to fill the SMs (partials are summed in a fixed order by k_reduce_splits)
+  const int splits = (int)max(1ll, min(128ll, BN / 128));
   float* part = L.part;
-  if (false && a->precision == REGT_PREC_TF32X3 && H % 16 == 0) {   // measured slower than the SIMT split-K path (cfg4: +8.6 ms/step)
-    // tensor cores (3xTF32 row contraction): dW1 = d_a1^T relu(hid) and, in the same pass over d_a1, its column sums
+  if (a->precision == REGT_PREC_TF32X3 && H % 32 == 0 && BN >= 128) {
+    // tensor cores (TMA-fed 3xTF32 row contraction): dW1 = d_a1^T relu(hid) and, in the same pass over d_a1, its column sums
     // (column 16 of the cell's feature plane is all ones; its first BN rows serve as the second operand)
-    float* p1 = part;                                        // [splits][128][H]
-    float* p2 = part + (size_t)splits * HEAD_HID * H;        // [splits][128][32]
-    if (launch_gemm_tn_tf32x3(L.d_a1, HEAD_HID, a->out_hidden, H, p1, BN, HEAD_HID, H, splits, st, L.Feat, 32, p2, 0, 1)) return -1;
-    if (launch_reduce_splits(p1, a->g.head_w1, (long long)HEAD_HID * H, splits, a->accumulate, st)) return -1;
-    k_pick_col<<<1, HEAD_HID, 0, st>>>(p2, splits, HEAD_HID, 16, a->accumulate, a->g.head_b1);
+    const int s1 = (int)max(1ll, min((long long)cdiv(148, cdiv(H, 128)), BN / 256));
+    float* p1 = part;                                    // [s1][128][H]
+    float* p2 = part + (size_t)s1 * HEAD_HID * H;        // [s1][128][32]
+    if (launch_gemm_tn_auto(L.d_a1, HEAD_HID, a->out_hidden, H, p1, BN, HEAD_HID, H, s1, st, L.Feat, 32, p2, 0, 1)) return -1;
+    if (launch_reduce_splits(p1, a->g.head_w1, (long long)HEAD_HID * H, s1, a->accumulate, st)) return -1;
+    k_pick_col<<<1, HEAD_HID, 0, st>>>(p2, s1, HEAD_HID, 16, a->accumulate, a->g.head_b1);
     REGT_LAUNCHED("k_pick_col", st);
     TNBatch tb{};
     tb.nprob = 1;

@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_model_parity.py tests/test_gpu_plan_spmm.py tests/test_gpu_shard.py -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -n 3 gpurun_out/pytest_gpu.log
+show() { python - "$1" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+k=d["kernels"]
+print(sys.argv[1], round(d["value"]), "samples/s", round(d["ms_per_step"]*1000,1), "us; e2e", round(d["e2e"]["value"]), {n: v["ms_per_step"] for n, v in k.items()})
+PY
+}
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/f_base.json 2>gpurun_out/f_base.err; show gpurun_out/f_base.json
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/f_base.json 2>gpurun_out/f_base.err; show gpurun_out/f_base.json
