@@ -57,6 +57,8 @@ def parse():
                     help="N>1: 'region' = each GPU owns a set of regions (strong scaling, SURVEY 8(e)); "
                          "'batch' = each GPU runs its own per-GPU batch (weak scaling); auto = region when the workload has regions")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the gradient all-reduce as one kernel over NVLink peer memory (csrc/peer.cu) or through NCCL")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -244,6 +246,7 @@ def main():
     graph_args = tuple(None if a is None else a.to(dev) for a in w.graph_args())
 
     from regt_b200 import shard as S
+    os.environ["REGT_EXCHANGE"] = args.exchange
     sharded = world > 1 and w.R > 0 and args.shard != "batch"
     if args.shard == "region" and world > 1 and w.R == 0:
         raise SystemExit("--shard region needs a regional workload (3, 4 or 5)")
@@ -284,7 +287,7 @@ def main():
     launches_per_step = lib.regt_launch_count(1) // max(3, args.warmup)
 
     def exchange(loss):
-        """the exchange step: shared-weight gradients + loss, ONE NCCL all-reduce of the flat buffer"""
+        """the exchange step: shared-weight gradients + loss, ONE all-reduce of the flat buffer (peer-memory kernel or NCCL)"""
         if not sharded:
             ex.add_loss(loss)
         return ex.sync()
@@ -354,8 +357,11 @@ def main():
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    align = torch.zeros(1, device=dev)
     for a, b in evs:
         flush.zero_()                      # evict L2 between timed iterations (outside the event pair)
+        if dist is not None:
+            dist.all_reduce(align)         # ... and re-align the ranks: the flush's skew is not part of the step
         a.record(); step(); b.record()
     barrier()
     per = [a.elapsed_time(b) for a, b in evs]
@@ -501,6 +507,8 @@ def main():
     if rank == 0:
         job_B = B if sharded else world * B     # snapshots the whole job processes per step
         h2d_bytes = xh.numel() * 4 + yh.numel() * 4
+        xport = {"peer": "one-kernel all-reduce over NVLink peer memory (CUDA IPC, csrc/peer.cu)", "nccl": "NCCL all-reduce",
+                 "gloo": "gloo all-reduce"}[ex.transport] if world > 1 else ""
         out = {
             "metric": METRIC, "value": job_B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -510,9 +518,9 @@ def main():
             "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, l2="flushed between timed steps (256 MiB memset)",
                            cuda_graph=graph is not None, exchange_in_graph=graph_has_exchange, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
                            parallelism=("single GPU" if world == 1 else
-                                        f"region-sharded x{world} (LPT regions->ranks, halo rows of x read locally), NCCL all-reduce of the flat gradient buffer"
+                                        f"region-sharded x{world} (LPT regions->ranks, halo rows of x read locally), {xport} of the flat gradient buffer"
                                         if sharded else
-                                        f"batch-sharded x{world}, NCCL all-reduce of the flat gradient buffer")),
+                                        f"batch-sharded x{world}, {xport} of the flat gradient buffer")),
             "clocks": clocks,
             "e2e": {"value": job_B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "pipeline": "double-buffered H2D on a copy stream; each step's loss read on the host one step late"},

@@ -183,6 +183,28 @@ int regt_head_backward(const regt_args* a);
  * wrt x is produced (x is data in the reference: batch.x never requires grad).          */
 int regt_cell_backward(const regt_args* a);
 
+/* ---- exchange step over NVLink peer memory (csrc/peer.cu) ------------------------------
+ * one sum all-reduce of the flat shared-weight gradient buffer per step.  The
+ * reference has no distributed path; these entry points replace what a DistributedDataParallel
+ * wrapper around run.py:190 would do with NCCL.  A rank allocates ONE communication region
+ * [flags | data | scratch], the others map it through CUDA IPC; the wgrad kernels write
+ * straight into `data`; regt_peer_allreduce_f32 is a single kernel (per-block flag barrier,
+ * peer reads in rank order -> bit-identical sums on every rank, copy back), capturable in a
+ * CUDA graph.  Explicit allocation: a peer-mappable region must be a whole cudaMalloc block. */
+size_t regt_comm_region_bytes(int64_t n_floats);
+size_t regt_comm_data_offset(void);
+int regt_comm_alloc(size_t bytes, void** ptr);
+int regt_comm_free(void* ptr);
+int regt_comm_export(void* ptr, unsigned char* handle64 /*host, 64 bytes*/);
+int regt_comm_import(const unsigned char* handle64 /*host*/, void** peer_ptr);
+int regt_comm_unimport(void* peer_ptr);
+/* last_in (optional, device): added to this rank's element n_floats - 4 (the loss slot) before the sum;
+ * last_out (optional, device): receives the reduced loss slot, which is then cleared.  Both need n_floats <= 2^18. */
+int regt_peer_allreduce_f32(void* const* regions /*host array [world]*/, int32_t rank, int32_t world, int64_t n_floats,
+                            const float* last_in, float* last_out, regt_stream_t stream);
+int64_t regt_peer_push_max_floats(void);
+int regt_comm_error(void* region);
+
 int regt_version(void);
 const char* regt_last_error(void);
 /* number of kernel launches issued by this library on the calling thread since the last

@@ -50,7 +50,9 @@ PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
 EXPORTS = ["regt_version", "regt_last_error", "regt_launch_count", "regt_plan_workspace_bytes",
            "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_gather_rows", "regt_scatter_rows", "regt_workspace_bytes",
            "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward",
-           "regt_profile", "regt_profile_begin", "regt_profile_read"]
+           "regt_profile", "regt_profile_begin", "regt_profile_read",
+           "regt_comm_region_bytes", "regt_comm_data_offset", "regt_comm_alloc", "regt_comm_free", "regt_comm_export",
+           "regt_comm_import", "regt_comm_unimport", "regt_peer_allreduce_f32", "regt_peer_push_max_floats", "regt_comm_error"]
 
 _lib = None
 
@@ -104,6 +106,24 @@ def load() -> C.CDLL:
     lib.regt_profile_begin.argtypes = [vp]
     lib.regt_profile_read.restype = C.c_int
     lib.regt_profile_read.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
+    lib.regt_comm_region_bytes.restype = C.c_size_t
+    lib.regt_comm_region_bytes.argtypes = [C.c_int64]
+    lib.regt_comm_data_offset.restype = C.c_size_t
+    lib.regt_comm_alloc.restype = C.c_int
+    lib.regt_comm_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.regt_comm_free.restype = C.c_int
+    lib.regt_comm_free.argtypes = [vp]
+    lib.regt_comm_export.restype = C.c_int
+    lib.regt_comm_export.argtypes = [vp, C.POINTER(C.c_ubyte)]
+    lib.regt_comm_import.restype = C.c_int
+    lib.regt_comm_import.argtypes = [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+    lib.regt_comm_unimport.restype = C.c_int
+    lib.regt_comm_unimport.argtypes = [vp]
+    lib.regt_peer_allreduce_f32.restype = C.c_int
+    lib.regt_peer_allreduce_f32.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
+    lib.regt_peer_push_max_floats.restype = C.c_int64
+    lib.regt_comm_error.restype = C.c_int
+    lib.regt_comm_error.argtypes = [vp]
     lib.regt_debug_gemm_nt.restype = C.c_int
     lib.regt_debug_gemm_nt.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp]
     lib.regt_debug_gemm_tn.restype = C.c_int

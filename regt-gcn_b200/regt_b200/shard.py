@@ -20,6 +20,8 @@ Host logic (partition, halo, CSR slicing, reassembly) is plain numpy/torch and r
 too, which is how tests/test_shard_cpu.py covers it with world_size-2 gloo groups."""
 from __future__ import annotations
 
+import os
+import sys
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -206,26 +208,115 @@ def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> tor
 # ------------------------------------------------------------------------------------------
 # the exchange step (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests)
 # ------------------------------------------------------------------------------------------
-def flatten_grads(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
-    """one flat buffer (fp32 in the product; the CPU tests use fp64 oracle modules) behind every ``.grad`` so that ONE all-reduce covers all shared weights."""
+def _flat_layout(params: Sequence[torch.nn.Parameter]):
     offs, tot = [], 0
     for p in params:
         offs.append(tot)
         tot += (p.numel() + 3) // 4 * 4
-    flat = torch.zeros(tot + 4, device=params[0].device, dtype=params[0].dtype)   # last 4: loss slot
+    return offs, tot + 4      # last 4: loss slot
+
+
+def flatten_grads(params: Sequence[torch.nn.Parameter], flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """one flat buffer (fp32 in the product; the CPU tests use fp64 oracle modules) behind every ``.grad`` so that ONE all-reduce covers all shared weights."""
+    offs, tot = _flat_layout(params)
+    if flat is None:
+        flat = torch.zeros(tot, device=params[0].device, dtype=params[0].dtype)
     for p, o in zip(params, offs):
         p.grad = flat[o:o + p.numel()].view_as(p)
     return flat
 
 
+class _DeviceSpan:
+    """zero-copy torch view of device memory owned by libregt_b200 (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerRegion:
+    """one rank's NVLink communication region (include/regt_b200.h, csrc/peer.cu): ``[flags | data | scratch]`` in one
+    cudaMalloc block, mapped into every other rank of the node through CUDA IPC.  ``data`` is exposed as a torch
+    tensor (the flat gradient buffer); ``allreduce()`` is ONE kernel launch on the current stream."""
+
+    def __init__(self, n_floats: int, device: torch.device, rank: int, world: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        self.lib, self.rank, self.world, self.n = _lib.load(), rank, world, n_floats
+        lib = self.lib
+        torch.cuda.set_device(device)
+        self.base = C.c_void_p()
+        _lib.check(lib.regt_comm_alloc(lib.regt_comm_region_bytes(n_floats), C.byref(self.base)), "regt_comm_alloc")
+        handle = (C.c_ubyte * 64)()
+        _lib.check(lib.regt_comm_export(self.base, handle), "regt_comm_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        every = torch.empty(world * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        every = every.cpu().view(world, 64)
+        self.peers = []
+        regions = []
+        for r in range(world):
+            if r == rank:
+                regions.append(self.base.value)
+                continue
+            h = (C.c_ubyte * 64)(*every[r].tolist())
+            ptr = C.c_void_p()
+            _lib.check(lib.regt_comm_import(h, C.byref(ptr)), "regt_comm_import")
+            self.peers.append(ptr)
+            regions.append(ptr.value)
+        self.regions = (C.c_void_p * world)(*regions)
+        self.data = torch.as_tensor(_DeviceSpan(self.base.value + lib.regt_comm_data_offset(), n_floats), device=device)
+        dist.barrier(group=group)      # every rank has mapped every region before the first all-reduce
+
+    def allreduce(self, last_in: Optional[torch.Tensor] = None, last_out: Optional[torch.Tensor] = None) -> None:
+        """in-place sum over the ranks of ``data``.  Push path only (``n <= regt_peer_push_max_floats()``): ``last_in`` (one
+        float) is added to this rank's loss slot ``data[-4]`` first; ``last_out`` receives the reduced slot, which is cleared."""
+        from . import _lib
+        _lib.check(self.lib.regt_peer_allreduce_f32(self.regions, self.rank, self.world, self.n,
+                                                    None if last_in is None else last_in.data_ptr(),
+                                                    None if last_out is None else last_out.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "regt_peer_allreduce_f32")
+
+    @property
+    def push(self) -> bool:
+        return self.n <= int(self.lib.regt_peer_push_max_floats()) and os.environ.get("REGT_PEER_PULL", "0") != "1"
+
+    def error(self) -> int:
+        return int(self.lib.regt_comm_error(self.base))
+
+
 class GradExchange:
     """the per-step exchange of a sharded job: every ``.grad`` of ``params`` is a view into ONE flat
     fp32 buffer (so the wgrad kernels write straight into the communication buffer), whose last
-    slots carry the loss; ``sync()`` is one sum all-reduce of that buffer."""
+    slots carry the loss; ``sync()`` is one sum all-reduce of that buffer.
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], world: int, group=None):
+    ``transport``: ``"peer"`` = the one-kernel all-reduce over NVLink peer memory (csrc/peer.cu; the buffer then lives in
+    a CUDA-IPC region), ``"nccl"`` = ``torch.distributed.all_reduce``; ``None`` picks ``"peer"`` on CUDA with world > 1
+    when every rank can map every region (env ``REGT_EXCHANGE=nccl`` forces NCCL), otherwise the process group's backend
+    (gloo in the CPU tests)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], world: int, group=None, transport: Optional[str] = None,
+                 rank: Optional[int] = None):
         self.params, self.world, self.group = list(params), world, group
-        self.flat = flatten_grads(self.params)
+        self.region = None
+        dev = self.params[0].device
+        want_peer = transport == "peer" or (transport is None and os.environ.get("REGT_EXCHANGE", "peer") != "nccl")
+        import torch.distributed as dist
+        if world > 1 and dev.type == "cuda" and self.params[0].dtype == torch.float32 and want_peer and dist.is_available() \
+                and dist.is_initialized():
+            rank = dist.get_rank(group) if rank is None else rank
+            _, tot = _flat_layout(self.params)
+            ok = torch.ones(1, device=dev)
+            try:
+                self.region = PeerRegion(tot, dev, rank, world, group)
+            except Exception as e:  # noqa: BLE001  (no P2P / IPC between these devices: every rank falls back together)
+                print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using the process group's all_reduce", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if not bool(ok.item()):
+                self.region = None
+        self.transport = "peer" if self.region is not None else ("nccl" if dev.type == "cuda" else "gloo")
+        self.flat = flatten_grads(self.params, None if self.region is None else self.region.data)
 
     def add_loss(self, loss: torch.Tensor) -> None:
         self.flat[-4:-3].add_(loss.reshape(1).to(self.flat.dtype))
@@ -233,8 +324,15 @@ class GradExchange:
     def sync(self) -> torch.Tensor:
         """returns the global loss accumulated since the last sync and clears the slot."""
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat, group=self.group)
+            if self.region is not None and self.region.push:
+                loss = torch.empty(1, device=self.flat.device)     # the kernel hands back the reduced loss and clears its slot
+                self.region.allreduce(None, loss)
+                return loss
+            if self.region is not None:
+                self.region.allreduce()
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(self.flat, group=self.group)
         loss = self.flat[-4:-3].clone()
         self.flat[-4:].zero_()
         return loss

@@ -115,3 +115,20 @@ def test_two_process_nccl_region_shards(tmp_path):
     for k, g in ref["grads"].items():
         if not is_dead(w.model, k):
             assert relerr(got["grads"][k], g) <= 1e-5, k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_peer_memory_allreduce_bit_exact_and_graph_capturable():
+    """csrc/peer.cu: the one-kernel NVLink all-reduce sums in rank order (bit-identical to the explicit sum on every
+    rank), survives repeated calls (device-side epochs) and CUDA-graph replay, and carries GradExchange's flat buffer."""
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_allreduce_worker.py")
+    world = min(torch.cuda.device_count(), 8)
+    port = 31700 + os.getpid() % 2000
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), str(port)]) for r in range(world)]
+    try:
+        for p in procs:
+            assert p.wait(timeout=300) == 0
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
