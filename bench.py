@@ -57,8 +57,9 @@ def parse():
                     help="N>1: 'region' = each GPU owns a set of regions (strong scaling, SURVEY 8(e)); "
                          "'batch' = each GPU runs its own per-GPU batch (weak scaling); auto = region when the workload has regions")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: the gradient all-reduce as one kernel over NVLink peer memory (csrc/peer.cu) or through NCCL")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: the gradient all-reduce as one kernel over NVLink peer memory (csrc/peer.cu) or through NCCL; "
+                         "auto = peer kernel up to 2^18 floats (its push path), NCCL above")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -439,24 +440,34 @@ def main():
         breakdown = {k: {"ms_per_step": round(v, 5), "launches": counts[k], "share": round(v / step_sum, 4)}
                      for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
         pk = peaks()
-        ab = kernel_alg_bytes(w, B if not args.micro_batch else min(B, args.micro_batch))
+        ab = kernel_alg_bytes(w, min(B, args.micro_batch or getattr(sm.model if sharded else model, '_mb', None) or B))
         dom = max((k for k in per_kernel if k in ab), key=lambda k: per_kernel[k], default=None)
-        if args.precision == "tf32x3" and "k_gemm_nt_tf32x3" in per_kernel:
-            # generic 3xTF32 path: the H x H contractions dominate -> tensor-pipe roofline.  Algorithmic flops of the NT
-            # GEMMs per step: 2*rows*H*H * (2 [z,r] + 1 [c] + 1 [dHR] + 2 [dhg]); the hardware executes 3 tf32 products
-            # per contraction at half the bf16 rate, so the attainable fp32-equivalent peak is bf16_peak / 6.
-            mbB = B if not args.micro_batch else min(B, args.micro_batch)
-            nmb = (B + mbB - 1) // mbB
-            flops = 2.0 * B * w.N * w.T * w.H * w.H * 6
-            t_all = per_kernel["k_gemm_nt_tf32x3"] * 1e-3
-            ach = flops / t_all / 1e12
-            peak = pk["bf16_tflops"] / 6.0
-            roofline = {"kernel": "k_gemm_nt_tf32x3", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        mb_used = args.micro_batch or getattr(sm.model if sharded else model, "_mb", None) or B
+        mb_used = min(B, mb_used)
+        if args.precision == "tf32x3" and "k_gemm_nt_tma" in per_kernel:
+            # generic 3xTF32 path: the H x H gate contractions (TMA-fed tcgen05 GEMMs, csrc/gemm_tma.cu) dominate.
+            # Algorithmic work of the six NT GEMMs per step (z, r, c forward; dHR, dhg (K = 2H) backward):
+            #   flops = 2*rows*H*H * (2 + 1 + 1 + 2);   bytes = rows * 4 * (2H + 2H + 2H + 2H + 3H)   (A read once, C written once)
+            # The hardware executes 3 tf32 products per contraction at half the bf16 rate -> fp32-equivalent peak = bf16 / 6.
+            # The binding roofline is whichever of the two times is longer (H = 128: HBM; H = 256: tensor pipe).
+            nmb = (B + mb_used - 1) // mb_used
+            rows_ = float(B) * w.N * w.T
+            flops = 2.0 * rows_ * w.H * w.H * 6
+            nbytes = rows_ * 4.0 * 11 * w.H
+            t_all = per_kernel["k_gemm_nt_tma"] * 1e-3
+            peak_tc = pk["bf16_tflops"] / 6.0
+            t_tc, t_hbm = flops / (peak_tc * 1e12), nbytes / (pk["hbm_gbs"] * 1e9)
+            if t_hbm >= t_tc:
+                ach, peak, unit, bound = nbytes / t_all / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
+            else:
+                ach, peak, unit, bound = flops / t_all / 1e12, peak_tc, "TFLOP/s", "tensor"
+            roofline = {"kernel": "k_gemm_nt_tma", "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                         "frac": ach / peak, "traffic": None,
-                        "peak_source": pk["source"] + ": bf16 dense / 6 (tf32 = half the bf16 rate, 3 products per contraction)",
-                        "alg_flops_per_step": flops, "launches_per_step": counts["k_gemm_nt_tf32x3"], "micro_batches": nmb,
-                        "launch_ms": per_kernel["k_gemm_nt_tf32x3"] / counts["k_gemm_nt_tf32x3"],
-                        "share_of_step": per_kernel["k_gemm_nt_tf32x3"] / step_sum}
+                        "peak_source": pk["source"] + ("" if bound == "hbm" else ": bf16 dense / 6 (tf32 = half the bf16 rate, 3 products per contraction)"),
+                        "alg_flops_per_step": flops, "alg_bytes_per_step": nbytes, "t_tensor_ms": t_tc * 1e3, "t_hbm_ms": t_hbm * 1e3,
+                        "launches_per_step": counts["k_gemm_nt_tma"], "micro_batches": nmb,
+                        "launch_ms": per_kernel["k_gemm_nt_tma"] / counts["k_gemm_nt_tma"],
+                        "share_of_step": per_kernel["k_gemm_nt_tma"] / step_sum}
         elif dom is not None:
             t_launch = per_kernel[dom] / counts[dom] * 1e-3
             ach = ab[dom] / t_launch / 1e9
@@ -477,9 +488,10 @@ def main():
 
     # ---------------- the fp32 (1e-5 parity) mode of the same step, same inputs, same run ----------------
     fp32_mode = None
-    if rank == 0 and world == 1 and args.precision != "fp32" and str(args.workload) == "2":   # small config only: a second workspace
-        m32 = (TemporalGCN(8, w.T, w.O, hidden=w.H, precision="fp32") if w.model == "TemporalGCN"
-               else RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R, precision="fp32"))
+    if rank == 0 and world == 1 and args.precision == "bf16" and str(args.workload) == "2":   # small config only: a second workspace
+        p32 = "tf32x3" if w.H % 32 == 0 else "fp32"
+        m32 = (TemporalGCN(8, w.T, w.O, hidden=w.H, precision=p32) if w.model == "TemporalGCN"
+               else RegionalTemporalGCN(8, w.N, w.T, w.O, hidden=w.H, n_regions=w.R, precision=p32))
         W.init_params_synthetic(m32, 1234)
         m32 = m32.to(dev)
         xd, yd = bufs[0]
@@ -494,7 +506,9 @@ def main():
             ts.append(a_.elapsed_time(b_))
         ms32 = sum(ts) / len(ts)
         fp32_mode = {"value": B / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "steps": 5,
-                     "note": "precision=fp32 (FFMA kernels, 1e-5 normwise parity vs the fp64 oracle), eager launches"}
+                     "precision": p32,
+                     "note": "fp32-equivalent arithmetic (tf32x3 = 3xTF32 split on the tensor cores with TMA-fed GEMMs, fp32 = FFMA kernels): "
+                             "1e-5 normwise parity vs the fp64 oracle on every output and gradient; eager launches"}
         del m32
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
@@ -515,7 +529,7 @@ def main():
             "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor cores)", "bf16": "bf16 operands, f32 accumulate (f32 inputs, outputs, loss, gradients)"}[args.precision],
             "data": "synthetic",
-            "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, l2="flushed between timed steps (256 MiB memset)",
+            "config": dict(w.describe(), per_gpu_batch=B, precision=args.precision, micro_batch=mb_used, l2="flushed between timed steps (256 MiB memset)",
                            cuda_graph=graph is not None, exchange_in_graph=graph_has_exchange, optimizer="none: metric is fwd+bwd; the reference steps once per epoch (run.py:194)",
                            parallelism=("single GPU" if world == 1 else
                                         f"region-sharded x{world} (LPT regions->ranks, halo rows of x read locally), {xport} of the flat gradient buffer"

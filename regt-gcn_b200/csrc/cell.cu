@@ -351,7 +351,27 @@ __global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ D, c
     const int node = seg_node[s];
     const float* ur = U + ((size_t)b * nseg + s) * F * T;
     const float* dr = D + (((size_t)b * N + node) * T) * 4 * H + 3 * H + n;
-    for (int t = 0; t < T; ++t) {
+    int t = 0;
+    for (; t + 4 <= T; t += 4) {   // four periods' loads in flight (the chain of fmas is short, the loads are not)
+      float d[4], u[4][F];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] = __ldg(dr + (size_t)(t + k) * 4 * H);
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        if (T % 4 == 0) {
+          const float4 u4 = __ldg(reinterpret_cast<const float4*>(ur + f * T + t));
+          u[0][f] = u4.x; u[1][f] = u4.y; u[2][f] = u4.z; u[3][f] = u4.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) u[k][f] = __ldg(ur + f * T + t + k);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(d[k], u[k][f], acc[f]);
+    }
+    for (; t < T; ++t) {
       const float d = __ldg(dr + (size_t)t * 4 * H);
 #pragma unroll
       for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(ur + f * T + t), acc[f]);
@@ -528,7 +548,7 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
 int launch_wgrad_m1(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, T = a->T, R = a->plan.R;
   float* part = L.part;
-  const int zs = (int)max(1ll, min(64ll, 1024ll / ((long long)R * cdiv(H, 128))));
+  const int zs = (int)max(1ll, min(256ll, 2048ll / ((long long)R * cdiv(H, 128))));   // zs * R <= 2048 partial blocks
   k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
                                                       a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
   REGT_LAUNCHED("k_wgrad_m1", st);

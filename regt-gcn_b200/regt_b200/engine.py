@@ -130,6 +130,28 @@ def build_state(mode: int, precision: int, plan: GraphPlanTensors, x: torch.Tens
     return st
 
 
+def workspace_bytes(mode: int, precision: int, plan: GraphPlanTensors, B: int, x_rows: int, T: int, H: int, O: int) -> int:
+    """bytes ``build_state`` will ask for at batch B (saved planes scale with B*N*T*H): used to size micro-batches."""
+    a = _lib.Args()
+    a.B, a.N, a.T, a.H, a.O = B, plan.N, T, H, O
+    a.mode, a.precision, a.x_rows = mode, precision, x_rows
+    a.fuse_head = 1
+    a.plan = plan.c_struct()
+    return int(_lib.load().regt_workspace_bytes(C.byref(a)))
+
+
+def auto_micro_batch(mode: int, precision: int, plan: GraphPlanTensors, B: int, x_rows: int, T: int, H: int, O: int,
+                     have: int = 0) -> int:
+    """largest divisor of B whose workspace fits 70 % of the free device memory (plus what a cached workspace of
+    ``have`` bytes already holds); SURVEY 8d: cfg 4/5 save 63 / 157 GB of planes at full B, so they micro-batch inside the step."""
+    free, _ = torch.cuda.mem_get_info()
+    budget = int(0.7 * (free + have))
+    for mb in sorted({d for d in range(1, B + 1) if B % d == 0}, reverse=True):
+        if workspace_bytes(mode, precision, plan, mb, x_rows, T, H, O) <= budget:
+            return mb
+    return 1
+
+
 def run_forward(st: StepState, head: bool = True) -> None:
     lib = _lib.load()
     st.args.stream = _stream()

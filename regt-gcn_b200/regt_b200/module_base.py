@@ -104,7 +104,16 @@ class RegTModelBase(nn.Module):
                 p.grad = torch.zeros_like(p)
             grads[k] = p.grad
         B = xb.shape[0]
-        mb = B if not micro_batch else min(B, micro_batch)
+        if micro_batch:
+            mb = min(B, micro_batch)
+        else:   # whole batch if its saved planes fit, else the largest divisor of B that does (decided once per shape)
+            key = (B, xb.shape[1], xb.shape[3])
+            if getattr(self, "_mb_key", None) != key:
+                ws = getattr(self, "_ws", None)
+                self._mb = engine.auto_micro_batch(self._mode, self._prec(), plan, B, xb.shape[1], xb.shape[3], self._hidden,
+                                                   self.output_dim, 0 if ws is None else ws.numel())
+                self._mb_key = key
+            mb = self._mb
         loss = None
         outs, hids = [], []
         for b0 in range(0, B, mb):
