@@ -117,6 +117,17 @@ struct NtArgs {
   int N, K;
   int resident;               // Bt hi/lo parked in shared memory for the whole kernel
   int ns;                     // pipeline stages
+  // fused gate epilogue (epi != 0):  g = sigmoid(acc + cb[n] + sum_f feat[row][f] * Ws[f][n])   -> C
+  //                     epi == 2:   additionally C2[row][n] = aux[row][n] * g                     (h * R)
+  int epi;
+  const float* Ws;            // [F][ldw] F-wide part of the gate weights, column n of this GEMM at Ws[f * ldw + n]
+  long long ldw;
+  const float* cb;            // [N]
+  const float* feat;          // [M][32] feature plane, S_t in columns 0..7
+  const float* aux;           // [M][ldaux]
+  long long ldaux;
+  float* C2;
+  long long ldc2;
 };
 constexpr int NT_CONV = 256;                    // converter threads (warps 0-7)
 constexpr int NT_W_TMA = NT_CONV / 32;          // producer warp
@@ -256,6 +267,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_gemm_nt_tma(const __grid_cons
       const long long arow = m0 + r;
       const bool a_ok = arow < a.M;
       float* cp = a.C + (a_ok ? arow : 0) * a.ldc + n0;
+      float sf[REGT_F];
+      if (a.epi && a_ok) {   // this row's S_t (the F-wide input of the gate), read while the accumulator is still filling
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.feat + arow * 32));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.feat + arow * 32) + 1);
+        sf[0] = s0.x; sf[1] = s0.y; sf[2] = s0.z; sf[3] = s0.w; sf[4] = s1.x; sf[5] = s1.y; sf[6] = s1.z; sf[7] = s1.w;
+      }
       mbar_wait(&bar_acc_full[buf], (uint32_t)((li / 2) & 1));
       tc_fence_after();
       for (int c0 = 0; c0 < nt; c0 += 32) {
@@ -270,9 +287,37 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_gemm_nt_tma(const __grid_cons
         }
         if (a_ok) {
           const int w = min(32, nt - c0);
+          if (a.epi) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < w) {   // warp-uniform weight loads (every lane reads the same columns): one broadcast each
+                const int col = n0 + c0 + j;
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.cb + col));
+                float x[4] = {v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w};
+#pragma unroll
+                for (int f = 0; f < REGT_F; ++f) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.Ws + f * a.ldw + col));
+                  x[0] = fmaf(sf[f], w4.x, x[0]); x[1] = fmaf(sf[f], w4.y, x[1]);
+                  x[2] = fmaf(sf[f], w4.z, x[2]); x[3] = fmaf(sf[f], w4.w, x[3]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[j + e] = 1.0f / (1.0f + expf(-x[e]));
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             if (j < w) *reinterpret_cast<float4*>(cp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (a.epi == 2) {
+            const float* ax = a.aux + arow * a.ldaux + n0 + c0;
+            float* c2 = a.C2 + arow * a.ldc2 + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < w) {
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(ax + j));
+                *reinterpret_cast<float4*>(c2 + j) = make_float4(h4.x * v[j], h4.y * v[j + 1], h4.z * v[j + 2], h4.w * v[j + 3]);
+              }
+          }
         }
       }
       tc_fence_before();
@@ -555,7 +600,8 @@ size_t gemm_nt_scratch_floats(int N, int K) { return (size_t)2 * ((N + 127) / 12
 // C[M][N] = A[M][K] . Bt[N][K]^T ; `scratch` (gemm_nt_scratch_floats(N, K) floats) receives the hi / lo images of Bt.
 // Falls back to the register-fed kernel when the TMA preconditions do not hold.
 int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M, int N,
-                       int K, float* scratch, cudaStream_t st) {
+                       int K, float* scratch, cudaStream_t st, const NtGate* gate) {
+  REGT_CHECK(!gate || (!legacy_forced() && scratch && M >= 128 && N % 16 == 0 && K % 4 == 0), "gemm_nt_tma: the fused gate epilogue needs the TMA path");
   if (legacy_forced() || !scratch || M < 128 || N % 16 != 0 || K % 4 != 0 || lda % 4 != 0 || ((uintptr_t)A % 16) != 0 ||
       ((uintptr_t)scratch % 16) != 0)
     return launch_gemm_nt_tf32x3(A, lda, Bt, ldb, C, ldc, M, N, K, st);
@@ -570,6 +616,14 @@ int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long
   if (tmap_2d(&a.tbh, hi, Kp, Np, Kp, 128, "gemm_nt_tma(B hi)")) return -1;
   if (tmap_2d(&a.tbl, lo, Kp, Np, Kp, 128, "gemm_nt_tma(B lo)")) return -1;
   a.C = C; a.M = M; a.ldc = ldc; a.N = N; a.K = K;
+  if (gate) {
+    REGT_CHECK(gate->Ws && gate->cb && gate->feat && gate->ldw % 4 == 0 && ((uintptr_t)gate->Ws % 16) == 0 && ((uintptr_t)gate->cb % 16) == 0 &&
+                   (!gate->C2 || (gate->aux && gate->ldaux % 4 == 0 && gate->ldc2 % 4 == 0)),
+               "gemm_nt_tma: bad gate epilogue operands");
+    a.epi = gate->C2 ? 2 : 1;
+    a.Ws = gate->Ws; a.ldw = gate->ldw; a.cb = gate->cb; a.feat = gate->feat;
+    a.aux = gate->aux; a.ldaux = gate->ldaux; a.C2 = gate->C2; a.ldc2 = gate->ldc2;
+  }
   a.resident = (N <= 128 && nchunks * 2 * TILE + 2 * 2 * TILE <= SMEM_BUDGET) ? 1 : 0;
   const int stage = a.resident ? 2 * TILE : 4 * TILE;
   const int fixed = a.resident ? nchunks * 2 * TILE : 0;
@@ -644,7 +698,14 @@ int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long
 // debug entry points (not part of the reference-facing ABI): tests/test_gpu_gemm.py
 extern "C" int regt_debug_gemm_nt_tma(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
                                       int32_t N, int32_t K, float* scratch, regt_stream_t stream) {
-  return regt::launch_gemm_nt_tma(A, lda, Bt, ldb, C, ldc, M, N, K, scratch, (cudaStream_t)stream);
+  return regt::launch_gemm_nt_tma(A, lda, Bt, ldb, C, ldc, M, N, K, scratch, (cudaStream_t)stream, nullptr);
+}
+// gate epilogue: C = sigmoid(A Bt^T + feat[:, 0:8] Ws + cb) ; C2 = aux * C (optional)
+extern "C" int regt_debug_gemm_nt_gate(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                                       int32_t N, int32_t K, float* scratch, const float* Ws, int64_t ldw, const float* cb,
+                                       const float* feat, const float* aux, int64_t ldaux, float* C2, int64_t ldc2, regt_stream_t stream) {
+  regt::NtGate g{Ws, ldw, cb, feat, aux, ldaux, C2, ldc2};
+  return regt::launch_gemm_nt_tma(A, lda, Bt, ldb, C, ldc, M, N, K, scratch, (cudaStream_t)stream, &g);
 }
 extern "C" int regt_debug_gemm_tn_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* Cp, int64_t M, int32_t K,
                                       int32_t N, int32_t splits, const float* B2, int64_t ldb2, float* Cp2, regt_stream_t stream) {

@@ -146,3 +146,31 @@ def test_gemm_tn_tma_stage_reuse_stress(M, K, N, splits):
         _lib.check(rc, "regt_debug_gemm_tn_tma")
         assert float((Cp.double().sum(0) - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
         assert float((Cp2.double().sum(0) - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max())
+
+
+@pytest.mark.parametrize("M,H,with_aux", [(1000, 128, False), (4099, 128, True), (3000, 256, True), (20000, 64, True)])
+def test_gemm_nt_gate_epilogue(M, H, with_aux):
+    """the gate GEMMs of the tf32x3 forward: sigmoid(h B^T + S W_s + c) computed in the epilogue warps (F-wide term as
+    fp32 FMAs on the accumulator, S from the feature plane), h * R written next to R."""
+    from regt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + H)
+    A = (torch.rand(M, H, generator=g) - 0.5).cuda()
+    W = (torch.rand(H, 2 * H, generator=g) - 0.5).cuda()        # linear_g.weight: the GEMM uses columns H..2H
+    Ws = (torch.rand(8, 2 * H, generator=g) - 0.5).cuda()       # [F][2H] collapsed F-wide weights, this gate = columns H..
+    cb = (torch.rand(2 * H, generator=g) - 0.5).cuda()
+    feat = torch.rand(M, 32, generator=g).cuda()
+    C = torch.full((M, H), float("nan"), device="cuda")
+    C2 = torch.full((M, H), float("nan"), device="cuda")
+    scratch = torch.empty(2 * ((H + 127) // 128 * 128) * H, device="cuda")
+    Bt = W[:, H:]
+    rc = lib.regt_debug_gemm_nt_gate(A.data_ptr(), H, Bt.data_ptr(), 2 * H, C.data_ptr(), H, M, H, H, scratch.data_ptr(),
+                                     Ws[:, H:].data_ptr(), 2 * H, cb[H:].data_ptr(), feat.data_ptr(),
+                                     A.data_ptr() if with_aux else None, H, C2.data_ptr() if with_aux else None, H, _st())
+    _lib.check(rc, "regt_debug_gemm_nt_gate")
+    ref = torch.sigmoid(A.double() @ Bt.double().t() + feat[:, :8].double() @ Ws[:, H:].double() + cb[H:].double())
+    assert relerr(C, ref) <= 1e-5
+    if with_aux:
+        assert relerr(C2, A.double() * ref) <= 1e-5
+    else:
+        assert torch.isnan(C2).all()
