@@ -6,10 +6,11 @@
 // all-reduce kernel then, per thread block b and without any grid-wide or host synchronisation:
 //   1. start barrier of block b across the ranks (one flag word per (phase, block, peer), stored with release.sys into
 //      the peer's region, polled with acquire.sys in the own region): every rank's data is complete;
-//   2. reads slice b of EVERY rank's data over NVLink (volatile 128-bit loads) and sums in rank order 0..W-1, so that all
-//      ranks produce bit-identical sums; the result goes to the local scratch;
-//   3. end barrier of block b: every peer has finished reading slice b of this rank's data;
-//   4. copies slice b of the scratch back over the own data.
+//   2. reduce-scatter: reads its part of chunk `rank` from EVERY rank's data over NVLink (volatile 128-bit loads) and sums
+//      in rank order 0..W-1 into the own scratch (each element is summed exactly once, by its owner);
+//   3. second barrier of block b: all sums are in place, every peer has finished reading this rank's data;
+//   4. all-gather: copies its part of every chunk from the owner's scratch over the own data -- every rank ends up with
+//      the same bits.
 // Small buffers (<= PEER_LL_MAX floats) take a push path instead (k_peer_allreduce_ll, NCCL's "LL" idea): every rank
 // STORES its values into a receive slot of every peer as 8-byte (value, epoch) words -- data and flag arrive in one
 // atomic store, one NVLink traversal, no barrier -- and sums what lands in its own slots, again in rank order.  Slots are
@@ -33,7 +34,7 @@ struct PeerArgs {
   float* data[PEER_MAXW];
   uint32_t* flags[PEER_MAXW];
   uint32_t* counter;   // own region, after the flag words
-  float* scratch;
+  float* scratch[PEER_MAXW];   // every rank's scratch (the reduce-scatter results are gathered from their owners)
   int* error;          // own region: set when a peer never arrived
   int rank, world;
   long long n4;        // float4 elements
@@ -78,6 +79,11 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int phase, uint3
   __syncthreads();
 }
 
+// pull path, two stages: rank r owns chunk r of the buffer.  Stage 1 (reduce-scatter): read chunk `rank` from every peer,
+// sum in rank order, keep the result in the own scratch.  Stage 2 (all-gather): copy every chunk's sum from its owner's
+// scratch into the own data.  Per rank 2 (W-1)/W * n * 4 bytes cross NVLink instead of (W-1) * n * 4 for a one-shot read.
+// Block b of every rank works on the same sub-slices of every chunk, so the two barriers are per block; the start barrier
+// of the NEXT call is what protects the scratch from being overwritten while a slow peer still gathers from it.
 __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(PeerArgs a) {
   __shared__ uint32_t epoch_s;
   if (threadIdx.x == 0) {
@@ -86,24 +92,33 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(PeerArgs a) {
   }
   __syncthreads();
   const uint32_t epoch = epoch_s;
-  peer_barrier(a, 0, epoch);
+  peer_barrier(a, 0, epoch);   // every rank's data is complete (and every rank has left the previous call)
+  const long long c4 = (a.n4 + a.world - 1) / a.world;           // float4 elements per chunk
   const long long stride = (long long)gridDim.x * PEER_THREADS;
-  float4* scratch = reinterpret_cast<float4*>(a.scratch);
-  for (long long i = blockIdx.x * (long long)PEER_THREADS + threadIdx.x; i < a.n4; i += stride) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const long long lo = (long long)a.rank * c4, hi = min(a.n4, lo + c4);
+    float4* scratch = reinterpret_cast<float4*>(a.scratch[a.rank]);
+    for (long long i = lo + blockIdx.x * (long long)PEER_THREADS + threadIdx.x; i < hi; i += stride) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < PEER_MAXW; ++r) {
-      if (r < a.world) {
-        const float4 v = ld_volatile4(reinterpret_cast<const float4*>(a.data[r]) + i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      for (int r = 0; r < PEER_MAXW; ++r) {
+        if (r < a.world) {
+          const float4 v = ld_volatile4(reinterpret_cast<const float4*>(a.data[r]) + i);
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
       }
+      scratch[i] = s;
     }
-    scratch[i] = s;
   }
-  peer_barrier(a, 1, epoch);
+  peer_barrier(a, 1, epoch);   // all sums are in place; every peer has finished reading this rank's data
   float4* mine = reinterpret_cast<float4*>(a.data[a.rank]);
-  for (long long i = blockIdx.x * (long long)PEER_THREADS + threadIdx.x; i < a.n4; i += stride) mine[i] = scratch[i];
+  for (int r = 0; r < a.world; ++r) {
+    const long long lo = (long long)r * c4, hi = min(a.n4, lo + c4);
+    const float4* src = reinterpret_cast<const float4*>(a.scratch[r]);
+    for (long long i = lo + blockIdx.x * (long long)PEER_THREADS + threadIdx.x; i < hi; i += stride) mine[i] = ld_volatile4(src + i);
+  }
 }
+
 // push path: thread = 2 consecutive floats
 __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce_ll(PeerArgs a) {
   __shared__ uint32_t epoch_s;
@@ -219,7 +234,7 @@ extern "C" int regt_peer_allreduce_f32(void* const* regions, int32_t rank, int32
   }
   a.counter = a.flags[rank] + 2 * PEER_MAXB * PEER_MAXW;
   a.error = (int*)((char*)regions[rank] + PEER_FLAG_BYTES - 64);
-  a.scratch = (float*)((char*)regions[rank] + PEER_FLAG_BYTES + align_up(n * sizeof(float), 256));
+  for (int r = 0; r < world; ++r) a.scratch[r] = (float*)((char*)regions[r] + PEER_FLAG_BYTES + align_up(n * sizeof(float), 256));
   a.rank = rank;
   a.world = world;
   a.n4 = (long long)(n / 4);

@@ -304,7 +304,7 @@ class GradExchange:
         self.region = None
         dev = self.params[0].device
         # transport None: the peer-memory kernel where it wins (push path, buffers up to 2^18 floats: 9 us vs NCCL 32 us at
-        # 8 GPUs); larger buffers go through NCCL, whose in-switch reduction moves 1/4 of the pull kernel's bytes
+        # 8 GPUs); larger buffers go through NCCL (17.7 MB at 8 GPUs: 104 us vs 113 us for the two-stage pull kernel)
         _, tot = _flat_layout(self.params)
         env = os.environ.get("REGT_EXCHANGE", "auto")
         want_peer = transport == "peer" or (transport is None and env == "peer") or \
