@@ -205,6 +205,19 @@ int regt_peer_allreduce_f32(void* const* regions /*host array [world]*/, int32_t
 int64_t regt_peer_push_max_floats(void);
 int regt_comm_error(void* region);
 
+/* ---- callers on either side of the path, on the device (csrc/loop.cu) ----
+ * regt_window_gather: load_dataset.py:451-457 + run.py:172 -- x[b,n,f,t] = node_data[n,f,starts[b]+t],
+ *   y[b,n,o] = node_data[n,target_f,starts[b]+T_in+o]; node_data [N,F,T_total] stays resident.
+ * regt_rmsprop_step: run.py:145,194 -- torch.optim.RMSprop (no momentum, not centred) over flat buffers.
+ * regt_eval_metrics: predict.py:142-194 -- sums[b] = { sum|y-out|, sum (y-out)^2, percentile q of y_b (numpy
+ *   'linear'), sum|y-out| / percentile } as doubles; the host combines them (regt_b200/loop.py). */
+int regt_window_gather(const float* node_data, const int64_t* starts, int32_t B, int32_t N, int32_t F, int64_t T_total,
+                       int32_t T_in, int32_t T_out, int32_t target_f, float* x, float* y, regt_stream_t stream);
+int regt_rmsprop_step(float* params, const float* grads, float* square_avg, int64_t n, float lr, float alpha, float eps,
+                      float weight_decay, regt_stream_t stream);
+int regt_eval_metrics(const float* out, const float* y, int32_t B, int64_t n_per_snapshot, double q, double* sums,
+                      regt_stream_t stream);
+
 int regt_version(void);
 const char* regt_last_error(void);
 /* number of kernel launches issued by this library on the calling thread since the last

@@ -52,7 +52,8 @@ EXPORTS = ["regt_version", "regt_last_error", "regt_launch_count", "regt_plan_wo
            "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward",
            "regt_profile", "regt_profile_begin", "regt_profile_read",
            "regt_comm_region_bytes", "regt_comm_data_offset", "regt_comm_alloc", "regt_comm_free", "regt_comm_export",
-           "regt_comm_import", "regt_comm_unimport", "regt_peer_allreduce_f32", "regt_peer_push_max_floats", "regt_comm_error"]
+           "regt_comm_import", "regt_comm_unimport", "regt_peer_allreduce_f32", "regt_peer_push_max_floats", "regt_comm_error",
+           "regt_window_gather", "regt_rmsprop_step", "regt_eval_metrics"]
 
 _lib = None
 
@@ -124,6 +125,12 @@ def load() -> C.CDLL:
     lib.regt_peer_push_max_floats.restype = C.c_int64
     lib.regt_comm_error.restype = C.c_int
     lib.regt_comm_error.argtypes = [vp]
+    lib.regt_window_gather.restype = C.c_int
+    lib.regt_window_gather.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
+    lib.regt_rmsprop_step.restype = C.c_int
+    lib.regt_rmsprop_step.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    lib.regt_eval_metrics.restype = C.c_int
+    lib.regt_eval_metrics.argtypes = [vp, vp, C.c_int32, C.c_int64, C.c_double, vp, vp]
     lib.regt_debug_gemm_nt.restype = C.c_int
     lib.regt_debug_gemm_nt.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp]
     lib.regt_debug_gemm_tn.restype = C.c_int
