@@ -444,30 +444,31 @@ def main():
         dom = max((k for k in per_kernel if k in ab), key=lambda k: per_kernel[k], default=None)
         mb_used = args.micro_batch or getattr(sm.model if sharded else model, "_mb", None) or B
         mb_used = min(B, mb_used)
-        if args.precision == "tf32x3" and "k_gemm_nt_tma" in per_kernel:
+        if args.precision == "tf32x3" and "k_gemm_nt_tma_ts" in per_kernel or "k_gemm_nt_tma" in per_kernel:
             # generic 3xTF32 path: the H x H gate contractions (TMA-fed tcgen05 GEMMs, csrc/gemm_tma.cu) dominate.
             # Algorithmic work of the six NT GEMMs per step (z, r, c forward; dHR, dhg (K = 2H) backward):
             #   flops = 2*rows*H*H * (2 + 1 + 1 + 2);   bytes = rows * 4 * (2H + 2H + 2H + 2H + 3H)   (A read once, C written once)
             # The hardware executes 3 tf32 products per contraction at half the bf16 rate -> fp32-equivalent peak = bf16 / 6.
             # The binding roofline is whichever of the two times is longer (H = 128: HBM; H = 256: tensor pipe).
+            gk = "k_gemm_nt_tma_ts" if "k_gemm_nt_tma_ts" in per_kernel else "k_gemm_nt_tma"   # A through TMEM (default) / shared memory
             nmb = (B + mb_used - 1) // mb_used
             rows_ = float(B) * w.N * w.T
             flops = 2.0 * rows_ * w.H * w.H * 6
             nbytes = rows_ * 4.0 * 11 * w.H
-            t_all = per_kernel["k_gemm_nt_tma"] * 1e-3
+            t_all = per_kernel[gk] * 1e-3
             peak_tc = pk["bf16_tflops"] / 6.0
             t_tc, t_hbm = flops / (peak_tc * 1e12), nbytes / (pk["hbm_gbs"] * 1e9)
             if t_hbm >= t_tc:
                 ach, peak, unit, bound = nbytes / t_all / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
             else:
                 ach, peak, unit, bound = flops / t_all / 1e12, peak_tc, "TFLOP/s", "tensor"
-            roofline = {"kernel": "k_gemm_nt_tma", "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+            roofline = {"kernel": gk, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                         "frac": ach / peak, "traffic": None,
                         "peak_source": pk["source"] + ("" if bound == "hbm" else ": bf16 dense / 6 (tf32 = half the bf16 rate, 3 products per contraction)"),
                         "alg_flops_per_step": flops, "alg_bytes_per_step": nbytes, "t_tensor_ms": t_tc * 1e3, "t_hbm_ms": t_hbm * 1e3,
-                        "launches_per_step": counts["k_gemm_nt_tma"], "micro_batches": nmb,
-                        "launch_ms": per_kernel["k_gemm_nt_tma"] / counts["k_gemm_nt_tma"],
-                        "share_of_step": per_kernel["k_gemm_nt_tma"] / step_sum}
+                        "launches_per_step": counts[gk], "micro_batches": nmb,
+                        "launch_ms": per_kernel[gk] / counts[gk],
+                        "share_of_step": per_kernel[gk] / step_sum}
         elif dom is not None:
             t_launch = per_kernel[dom] / counts[dom] * 1e-3
             ach = ab[dom] / t_launch / 1e9

@@ -329,6 +329,190 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_gemm_nt_tma(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
+// gemm_nt, A operand through TMEM ("TS" MMAs; the default, REGT_NT_TS=0 selects k_gemm_nt_tma).  With the weight operand parked in shared memory
+// (128 KB at N = K = 128) the shared-memory version has room for 3 stages of [A hi | A lo] = 48 KB of TMA loads in
+// flight, and runs at 55 % of the HBM bandwidth.  Here the converters write hi / lo straight into TMEM
+// (tcgen05.st, 4 slots x 64 columns next to the two 128-column accumulators), the MMAs read A from there, and shared
+// memory holds only RAW fp32 chunks: 6 stages x 16 KB in flight (H = 128: 1.11 -> 0.88 ms, 4.5 TB/s = 68 % of the
+// measured HBM peak).  Streamed weights (N or K > 128): a stage is [raw A | B hi | B lo] = 48 KB, four of them.
+// ------------------------------------------------------------------------------------------
+constexpr int TS_SLOTS = 4;      // A (hi | lo) slots in TMEM, 64 columns each, after the two accumulators
+__global__ void __launch_bounds__(NT_THREADS, 1) k_gemm_nt_tma_ts(const __grid_constant__ NtArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_tma[MAXS], bar_rfree[MAXS], bar_afull[TS_SLOTS], bar_afree[TS_SLOTS], bar_b, bar_acc_full[2], bar_acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ns = a.ns;
+  const int nchunks = (a.K + KC - 1) / KC;
+  const int ntn = (a.N + 127) / 128;
+  const long long ntiles = ((a.M + 127) / 128) * ntn;
+  const int stage_bytes = a.resident ? TILE : 3 * TILE;           // raw fp32 A chunk ( | B hi | B lo when the weights stream)
+  uint8_t* bres = sm;
+  uint8_t* stages = sm + (a.resident ? nchunks * 2 * TILE : 0);
+  if (tid == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(&bar_tma[s], 1);
+      mbar_init(&bar_rfree[s], a.resident ? NT_CONV : NT_CONV + 1);   // streamed weights: + the commit of the MMAs that read them
+    }
+    for (int s = 0; s < TS_SLOTS; ++s) {
+      mbar_init(&bar_afull[s], NT_CONV);
+      mbar_init(&bar_afree[s], 1);
+    }
+    mbar_init(&bar_b, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_acc_full[b], 1);
+      mbar_init(&bar_acc_free[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == NT_W_MMA) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem_a = tmem + 256;              // slot s: hi at columns 64 s .. +31, lo at 64 s + 32 .. +63
+
+  if (warp < NT_W_TMA) {
+    // ---- converters: thread = (row of the tile, half of the chunk's 32 k values); the two warps of a TMEM lane quarter
+    //      take one half each.  Raw rows are 128-byte swizzled: the 8 lanes of a quarter-warp read 8 different banks groups.
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t tl = tmem_a + ((uint32_t)(q * 32) << 16) + 16 * half;
+    long long gc = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nchunks; ++kc, ++gc) {
+        const int s = (int)(gc % ns), sl = (int)(gc % TS_SLOTS);
+        mbar_wait(&bar_tma[s], (uint32_t)((gc / ns) & 1));
+        const uint8_t* rw = stages + (size_t)s * stage_bytes + r * 128;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(rw + (((half * 4 + c) ^ (r & 7)) << 4));
+          float4 h, l;
+          split4(v, h, l);
+          hi[4 * c] = __float_as_uint(h.x); hi[4 * c + 1] = __float_as_uint(h.y); hi[4 * c + 2] = __float_as_uint(h.z); hi[4 * c + 3] = __float_as_uint(h.w);
+          lo[4 * c] = __float_as_uint(l.x); lo[4 * c + 1] = __float_as_uint(l.y); lo[4 * c + 2] = __float_as_uint(l.z); lo[4 * c + 3] = __float_as_uint(l.w);
+        }
+        // the raw stage may be refilled once every converter has arrived; an arrive does not wait for this thread's loads
+        // (see k_gemm_tn_tma), so it sits behind a branch on the loaded values
+        if ((hi[0] | hi[4] | hi[8] | hi[12]) == 0x7FC0DEADu) __nanosleep(1);
+        mbar_arrive(&bar_rfree[s]);
+        if (gc >= TS_SLOTS) {
+          mbar_wait(&bar_afree[sl], (uint32_t)((gc / TS_SLOTS - 1) & 1));
+          tc_fence_after();
+        }
+        tmem_st16(tl + 64 * sl, hi);
+        tmem_st16(tl + 64 * sl + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_afull[sl]);
+      }
+    }
+  } else if (warp == NT_W_TMA) {
+    if (lane == 0) {
+      tmap_prefetch(&a.ta);
+      tmap_prefetch(&a.tbh);
+      tmap_prefetch(&a.tbl);
+      if (a.resident) {
+        mbar_arrive_expect_tx(&bar_b, (uint32_t)(nchunks * 2 * TILE));
+        for (int kc = 0; kc < nchunks; ++kc) {
+          tma_2d(bres + (size_t)kc * 2 * TILE, &a.tbh, kc * KC, 0, &bar_b);
+          tma_2d(bres + (size_t)kc * 2 * TILE + TILE, &a.tbl, kc * KC, 0, &bar_b);
+        }
+      }
+      long long gc = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (int)((tile / ntn) * 128), n0 = (int)(tile % ntn) * 128;
+        for (int kc = 0; kc < nchunks; ++kc, ++gc) {
+          const int s = (int)(gc % ns);
+          if (gc >= ns) mbar_wait(&bar_rfree[s], (uint32_t)((gc / ns - 1) & 1));
+          uint8_t* st = stages + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&bar_tma[s], (uint32_t)stage_bytes);
+          tma_2d(st, &a.ta, kc * KC, m0, &bar_tma[s]);
+          if (!a.resident) {
+            tma_2d(st + TILE, &a.tbh, kc * KC, n0, &bar_tma[s]);
+            tma_2d(st + 2 * TILE, &a.tbl, kc * KC, n0, &bar_tma[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == NT_W_MMA) {
+    const uint32_t bres0 = smem_u32(bres), stage0 = smem_u32(stages);
+    if (a.resident) mbar_wait(&bar_b, 0);
+    long long gc = 0, li = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+      const int nt = min(128, a.N - (int)(tile % ntn) * 128);
+      const uint32_t idesc = make_idesc(FMT_TF32, 128, nt, 0, 0);
+      const int buf = (int)(li & 1);
+      if (li >= 2) {
+        mbar_wait(&bar_acc_free[buf], (uint32_t)((li / 2 - 1) & 1));
+        tc_fence_after();
+      }
+      for (int kc = 0; kc < nchunks; ++kc, ++gc) {
+        const int sl = (int)(gc % TS_SLOTS);
+        mbar_wait(&bar_afull[sl], (uint32_t)((gc / TS_SLOTS) & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t ah = tmem_a + 64 * sl, al = ah + 32;
+          const int s = (int)(gc % ns);
+          const uint32_t bt = a.resident ? bres0 + kc * 2 * TILE : stage0 + s * stage_bytes + TILE;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {   // hi*hi, lo*hi, hi*lo
+            const uint32_t ap = (p == 1) ? al : ah, bp = bt + (p == 2 ? TILE : 0);
+#pragma unroll
+            for (int k = 0; k < KC / 8; ++k)
+              umma_ts_tf32(tmem + buf * 128, ap + 8 * k, make_desc(bp + k * 32, 16, 1024, LAYOUT_SW128), idesc,
+                           (kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_afree[sl]);
+          if (!a.resident) umma_commit(&bar_rfree[s]);   // the streamed weight tiles of this stage have been read
+          if (kc + 1 == nchunks) umma_commit(&bar_acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---- epilogue warps: TMEM -> registers -> C (thread = row of the tile) ----
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    long long li = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+      const int buf = (int)(li & 1);
+      const int n0 = (int)(tile % ntn) * 128;
+      const int nt = min(128, a.N - n0);
+      const long long arow = (tile / ntn) * 128 + r;
+      const bool a_ok = arow < a.M;
+      float* cp = a.C + (a_ok ? arow : 0) * a.ldc + n0;
+      mbar_wait(&bar_acc_full[buf], (uint32_t)((li / 2) & 1));
+      tc_fence_after();
+      for (int c0 = 0; c0 < nt; c0 += 32) {
+        float v[32];
+        if (c0 + 32 <= nt) {
+          tmem_ld32(tlane + buf * 128 + c0, v);
+        } else {
+          float u[16];
+          tmem_ld16(tlane + buf * 128 + c0, u);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = u[j];
+        }
+        if (a_ok) {
+          const int w = min(32, nt - c0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (j < w) *reinterpret_cast<float4*>(cp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acc_free[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == NT_W_MMA) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // gemm_tn
 // ------------------------------------------------------------------------------------------
 struct TnSeg {
@@ -628,9 +812,23 @@ int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long
   const int stage = a.resident ? 2 * TILE : 4 * TILE;
   const int fixed = a.resident ? nchunks * 2 * TILE : 0;
   a.ns = min(MAXS, (SMEM_BUDGET - fixed) / stage);
+  const long long ntiles = (long long)cdiv(M, 128) * cdiv(N, 128);
+  static int use_ts = -1;
+  if (use_ts < 0) {
+    const char* e = getenv("REGT_NT_TS");
+    use_ts = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!gate && use_ts) {   // A operand through TMEM: shared memory holds the weights (parked or streamed) + raw fp32 chunks only
+    const int stage_ts = a.resident ? TILE : 3 * TILE;
+    a.ns = min(MAXS, (SMEM_BUDGET - fixed) / stage_ts);
+    const size_t smem_ts = (size_t)fixed + (size_t)a.ns * stage_ts + 1024;
+    REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+    k_gemm_nt_tma_ts<<<(int)min(ntiles, (long long)sm_count()), NT_THREADS, smem_ts, st>>>(a);
+    REGT_LAUNCHED("k_gemm_nt_tma_ts", st);
+    return 0;
+  }
   const size_t smem = (size_t)fixed + (size_t)a.ns * stage + 1024;
   REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long ntiles = (long long)cdiv(M, 128) * cdiv(N, 128);
   k_gemm_nt_tma<<<(int)min(ntiles, (long long)sm_count()), NT_THREADS, smem, st>>>(a);
   REGT_LAUNCHED("k_gemm_nt_tma", st);
   return 0;
