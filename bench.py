@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: the gradient all-reduce as one kernel over NVLink peer memory (csrc/peer.cu) or through NCCL; "
-                         "auto = peer kernel up to 2^18 floats (its push path), NCCL above")
+                         "auto = the peer kernels (NCCL only if CUDA IPC is unavailable)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -4,13 +4,12 @@
 // Every rank owns one cudaMalloc'ed communication region  [ flags | data | scratch ]  that the other ranks of the node map
 // through CUDA IPC.  The weight-gradient kernels write straight into `data` (the .grad tensors are views of it).  The
 // all-reduce kernel then, per thread block b and without any grid-wide or host synchronisation:
-//   1. start barrier of block b across the ranks (one flag word per (phase, block, peer), stored with release.sys into
-//      the peer's region, polled with acquire.sys in the own region): every rank's data is complete;
-//   2. reduce-scatter: reads its part of chunk `rank` from EVERY rank's data over NVLink (volatile 128-bit loads) and sums
-//      in rank order 0..W-1 into the own scratch (each element is summed exactly once, by its owner);
-//   3. second barrier of block b: all sums are in place, every peer has finished reading this rank's data;
-//   4. all-gather: copies its part of every chunk from the owner's scratch over the own data -- every rank ends up with
-//      the same bits.
+//   1. reduce-scatter by PUSH: stores its copy of chunk r into slot `rank` of rank r's scratch (128-bit NVLink writes);
+//   2. barrier of block b across the ranks (one flag word per (phase, block, peer), stored with release.sys into the
+//      peer's region, polled with acquire.sys in the own region): all copies of the own chunk have landed;
+//   3. sums them in rank order 0..W-1 (each element is summed exactly once, by its owner) and pushes the sums into chunk
+//      `rank` of every rank's data -- every rank ends up with the same bits;
+//   4. second barrier: all chunks have landed before the kernel ends.
 // Small buffers (<= PEER_LL_MAX floats) take a push path instead (k_peer_allreduce_ll, NCCL's "LL" idea): every rank
 // STORES its values into a receive slot of every peer as 8-byte (value, epoch) words -- data and flag arrive in one
 // atomic store, one NVLink traversal, no barrier -- and sums what lands in its own slots, again in rank order.  Slots are
@@ -79,11 +78,13 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int phase, uint3
   __syncthreads();
 }
 
-// pull path, two stages: rank r owns chunk r of the buffer.  Stage 1 (reduce-scatter): read chunk `rank` from every peer,
-// sum in rank order, keep the result in the own scratch.  Stage 2 (all-gather): copy every chunk's sum from its owner's
-// scratch into the own data.  Per rank 2 (W-1)/W * n * 4 bytes cross NVLink instead of (W-1) * n * 4 for a one-shot read.
-// Block b of every rank works on the same sub-slices of every chunk, so the two barriers are per block; the start barrier
-// of the NEXT call is what protects the scratch from being overwritten while a slow peer still gathers from it.
+// large buffers, two stages, every NVLink transfer a WRITE (peer reads are request/response bound: the read-based version
+// of this kernel reached 285 GB/s per GPU).  Rank r owns chunk r of the buffer.
+//   stage 1 (reduce-scatter by push): every rank stores its copy of chunk r into slot `rank` of rank r's scratch;
+//   barrier; rank r sums the W copies in rank order (its own straight from data, the others from its scratch: local reads);
+//   stage 2 (all-gather by push): rank r stores the sums into chunk r of EVERY rank's data;
+//   barrier: all chunks have landed here before the kernel ends (and nobody still reads a scratch the next call refills).
+// Block b of every rank works on the same sub-slices of every chunk, so both barriers are per block.
 __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(PeerArgs a) {
   __shared__ uint32_t epoch_s;
   if (threadIdx.x == 0) {
@@ -92,31 +93,43 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(PeerArgs a) {
   }
   __syncthreads();
   const uint32_t epoch = epoch_s;
-  peer_barrier(a, 0, epoch);   // every rank's data is complete (and every rank has left the previous call)
   const long long c4 = (a.n4 + a.world - 1) / a.world;           // float4 elements per chunk
   const long long stride = (long long)gridDim.x * PEER_THREADS;
-  {
-    const long long lo = (long long)a.rank * c4, hi = min(a.n4, lo + c4);
-    float4* scratch = reinterpret_cast<float4*>(a.scratch[a.rank]);
-    for (long long i = lo + blockIdx.x * (long long)PEER_THREADS + threadIdx.x; i < hi; i += stride) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* mine = reinterpret_cast<const float4*>(a.data[a.rank]);
+  // stage 1: my copy of chunk r -> slot `rank` of rank r's scratch (scratch = W slots of c4 elements)
+  for (long long j = blockIdx.x * (long long)PEER_THREADS + threadIdx.x; j < c4; j += stride) {
+    float4 v[PEER_MAXW];
 #pragma unroll
-      for (int r = 0; r < PEER_MAXW; ++r) {
-        if (r < a.world) {
-          const float4 v = ld_volatile4(reinterpret_cast<const float4*>(a.data[r]) + i);
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-      }
-      scratch[i] = s;
+    for (int r = 0; r < PEER_MAXW; ++r) {
+      const long long i = (long long)r * c4 + j;
+      if (r < a.world && r != a.rank && i < a.n4) v[r] = mine[i];
+    }
+#pragma unroll
+    for (int r = 0; r < PEER_MAXW; ++r) {
+      const long long i = (long long)r * c4 + j;
+      if (r < a.world && r != a.rank && i < a.n4) reinterpret_cast<float4*>(a.scratch[r])[(long long)a.rank * c4 + j] = v[r];
     }
   }
-  peer_barrier(a, 1, epoch);   // all sums are in place; every peer has finished reading this rank's data
-  float4* mine = reinterpret_cast<float4*>(a.data[a.rank]);
-  for (int r = 0; r < a.world; ++r) {
-    const long long lo = (long long)r * c4, hi = min(a.n4, lo + c4);
-    const float4* src = reinterpret_cast<const float4*>(a.scratch[r]);
-    for (long long i = lo + blockIdx.x * (long long)PEER_THREADS + threadIdx.x; i < hi; i += stride) mine[i] = ld_volatile4(src + i);
+  peer_barrier(a, 0, epoch);   // every rank's copies of my chunk have landed in my scratch
+  {
+    const long long lo = (long long)a.rank * c4, hi = min(a.n4, lo + c4);
+    const float4* slots = reinterpret_cast<const float4*>(a.scratch[a.rank]);
+    for (long long j = blockIdx.x * (long long)PEER_THREADS + threadIdx.x; lo + j < hi; j += stride) {
+      float4 v[PEER_MAXW];
+#pragma unroll
+      for (int r = 0; r < PEER_MAXW; ++r)
+        if (r < a.world) v[r] = (r == a.rank) ? mine[lo + j] : ld_volatile4(slots + (long long)r * c4 + j);
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < PEER_MAXW; ++r)
+        if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+      // stage 2: the sum goes to chunk `rank` of every rank's data (the own copy last: it was an input above)
+#pragma unroll
+      for (int r = 0; r < PEER_MAXW; ++r)
+        if (r < a.world) reinterpret_cast<float4*>(a.data[r])[lo + j] = s;
+    }
   }
+  peer_barrier(a, 1, epoch);   // every chunk has landed in my data; every rank is done with its scratch
 }
 
 // push path: thread = 2 consecutive floats
