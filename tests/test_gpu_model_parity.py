@@ -135,3 +135,29 @@ def test_batch_additivity_full_size_config2():
     with torch.no_grad():
         out_p, _ = m1(x[perm].contiguous(), *g)
     assert torch.equal(out_p, out1[perm])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32x3", 1e-5)])
+def test_config1_matches_committed_golden(precision, tol):
+    """BASELINE configs[0] (the reference's own CPU-runnable case: TPIMS graph, R=5, H=256) against the COMMITTED oracle
+    vectors (tests/golden/cfg1_oracle_fp64.npz, made by make_cfg1_golden.py): no live oracle in the loop, so a drift of the
+    oracle and of the kernels in the same direction cannot hide."""
+    import os
+    from parity_util import build_oracle
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg1_oracle_fp64.npz"))
+    w = W.make_workload(1)
+    state = build_oracle(w).state_dict()            # the seeded synthetic parameters the golden run used
+    m = build_cuda(w, state, precision=precision)
+    x, y = w.inputs(1)
+    loss, out, hid = m.fused_step(x.cuda(), y.cuda(), *to_dev(w.graph_args(), "cuda"))
+    assert relerr(out, torch.from_numpy(gold["out"])) <= tol
+    assert relerr(hid, torch.from_numpy(gold["hid"])) <= tol
+    assert abs(float(loss) - float(gold["loss"])) <= tol * abs(float(gold["loss"]))
+    for k, p in m.named_parameters():
+        if is_dead(w.model, k) or ("gmax:" + k) not in gold:
+            continue
+        g = p.grad.double().reshape(-1).cpu()
+        gmax = float(gold["gmax:" + k])
+        lim = 1e-4 if (precision == "tf32x3" and k.endswith("_attention")) else tol
+        assert float((g[:32] - torch.from_numpy(gold["ghead:" + k])).abs().max()) <= lim * gmax, k
+        assert float(g.abs().max()) <= (1.0 + 10 * lim) * gmax + 1e-30, k      # and nothing larger than the oracle's largest entry

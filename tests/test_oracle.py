@@ -117,3 +117,23 @@ def test_workload_shapes_match_survey():
     assert abs(W.alg_bytes_per_step(w3) / 4.23e9 - 1) < 0.02
     assert abs(W.fwd_flops_per_step(w2) / 4.98e9 - 1) < 0.02
     assert abs(W.fwd_flops_per_step(w3) / 209e9 - 1) < 0.02
+
+
+def test_oracle_reproduces_committed_config1_golden():
+    """drift guard: the oracle of today gives the vectors committed under tests/golden/ (config 1 = BASELINE configs[0])."""
+    import os
+    import numpy as np
+    from parity_util import W, is_dead, oracle_step
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg1_oracle_fp64.npz"))
+    w = W.make_workload(1)
+    ref = oracle_step(w, 1)
+    assert np.allclose(ref["out"].numpy(), gold["out"], rtol=0, atol=1e-12)
+    assert np.allclose(ref["hid"].numpy(), gold["hid"], rtol=0, atol=1e-12)
+    assert abs(float(ref["loss"]) - float(gold["loss"])) <= 1e-12
+    n = 0
+    for k, g in ref["grads"].items():
+        if g is None or is_dead(w.model, k):
+            continue
+        assert np.allclose(g.double().reshape(-1).numpy()[:32], gold["ghead:" + k], rtol=0, atol=1e-12 * max(1.0, float(gold["gmax:" + k]))), k
+        n += 1
+    assert n >= 20
