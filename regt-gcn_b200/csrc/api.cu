@@ -69,7 +69,7 @@ Layout make_layout(const regt_args* a, void* base) {
   pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * 32);                  // F-wide partials ([4H][F+1] fp32 path, [4H][32] tf32x3 GEMM)
   pf = max(pf, (size_t)3 * H * H + 1024 * 64);                      // tf32x3: packed B^T operands + attention partials
   pf = max(pf, (size_t)WGRAD_SPLITS * (3 * H * H + 4 * H * 32));    // tf32x3: H x H and F-wide weight-gradient partials side by side
-  pf = max(pf, (size_t)max((size_t)2048, R) * H * F);               // per-region partials (z-splits * R <= 2048)
+  pf = max(pf, (size_t)(2048 + R + 2) * H * F);                     // per-region dM1 partials: <= 2048 + R chunks (cell.cu)
   pf = max(pf, (size_t)128 * T);                                    // attention partials
   pf = max(pf, (size_t)128 * (O * HEAD_HID + HEAD_HID * H));        // head split-K partials (<= 128 splits)
   pf = max(pf, (size_t)152 * HEAD_HID * (H + 32));                  // head dW1 on the tensor cores (+ the 32-wide second operand, tf32x3)
@@ -78,6 +78,7 @@ Layout make_layout(const regt_args* a, void* base) {
   L.hpart = c.take<float>((size_t)148 * (HEAD_HID * H + O * HEAD_HID + HEAD_HID + O + 8));
   L.part = c.take<float>(pf);
   L.part_floats = pf;
+  L.m1cp = c.take<int32_t>(R + 2);
   L.total = align_up(c.off, 256);
   return L;
 }

@@ -328,58 +328,126 @@ __global__ void k_skinny_reduce(const float* __restrict__ part, int splits, int 
   }
 }
 
-// dM1[r] = sum over the (node, region r) segments of D_3^T U ; part[zsplit][r][n][F]
-// work items of region r = (segment of r, snapshot b), split evenly over gridDim.z
-__global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ D, const float* __restrict__ U,
-                                                  const int32_t* __restrict__ rseg_ptr,
-                                                  const int32_t* __restrict__ rseg_list,
-                                                  const int32_t* __restrict__ seg_node, int B, int N, int T, int H,
-                                                  int R, int nseg, float* __restrict__ part) {
-  const int r = blockIdx.x;
-  const int n = blockIdx.y * 128 + threadIdx.x;
-  if (n >= H) return;
+// dM1[r] = sum over the (node, region r) segments of dhp^T U          (models/RegionalTemporalGCN.py:136-141 backward)
+// Work items = (segment, snapshot) pairs in region-sorted order (rseg_list).  A region is cut into chunks of at most
+// `per` items; chunk_ptr[r] = number of chunks before region r (k_m1_chunks), so EMPTY regions -- every list a region
+// shard does not own -- cost nothing and the grid follows the work, not R.  A block owns one chunk: its warps stride
+// over the chunk's items, a lane owns four gate columns (one 128-bit load per period, all T periods in flight), the
+// item's U row [F][T] is a warp-uniform broadcast.  part[chunk][H][F]; k_m1_reduce sums a region's chunks in order.
+constexpr int M1_TARGET_CHUNKS = 2048;
+__global__ void k_m1_chunks(const int32_t* __restrict__ rseg_ptr, int R, int B, int per, int32_t* __restrict__ chunk_ptr) {
+  __shared__ int part_sum[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per_thr = (R + nt - 1) / nt;
+  const int r0 = min(R, tid * per_thr), r1 = min(R, r0 + per_thr);
+  int s = 0;
+  for (int r = r0; r < r1; ++r) {
+    const long long items = (long long)(rseg_ptr[r + 1] - rseg_ptr[r]) * B;
+    s += (int)((items + per - 1) / per);
+  }
+  part_sum[tid] = s;
+  __syncthreads();
+  if (tid == 0) {   // exclusive scan of <= 1024 slice sums
+    int run = 0;
+    for (int i = 0; i < nt; ++i) {
+      const int v = part_sum[i];
+      part_sum[i] = run;
+      run += v;
+    }
+    chunk_ptr[R] = run;
+  }
+  __syncthreads();
+  int run = part_sum[tid];
+  for (int r = r0; r < r1; ++r) {
+    chunk_ptr[r] = run;
+    const long long items = (long long)(rseg_ptr[r + 1] - rseg_ptr[r]) * B;
+    run += (int)((items + per - 1) / per);
+  }
+}
+
+template <int TT>   // TT = periods held in flight per pass (T is processed in groups of TT)
+__global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ dhp, long long ldd, const float* __restrict__ U,
+                                                  const int32_t* __restrict__ rseg_ptr, const int32_t* __restrict__ rseg_list,
+                                                  const int32_t* __restrict__ seg_node, const int32_t* __restrict__ chunk_ptr,
+                                                  int B, int N, int T, int H, int R, int nseg, int per,
+                                                  float* __restrict__ part) {
+  __shared__ float red[3][32][4 * F + 1];
+  const int c = blockIdx.x;
+  if (c >= chunk_ptr[R]) return;
+  int lo = 0, hi = R;             // region of this chunk: largest r with chunk_ptr[r] <= c (empty regions share a value)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk_ptr[mid] <= c) lo = mid; else hi = mid;
+  }
+  const int r = lo;
   const int s0 = rseg_ptr[r];
   const long long items = (long long)(rseg_ptr[r + 1] - s0) * B;
-  const long long per = (items + gridDim.z - 1) / gridDim.z;
-  const long long i0 = blockIdx.z * per, i1 = min(items, i0 + per);
-  float acc[F];
+  const long long i0 = (long long)(c - chunk_ptr[r]) * per, i1 = min(items, i0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y * 128 + lane * 4;
+  const bool n_ok = n < H;
+  float acc[4][F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) acc[f] = 0.f;
-  for (long long i = i0; i < i1; ++i) {
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[e][f] = 0.f;
+  for (long long i = i0 + warp; i < i1; i += 4) {
     const int s = rseg_list[s0 + (int)(i / B)];
     const int b = (int)(i % B);
     const int node = seg_node[s];
     const float* ur = U + ((size_t)b * nseg + s) * F * T;
-    const float* dr = D + (((size_t)b * N + node) * T) * 4 * H + 3 * H + n;
-    int t = 0;
-    for (; t + 4 <= T; t += 4) {   // four periods' loads in flight (the chain of fmas is short, the loads are not)
-      float d[4], u[4][F];
+    const float* dr = dhp + (((size_t)b * N + node) * T) * ldd + n;
+    for (int t0 = 0; t0 < T; t0 += TT) {
+      float4 d[TT];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] = __ldg(dr + (size_t)(t + k) * 4 * H);
+      for (int k = 0; k < TT; ++k)
+        d[k] = (n_ok && t0 + k < T) ? __ldg(reinterpret_cast<const float4*>(dr + (size_t)(t0 + k) * ldd)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int f = 0; f < F; ++f) {
-        if (T % 4 == 0) {
-          const float4 u4 = __ldg(reinterpret_cast<const float4*>(ur + f * T + t));
-          u[0][f] = u4.x; u[1][f] = u4.y; u[2][f] = u4.z; u[3][f] = u4.w;
-        } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) u[k][f] = __ldg(ur + f * T + t + k);
+        for (int k = 0; k < TT; ++k) {
+          const float u = (t0 + k < T) ? __ldg(ur + f * T + t0 + k) : 0.f;
+          acc[0][f] = fmaf(d[k].x, u, acc[0][f]);
+          acc[1][f] = fmaf(d[k].y, u, acc[1][f]);
+          acc[2][f] = fmaf(d[k].z, u, acc[2][f]);
+          acc[3][f] = fmaf(d[k].w, u, acc[3][f]);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int f = 0; f < F; ++f) acc[f] = fmaf(d[k], u[k][f], acc[f]);
-    }
-    for (; t < T; ++t) {
-      const float d = __ldg(dr + (size_t)t * 4 * H);
-#pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] = fmaf(d, __ldg(ur + f * T + t), acc[f]);
     }
   }
-  float* o = part + (((size_t)blockIdx.z * R + r) * H + n) * F;
+  // warps 1..3 hand their sums to warp 0 (fixed order -> deterministic)
+  if (warp > 0) {
 #pragma unroll
-  for (int f = 0; f < F; ++f) o[f] = acc[f];
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < F; ++f) red[warp - 1][lane][e * F + f] = acc[e][f];
+  }
+  __syncthreads();
+  if (warp == 0 && n_ok) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[e][f] += red[w][lane][e * F + f];
+    float* o = part + ((size_t)c * H + n) * F;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      *reinterpret_cast<float4*>(o + e * F) = make_float4(acc[e][0], acc[e][1], acc[e][2], acc[e][3]);
+      *reinterpret_cast<float4*>(o + e * F + 4) = make_float4(acc[e][4], acc[e][5], acc[e][6], acc[e][7]);
+    }
+  }
+}
+// dM1[r][n][f] = sum of the region's chunk partials, in chunk order (zero for a region without segments)
+__global__ void __launch_bounds__(256) k_m1_reduce(const float* __restrict__ part, const int32_t* __restrict__ chunk_ptr, int HF,
+                                                   float* __restrict__ dM1) {
+  const int r = blockIdx.x;
+  const int c0 = chunk_ptr[r], c1 = chunk_ptr[r + 1];
+  for (int i = threadIdx.x; i < HF; i += blockDim.x) {
+    float s = 0.f;
+    for (int c = c0; c < c1; ++c) s += part[(size_t)c * HF + i];
+    dM1[(size_t)r * HF + i] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -544,15 +612,29 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
   return 0;
 }
 
-// dM1[r] = sum over the (node, region r) segments of D_3^T U  -- shared with cell_g.cu
-int launch_wgrad_m1(const regt_args* a, const Layout& L, cudaStream_t st) {
+// dM1[r] = sum over the (node, region r) segments of dhp^T U  -- shared with cell_g.cu; dhp = rows of `ldd` floats
+int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, long long ldd, cudaStream_t st) {
   const int H = a->H, T = a->T, R = a->plan.R;
-  float* part = L.part;
-  const int zs = (int)max(1ll, min(256ll, 2048ll / ((long long)R * cdiv(H, 128))));   // zs * R <= 2048 partial blocks
-  k_wgrad_m1<<<dim3(R, cdiv(H, 128), zs), 128, 0, st>>>(L.D, L.U, a->plan.rseg_ptr, a->plan.rseg_list,
-                                                      a->plan.seg_node, a->B, a->N, T, H, R, a->plan.nseg, part);
+  REGT_CHECK(H % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)dhp % 16) == 0, "wgrad_m1: H and the row pitch must be multiples of 4 floats");
+  const long long total = (long long)a->plan.nseg * a->B;
+  const int per = (int)max(8ll, (total + M1_TARGET_CHUNKS - 1) / M1_TARGET_CHUNKS);
+  const int max_chunks = (int)(total / per) + R + 1;
+  REGT_CHECK((size_t)max_chunks * H * F <= L.part_floats, "wgrad_m1: partial buffer too small (%d chunks)", max_chunks);
+  k_m1_chunks<<<1, 1024, 0, st>>>(a->plan.rseg_ptr, R, a->B, per, L.m1cp);
+  REGT_LAUNCHED("k_m1_chunks", st);
+  if (T % 6 == 0)
+    k_wgrad_m1<6><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, ldd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
+                                                                L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
+  else
+    k_wgrad_m1<4><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, ldd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
+                                                                L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
   REGT_LAUNCHED("k_wgrad_m1", st);
-  return launch_reduce_splits(part, L.dM1, (long long)R * H * F, zs, 0, st);
+  k_m1_reduce<<<R, 256, 0, st>>>(L.part, L.m1cp, H * F, L.dM1);
+  REGT_LAUNCHED("k_m1_reduce", st);
+  return 0;
+}
+int launch_wgrad_m1(const regt_args* a, const Layout& L, cudaStream_t st) {
+  return launch_wgrad_m1_from(a, L, L.D + 3 * (size_t)a->H, 4ll * a->H, st);
 }
 
 // F-wide weight gradients (dP_g = D_g^T S, dM0 = D_3^T X, biases = column sums, dM1 per region)

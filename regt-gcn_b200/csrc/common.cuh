@@ -111,6 +111,7 @@ struct Layout {
   float* hpart;  // fused-head per-CTA partials
   float* part;   // split-K partials
   size_t part_floats;
+  int32_t* m1cp; // [R+1] chunk table of the per-region dM1 reduction (cell.cu k_m1_chunks)
   // tensor-core path (precision != FP32): weight images, tile-layout planes, per-CTA partials
   unsigned char* tc_img_f;   // forward weight image
   unsigned char* tc_img_b;   // backward weight image

@@ -175,6 +175,13 @@ def make_workload(cfg: int | str, B: Optional[int] = None) -> Workload:
     return w
 
 
+def cfg5_shaped(N: int = 2560, T: int = 2, B: int = 2, H: int = 128, R: int = 256, O: int = 12) -> Workload:
+    """config 5's generator (same seed, R = 256 regions, H = 128, 6 intra-region out-edges per node, N/10 cross-region
+    edges) at a node count the literal CPU oracle can hold: its [N, R*H] regional concat is N * 256 KiB per period in fp64."""
+    full, rei, rea = _regional_graph(N, R, 6, max(1, N // 10), 105)
+    return Workload(f"cfg5_shaped_N{N}_R{R}_H{H}_T{T}", "RegionalTemporalGCN", B, N, T, H, O, R, 105, full, None, rei, rea)
+
+
 def tiny_workload(model: str, N: int, T: int, H: int, O: int, R: int, B: int, seed: int,
                   k_intra: int = 3, n_cross: int = 4, adversarial: bool = False) -> Workload:
     """small seeded cases for parity tests.  ``adversarial`` adds what SURVEY section 4 asks for:

@@ -68,3 +68,25 @@ def relerr(a: torch.Tensor, ref: torch.Tensor) -> float:
     if den == 0.0:
         return num
     return num / den
+
+
+def attention_limit(w, B, ref, tol=1e-5, seed=1234):
+    """bound for the period-attention gradient: <= tol, or within 4x of the fp32 twin's own error.
+    d_attention is a softmax-Jacobian difference of nearly equal dot products <G, H'_t>; the reference's own fp32
+    arithmetic (restated by the fp32 twin of the oracle) loses the same digits -- 1.6e-5 at config 4."""
+    twin = oracle_step(w, B, dtype=torch.float32, seed=seed)
+    att = [k for k in ref["grads"] if k.endswith("_attention")]
+    if not att:
+        return tol, 0.0
+    e = relerr(twin["grads"][att[0]], ref["grads"][att[0]])
+    return max(tol, 4.0 * e), e
+
+
+def twin_limits(w, B, ref, tol=1e-5, seed=1234):
+    """per-gradient bound of SURVEY 8(c): tol, or 4x the fp32 twin's own error where that is larger.  The twin restates the
+    reference's fp32 arithmetic; where IT deviates from the fp64 master by more than tol (a ReLU / leaky_relu unit whose
+    pre-activation rounds to the other side of zero changes every upstream gradient by a discrete amount -- seen at
+    R = 256, T = 2), no fp32 implementation can be asked for more."""
+    twin = oracle_step(w, B, dtype=torch.float32, seed=seed)
+    errs = {k: relerr(twin["grads"][k], g) for k, g in ref["grads"].items() if g is not None and twin["grads"][k] is not None}
+    return {k: max(tol, 4.0 * e) for k, e in errs.items()}, errs

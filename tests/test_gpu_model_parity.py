@@ -153,11 +153,13 @@ def test_config1_matches_committed_golden(precision, tol):
     assert relerr(out, torch.from_numpy(gold["out"])) <= tol
     assert relerr(hid, torch.from_numpy(gold["hid"])) <= tol
     assert abs(float(loss) - float(gold["loss"])) <= tol * abs(float(gold["loss"]))
+    from parity_util import attention_limit, oracle_step
+    att_lim, _ = attention_limit(w, 1, oracle_step(w, 1), tol)      # 1e-5 or within 4x of the fp32 twin
     for k, p in m.named_parameters():
         if is_dead(w.model, k) or ("gmax:" + k) not in gold:
             continue
         g = p.grad.double().reshape(-1).cpu()
         gmax = float(gold["gmax:" + k])
-        lim = 1e-4 if (precision == "tf32x3" and k.endswith("_attention")) else tol
+        lim = att_lim if k.endswith("_attention") else tol
         assert float((g[:32] - torch.from_numpy(gold["ghead:" + k])).abs().max()) <= lim * gmax, k
         assert float(g.abs().max()) <= (1.0 + 10 * lim) * gmax + 1e-30, k      # and nothing larger than the oracle's largest entry

@@ -16,6 +16,8 @@ def _graphs():
     gs.append(W.make_workload(1))
     gs.append(W.make_workload(2))
     gs.append(W.make_workload(3))
+    gs.append(W.make_workload(4))      # 10 k nodes, 32 regions, 61 k edges
+    gs.append(W.make_workload(5))      # 100 k nodes, 256 regions, 610 k edges (the region-sharded config)
     return gs
 
 

@@ -4,7 +4,7 @@ tf32x3 (generic 3xTF32 GEMM path, any hidden % 32 == 0): fp32-equivalent accurac
 import pytest
 import torch
 
-from parity_util import W, build_cuda, is_dead, oracle_step, relerr, to_dev
+from parity_util import W, attention_limit, build_cuda, is_dead, oracle_step, relerr, to_dev
 
 pytestmark = pytest.mark.gpu
 TOL = {"tf32x3": (1e-5, 1e-5), "bf16": (2e-2, 5e-2)}
@@ -76,12 +76,15 @@ def test_tf32x3_fused_step_matches_oracle(w, B):
     loss, out, hid = m.fused_step(x.cuda(), y.cuda(), *to_dev(w.graph_args(), "cuda"))
     assert relerr(hid, ref["hid"]) <= 1e-5 and relerr(out, ref["out"]) <= 1e-5
     assert abs(float(loss) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    # the attention gradient is a difference of nearly equal dot products <G, H'_t>: SURVEY 8(c)'s rule -- 1e-5, or within
+    # 4x of the error the fp32 twin of the oracle (the reference's own arithmetic) makes on the same inputs
+    att_lim, twin_err = attention_limit(w, B, ref)
     for k, g in ref["grads"].items():
         if not is_dead(w.model, k):
             e = relerr(m.get_parameter(k).grad, g)
-            # the attention gradient is a difference of nearly equal dot products <G, H'_t>: the ~2e-6 error of a
-            # 3xTF32 contraction (tests/test_gpu_gemm.py) is amplified by the cancellation -> stated bound 1e-4
-            assert e <= (1e-4 if k.endswith("_attention") else 1e-5), f"grad {k}: {e:.3e}"
+            if k.endswith("_attention"):
+                print(f"{w.name}: d_attention err {e:.3e}, fp32 twin {twin_err:.3e}, limit {att_lim:.3e}")
+            assert e <= (att_lim if k.endswith("_attention") else 1e-5), f"grad {k}: {e:.3e}"
 
 
 def test_tf32x3_autograd_path_and_unsupported_width():
@@ -91,9 +94,10 @@ def test_tf32x3_autograd_path_and_unsupported_width():
     x, y = w.inputs(3)
     out, hid = m(x.cuda(), *to_dev(w.graph_args(), "cuda"))
     ((out - y.cuda()) ** 2).mean(dim=(1, 2)).sum().backward()
+    att_lim, _ = attention_limit(w, 3, ref)
     for k, g in ref["grads"].items():
         if not is_dead(w.model, k):
-            assert relerr(m.get_parameter(k).grad, g) <= (1e-4 if k.endswith("_attention") else 1e-5), k
+            assert relerr(m.get_parameter(k).grad, g) <= (att_lim if k.endswith("_attention") else 1e-5), k
     w2 = W.tiny_workload("TemporalGCN", N=30, T=3, H=72, O=2, R=0, B=1, seed=3)
     m2 = build_cuda(w2, oracle_step(w2, 1)["state"], precision="tf32x3")
     x2, _ = w2.inputs(1)
