@@ -38,7 +38,7 @@ int launch_gemm_tn_tf32x3(const float* A, long long lda, const float* B, long lo
                           int splits, cudaStream_t st, const float* B2 = nullptr, long long ldb2 = 0, float* Cp2 = nullptr,
                           long long c2_split = 0, int relu_b = 0);
 int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M, int N,
-                       int K, float* scratch, cudaStream_t st, const NtGate* gate = nullptr);
+                       int K, float* scratch, cudaStream_t st);
 int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int nseg, const int* seg_k0, const int* seg_b,
                        float* const* seg_C, const float* const* Bs, const long long* ldbs, int N, int splits, const float* B2,
                        long long ldb2, float* C2, long long c2_split, cudaStream_t st, int relu_b);
@@ -385,22 +385,12 @@ int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   k_g_feat<<<cdiv(k.rows * 8, 256), 256, 0, st>>>(k);
   REGT_LAUNCHED("k_g_feat", st);
   // Pzr = h . [B_z | B_r]^T : the K-major B operand is the reference parameter itself (linear_g.weight[:, H:]).
-  // REGT_FUSE_GATES=1 moves the F-wide term, the sigmoid and h * R into the GEMM's epilogue warps (NtGate; no gate
-  // pre-activation plane, no k_g_zr pass).  Measured on B200 it LOSES: four epilogue warps cannot hide 1152 FMAs + 128
-  // sigmoids per row behind a main loop that is already HBM-bound (config 4: gate GEMMs 1.1 -> 3.9 ms per launch, step
-  // 200 -> 231 ms), and the parked weight operand leaves no shared memory for a fifth K chunk that would let the MMA do
-  // the F-wide term.  Kept (and unit-tested) for a kernel generation with room for it.
-  static const bool fuse_gates = getenv("REGT_FUSE_GATES") && getenv("REGT_FUSE_GATES")[0] == '1';
-  if (fuse_gates && k.rows >= 128 && !getenv("REGT_GEMM_LEGACY")) {
-    NtGate gz{L.Wzr, 2 * H, L.czr, L.Feat, nullptr, 0, nullptr, 0};
-    NtGate gr{L.Wzr + H, 2 * H, L.czr + H, L.Feat, L.h, H, L.hR, H};
-    if (launch_gemm_nt_tma(L.h, H, a->p.lin_w[0] + H, 2 * H, L.Z, H, k.rows, H, H, L.bsplit, st, &gz)) return -1;
-    if (launch_gemm_nt_tma(L.h, H, a->p.lin_w[1] + H, 2 * H, L.Rg, H, k.rows, H, H, L.bsplit, st, &gr)) return -1;
-  } else {
-    for (int g = 0; g < 2; ++g)
-      if (launch_gemm_nt_tma(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, L.bsplit, st)) return -1;
-    G_LAUNCH(k_g_zr, "k_g_zr");
-  }
+  // (A gate epilogue inside this GEMM -- F-wide term as FMAs on the accumulator + sigmoid + h * R in the four epilogue
+  // warps -- was built and measured in round 1: slower, 200 -> 231 ms at config 4.  The fused cell of cell_f.cu is the
+  // route that removes these round trips for H = 128.)
+  for (int g = 0; g < 2; ++g)
+    if (launch_gemm_nt_tma(L.h, H, a->p.lin_w[g] + H, 2 * H, L.D + (size_t)g * H, 4 * H, k.rows, H, H, L.bsplit, st)) return -1;
+  G_LAUNCH(k_g_zr, "k_g_zr");
   if (launch_gemm_nt_tma(L.hR, H, a->p.lin_w[2] + H, 2 * H, L.D + 2 * H, 4 * H, k.rows, H, H, L.bsplit, st)) return -1;
   k_g_c<<<cdiv(BN * (H / 4), 256), 256, 0, st>>>(k);
   REGT_LAUNCHED("k_g_c", st);

@@ -127,17 +127,6 @@ constexpr int TC_IMG_BYTES = 160 * 1024;
 
 Layout make_layout(const regt_args* a, void* base);
 size_t gemm_nt_scratch_floats(int N, int K);
-// fused gate epilogue of gemm_nt (gemm_tma.cu):  g = sigmoid(acc + cb[n] + sum_f feat[row][f] * Ws[f][n]) -> C ;  C2 = aux * g
-struct NtGate {
-  const float* Ws;
-  long long ldw;
-  const float* cb;
-  const float* feat;
-  const float* aux;
-  long long ldaux;
-  float* C2;
-  long long ldc2;
-};
 
 constexpr int HEAD_HID = 128;  // hidden_dim of the decoder MLP (models/RegionalTemporalGCN.py:19)
 constexpr int WGRAD_SPLITS = 64;

@@ -117,17 +117,6 @@ struct NtArgs {
   int N, K;
   int resident;               // Bt hi/lo parked in shared memory for the whole kernel
   int ns;                     // pipeline stages
-  // fused gate epilogue (epi != 0):  g = sigmoid(acc + cb[n] + sum_f feat[row][f] * Ws[f][n])   -> C
-  //                     epi == 2:   additionally C2[row][n] = aux[row][n] * g                     (h * R)
-  int epi;
-  const float* Ws;            // [F][ldw] F-wide part of the gate weights, column n of this GEMM at Ws[f * ldw + n]
-  long long ldw;
-  const float* cb;            // [N]
-  const float* feat;          // [M][32] feature plane, S_t in columns 0..7
-  const float* aux;           // [M][ldaux]
-  long long ldaux;
-  float* C2;
-  long long ldc2;
 };
 constexpr int NT_CONV = 256;                    // converter threads (warps 0-7)
 constexpr int NT_W_TMA = NT_CONV / 32;          // producer warp
@@ -135,203 +124,10 @@ constexpr int NT_W_MMA = NT_W_TMA + 1;          // MMA issuer (owns the TMEM all
 constexpr int NT_W_EPI = NT_W_MMA + 1;          // 4 epilogue warps
 constexpr int NT_THREADS = (NT_W_EPI + 4) * 32;
 
-__global__ void __launch_bounds__(NT_THREADS, 1) k_gemm_nt_tma(const __grid_constant__ NtArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t bar_tma[MAXS], bar_full[MAXS], bar_free[MAXS], bar_b, bar_acc_full[2], bar_acc_free[2];
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ns = a.ns;
-  const int nchunks = (a.K + KC - 1) / KC;
-  const int ntn = (a.N + 127) / 128;
-  const long long ntiles = ((a.M + 127) / 128) * ntn;
-  const int stage_bytes = a.resident ? 2 * TILE : 4 * TILE;      // A hi | A lo ( | B hi | B lo )
-  uint8_t* bres = sm;                                            // resident: [chunk][hi | lo] tiles of Bt
-  uint8_t* stages = sm + (a.resident ? nchunks * 2 * TILE : 0);
-  if (tid == 0) {
-    for (int s = 0; s < ns; ++s) {
-      mbar_init(&bar_tma[s], 1);
-      mbar_init(&bar_full[s], NT_CONV);
-      mbar_init(&bar_free[s], 1);
-    }
-    mbar_init(&bar_b, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_acc_full[b], 1);
-      mbar_init(&bar_acc_free[b], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == NT_W_MMA) tmem_alloc(&tmem_base_s, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-
-  if (warp < NT_W_TMA) {
-    // ---- converters: fp32 chunk -> hi (in place) | lo; linear over the 16 KB tile, the swizzle is position-preserving ----
-    long long gc = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int kc = 0; kc < nchunks; ++kc, ++gc) {
-        const int s = (int)(gc % ns);
-        mbar_wait(&bar_tma[s], (uint32_t)((gc / ns) & 1));
-        float4* hi = reinterpret_cast<float4*>(stages + (size_t)s * stage_bytes);
-        float4* lo = hi + TILE / 16;
-        float4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = hi[tid + NT_CONV * i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 h, l;
-          split4(v[i], h, l);
-          hi[tid + NT_CONV * i] = h;
-          lo[tid + NT_CONV * i] = l;
-        }
-        fence_proxy_async();
-        mbar_arrive(&bar_full[s]);
-      }
-    }
-  } else if (warp == NT_W_TMA) {
-    // ---- producer: one thread keeps the stage ring full ----
-    if (lane == 0) {
-      tmap_prefetch(&a.ta);
-      tmap_prefetch(&a.tbh);
-      tmap_prefetch(&a.tbl);
-      if (a.resident) {
-        mbar_arrive_expect_tx(&bar_b, (uint32_t)(nchunks * 2 * TILE));
-        for (int kc = 0; kc < nchunks; ++kc) {
-          tma_2d(bres + (size_t)kc * 2 * TILE, &a.tbh, kc * KC, 0, &bar_b);
-          tma_2d(bres + (size_t)kc * 2 * TILE + TILE, &a.tbl, kc * KC, 0, &bar_b);
-        }
-      }
-      long long gc = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (int)((tile / ntn) * 128), n0 = (int)(tile % ntn) * 128;
-        for (int kc = 0; kc < nchunks; ++kc, ++gc) {
-          const int s = (int)(gc % ns);
-          if (gc >= ns) mbar_wait(&bar_free[s], (uint32_t)((gc / ns - 1) & 1));
-          uint8_t* st = stages + (size_t)s * stage_bytes;
-          mbar_arrive_expect_tx(&bar_tma[s], (uint32_t)(a.resident ? TILE : 3 * TILE));
-          tma_2d(st, &a.ta, kc * KC, m0, &bar_tma[s]);
-          if (!a.resident) {
-            tma_2d(st + 2 * TILE, &a.tbh, kc * KC, n0, &bar_tma[s]);
-            tma_2d(st + 3 * TILE, &a.tbl, kc * KC, n0, &bar_tma[s]);
-          }
-        }
-      }
-    }
-  } else if (warp == NT_W_MMA) {
-    // ---- MMA issuer: hi*hi + lo*hi + hi*lo per chunk, two TMEM accumulators alternate between tiles ----
-    const uint32_t stage0 = smem_u32(stages), bres0 = smem_u32(bres);
-    if (a.resident) mbar_wait(&bar_b, 0);
-    long long gc = 0, li = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
-      const int nt = min(128, a.N - (int)(tile % ntn) * 128);
-      const uint32_t idesc = make_idesc(FMT_TF32, 128, nt, 0, 0);
-      const int buf = (int)(li & 1);
-      if (li >= 2) {
-        mbar_wait(&bar_acc_free[buf], (uint32_t)((li / 2 - 1) & 1));
-        tc_fence_after();
-      }
-      for (int kc = 0; kc < nchunks; ++kc, ++gc) {
-        const int s = (int)(gc % ns);
-        mbar_wait(&bar_full[s], (uint32_t)((gc / ns) & 1));
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t at = stage0 + s * stage_bytes;
-          const uint32_t bt = a.resident ? bres0 + kc * 2 * TILE : at + 2 * TILE;
-#pragma unroll
-          for (int p = 0; p < 3; ++p) {   // hi*hi, lo*hi, hi*lo
-            const uint32_t ap = at + (p == 1 ? TILE : 0), bp = bt + (p == 2 ? TILE : 0);
-#pragma unroll
-            for (int k = 0; k < KC / 8; ++k)
-              umma<FMT_TF32>(tmem + buf * 128, make_desc(ap + k * 32, 16, 1024, LAYOUT_SW128), make_desc(bp + k * 32, 16, 1024, LAYOUT_SW128),
-                             idesc, (kc > 0 || p > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&bar_free[s]);
-          if (kc + 1 == nchunks) umma_commit(&bar_acc_full[buf]);
-        }
-        __syncwarp();
-      }
-    }
-    tc_fence_before();
-  } else {
-    // ---- epilogue warps: TMEM -> registers -> C (thread = row of the tile) ----
-    const int r = (warp & 3) * 32 + lane;     // a warp may only touch TMEM lanes 32*(warp%4) ..
-    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    long long li = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
-      const long long m0 = (tile / ntn) * 128;
-      const int n0 = (int)(tile % ntn) * 128;
-      const int nt = min(128, a.N - n0);
-      const int buf = (int)(li & 1);
-      const long long arow = m0 + r;
-      const bool a_ok = arow < a.M;
-      float* cp = a.C + (a_ok ? arow : 0) * a.ldc + n0;
-      float sf[REGT_F];
-      if (a.epi && a_ok) {   // this row's S_t (the F-wide input of the gate), read while the accumulator is still filling
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.feat + arow * 32));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.feat + arow * 32) + 1);
-        sf[0] = s0.x; sf[1] = s0.y; sf[2] = s0.z; sf[3] = s0.w; sf[4] = s1.x; sf[5] = s1.y; sf[6] = s1.z; sf[7] = s1.w;
-      }
-      mbar_wait(&bar_acc_full[buf], (uint32_t)((li / 2) & 1));
-      tc_fence_after();
-      for (int c0 = 0; c0 < nt; c0 += 32) {
-        float v[32];
-        if (c0 + 32 <= nt) {
-          tmem_ld32(tlane + buf * 128 + c0, v);
-        } else {   // nt is a multiple of 16: a final half group
-          float u[16];
-          tmem_ld16(tlane + buf * 128 + c0, u);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = u[j];
-        }
-        if (a_ok) {
-          const int w = min(32, nt - c0);
-          if (a.epi) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < w) {   // warp-uniform weight loads (every lane reads the same columns): one broadcast each
-                const int col = n0 + c0 + j;
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.cb + col));
-                float x[4] = {v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w};
-#pragma unroll
-                for (int f = 0; f < REGT_F; ++f) {
-                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.Ws + f * a.ldw + col));
-                  x[0] = fmaf(sf[f], w4.x, x[0]); x[1] = fmaf(sf[f], w4.y, x[1]);
-                  x[2] = fmaf(sf[f], w4.z, x[2]); x[3] = fmaf(sf[f], w4.w, x[3]);
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[j + e] = 1.0f / (1.0f + expf(-x[e]));
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (j < w) *reinterpret_cast<float4*>(cp + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (a.epi == 2) {
-            const float* ax = a.aux + arow * a.ldaux + n0 + c0;
-            float* c2 = a.C2 + arow * a.ldc2 + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < w) {
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(ax + j));
-                *reinterpret_cast<float4*>(c2 + j) = make_float4(h4.x * v[j], h4.y * v[j + 1], h4.z * v[j + 2], h4.w * v[j + 3]);
-              }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&bar_acc_free[buf]);
-    }
-  }
-  __syncthreads();
-  if (warp == NT_W_MMA) tmem_dealloc(tmem, 256);
-}
-
 // ------------------------------------------------------------------------------------------
-// gemm_nt, A operand through TMEM ("TS" MMAs; the default, REGT_NT_TS=0 selects k_gemm_nt_tma).  With the weight operand parked in shared memory
-// (128 KB at N = K = 128) the shared-memory version has room for 3 stages of [A hi | A lo] = 48 KB of TMA loads in
-// flight, and runs at 55 % of the HBM bandwidth.  Here the converters write hi / lo straight into TMEM
+// gemm_nt, A operand through TMEM ("TS" MMAs).  With the weight operand parked in shared memory (128 KB at N = K = 128) a
+// version that kept [A hi | A lo] in shared memory had room for 3 stages = 48 KB of TMA loads in flight and ran at 55 % of
+// the HBM bandwidth (measured in round 1, since removed).  Here the converters write hi / lo straight into TMEM
 // (tcgen05.st, 4 slots x 64 columns next to the two 128-column accumulators), the MMAs read A from there, and shared
 // memory holds only RAW fp32 chunks: 6 stages x 16 KB in flight (H = 128: 1.11 -> 0.88 ms, 4.5 TB/s = 68 % of the
 // measured HBM peak).  Streamed weights (N or K > 128): a stage is [raw A | B hi | B lo] = 48 KB, four of them.
@@ -784,8 +580,7 @@ size_t gemm_nt_scratch_floats(int N, int K) { return (size_t)2 * ((N + 127) / 12
 // C[M][N] = A[M][K] . Bt[N][K]^T ; `scratch` (gemm_nt_scratch_floats(N, K) floats) receives the hi / lo images of Bt.
 // Falls back to the register-fed kernel when the TMA preconditions do not hold.
 int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long ldb, float* C, long long ldc, long long M, int N,
-                       int K, float* scratch, cudaStream_t st, const NtGate* gate) {
-  REGT_CHECK(!gate || (!legacy_forced() && scratch && M >= 128 && N % 16 == 0 && K % 4 == 0), "gemm_nt_tma: the fused gate epilogue needs the TMA path");
+                       int K, float* scratch, cudaStream_t st) {
   if (legacy_forced() || !scratch || M < 128 || N % 16 != 0 || K % 4 != 0 || lda % 4 != 0 || ((uintptr_t)A % 16) != 0 ||
       ((uintptr_t)scratch % 16) != 0)
     return launch_gemm_nt_tf32x3(A, lda, Bt, ldb, C, ldc, M, N, K, st);
@@ -800,37 +595,16 @@ int launch_gemm_nt_tma(const float* A, long long lda, const float* Bt, long long
   if (tmap_2d(&a.tbh, hi, Kp, Np, Kp, 128, "gemm_nt_tma(B hi)")) return -1;
   if (tmap_2d(&a.tbl, lo, Kp, Np, Kp, 128, "gemm_nt_tma(B lo)")) return -1;
   a.C = C; a.M = M; a.ldc = ldc; a.N = N; a.K = K;
-  if (gate) {
-    REGT_CHECK(gate->Ws && gate->cb && gate->feat && gate->ldw % 4 == 0 && ((uintptr_t)gate->Ws % 16) == 0 && ((uintptr_t)gate->cb % 16) == 0 &&
-                   (!gate->C2 || (gate->aux && gate->ldaux % 4 == 0 && gate->ldc2 % 4 == 0)),
-               "gemm_nt_tma: bad gate epilogue operands");
-    a.epi = gate->C2 ? 2 : 1;
-    a.Ws = gate->Ws; a.ldw = gate->ldw; a.cb = gate->cb; a.feat = gate->feat;
-    a.aux = gate->aux; a.ldaux = gate->ldaux; a.C2 = gate->C2; a.ldc2 = gate->ldc2;
-  }
+  // shared memory holds the weights (parked when N, K <= 128, else streamed next to A) + raw fp32 A chunks only
   a.resident = (N <= 128 && nchunks * 2 * TILE + 2 * 2 * TILE <= SMEM_BUDGET) ? 1 : 0;
-  const int stage = a.resident ? 2 * TILE : 4 * TILE;
   const int fixed = a.resident ? nchunks * 2 * TILE : 0;
-  a.ns = min(MAXS, (SMEM_BUDGET - fixed) / stage);
+  const int stage_ts = a.resident ? TILE : 3 * TILE;
+  a.ns = min(MAXS, (SMEM_BUDGET - fixed) / stage_ts);
   const long long ntiles = (long long)cdiv(M, 128) * cdiv(N, 128);
-  static int use_ts = -1;
-  if (use_ts < 0) {
-    const char* e = getenv("REGT_NT_TS");
-    use_ts = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!gate && use_ts) {   // A operand through TMEM: shared memory holds the weights (parked or streamed) + raw fp32 chunks only
-    const int stage_ts = a.resident ? TILE : 3 * TILE;
-    a.ns = min(MAXS, (SMEM_BUDGET - fixed) / stage_ts);
-    const size_t smem_ts = (size_t)fixed + (size_t)a.ns * stage_ts + 1024;
-    REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
-    k_gemm_nt_tma_ts<<<(int)min(ntiles, (long long)sm_count()), NT_THREADS, smem_ts, st>>>(a);
-    REGT_LAUNCHED("k_gemm_nt_tma_ts", st);
-    return 0;
-  }
-  const size_t smem = (size_t)fixed + (size_t)a.ns * stage + 1024;
-  REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_gemm_nt_tma<<<(int)min(ntiles, (long long)sm_count()), NT_THREADS, smem, st>>>(a);
-  REGT_LAUNCHED("k_gemm_nt_tma", st);
+  const size_t smem_ts = (size_t)fixed + (size_t)a.ns * stage_ts + 1024;
+  REGT_CUDA(cudaFuncSetAttribute(k_gemm_nt_tma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+  k_gemm_nt_tma_ts<<<(int)min(ntiles, (long long)sm_count()), NT_THREADS, smem_ts, st>>>(a);
+  REGT_LAUNCHED("k_gemm_nt_tma_ts", st);
   return 0;
 }
 
@@ -896,14 +670,7 @@ int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long
 // debug entry points (not part of the reference-facing ABI): tests/test_gpu_gemm.py
 extern "C" int regt_debug_gemm_nt_tma(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
                                       int32_t N, int32_t K, float* scratch, regt_stream_t stream) {
-  return regt::launch_gemm_nt_tma(A, lda, Bt, ldb, C, ldc, M, N, K, scratch, (cudaStream_t)stream, nullptr);
-}
-// gate epilogue: C = sigmoid(A Bt^T + feat[:, 0:8] Ws + cb) ; C2 = aux * C (optional)
-extern "C" int regt_debug_gemm_nt_gate(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
-                                       int32_t N, int32_t K, float* scratch, const float* Ws, int64_t ldw, const float* cb,
-                                       const float* feat, const float* aux, int64_t ldaux, float* C2, int64_t ldc2, regt_stream_t stream) {
-  regt::NtGate g{Ws, ldw, cb, feat, aux, ldaux, C2, ldc2};
-  return regt::launch_gemm_nt_tma(A, lda, Bt, ldb, C, ldc, M, N, K, scratch, (cudaStream_t)stream, &g);
+  return regt::launch_gemm_nt_tma(A, lda, Bt, ldb, C, ldc, M, N, K, scratch, (cudaStream_t)stream);
 }
 extern "C" int regt_debug_gemm_tn_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* Cp, int64_t M, int32_t K,
                                       int32_t N, int32_t splits, const float* B2, int64_t ldb2, float* Cp2, regt_stream_t stream) {

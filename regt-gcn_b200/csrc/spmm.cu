@@ -56,27 +56,6 @@ __global__ void __launch_bounds__(256) k_spmm_rows(const int32_t* __restrict__ r
   }
 }
 
-// NB neighbour rows of one batch: lane metadata (column, weight) is broadcast by shuffle; slots past
-// the end of the row re-read the row's last neighbour with weight 0 (acc + 0*v leaves acc unchanged),
-// so the loads are unconditional and issue back to back.  Sums stay in sequential CSR order.
-template <int NB>
-__device__ __forceinline__ void gather_batch(const float4* __restrict__ xb, int W4, int c, int mycol, float myval, int j,
-                                             float4& acc) {
-  float4 v[NB];
-  float wv[NB];
-#pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    const int cu = __shfl_sync(0xffffffffu, mycol, (j + u) & 31);
-    wv[u] = __shfl_sync(0xffffffffu, myval, (j + u) & 31);
-    v[u] = __ldg(xb + (size_t)cu * W4 + c);
-  }
-#pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    acc.x = fmaf(wv[u], v[u].x, acc.x); acc.y = fmaf(wv[u], v[u].y, acc.y);
-    acc.z = fmaf(wv[u], v[u].z, acc.z); acc.w = fmaf(wv[u], v[u].w, acc.w);
-  }
-}
-
 // Feature builder of the tensor-core path: the results are written period-major so that one (tile, period) of the
 // cell kernels reads contiguous 32-byte rows:
 //   Xt[t][q][F] = x[q][:, t]      St[t][q][F] = (A_hat x)[q][:, t]      Ut[t][b*nseg+s][F] = (L_hat_r x) per segment

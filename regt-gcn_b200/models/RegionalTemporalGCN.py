@@ -41,7 +41,7 @@ class RegionalTemporalGCN(RegTModelBase):
     _mode = _lib.MODE_REGIONAL
 
     def __init__(self, node_features, num_nodes, periods, output_dim, hidden: int = 256, n_regions: int = 5,
-                 precision: str = "fp32"):
+                 precision: str = "auto"):
         super().__init__()
         self.tgnn = RegionalA3TGCN(in_channels=node_features, out_channels=hidden, num_nodes=num_nodes,
                                    periods=periods, n_regions=n_regions)

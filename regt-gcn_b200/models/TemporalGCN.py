@@ -29,7 +29,7 @@ class A3TGCN(nn.Module):
 class TemporalGCN(RegTModelBase):
     _mode = _lib.MODE_A3TGCN
 
-    def __init__(self, node_features, periods, output_dim, hidden: int = 256, precision: str = "fp32"):
+    def __init__(self, node_features, periods, output_dim, hidden: int = 256, precision: str = "auto"):
         super().__init__()
         self.tgnn = A3TGCN(in_channels=node_features, out_channels=hidden, periods=periods)
         self.output_dim = output_dim

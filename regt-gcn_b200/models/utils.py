@@ -41,6 +41,6 @@ class TGCN(nn.Module):
         h_ext = None
         if H is not None:  # H=None -> zeros (models/utils.py:163-166)
             h_ext = H.to(torch.float32).contiguous().view(1, N, 1, self.out_channels)
-        out = engine.model_apply(_lib.MODE_TGCN, _lib.PRECISIONS[self.precision], plan, self.out_channels, 1, x4,
+        out = engine.model_apply(_lib.MODE_TGCN, _lib.PRECISIONS["fp32" if self.precision == "auto" else self.precision], plan, self.out_channels, 1, x4,
                                  tgcn_param_dict(self), h_ext, head=False)
         return out[0]

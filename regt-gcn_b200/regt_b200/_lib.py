@@ -140,9 +140,6 @@ def load() -> C.CDLL:
                                         vp, C.c_int64, vp, vp]
     lib.regt_debug_gemm_nt_tma.restype = C.c_int
     lib.regt_debug_gemm_nt_tma.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp, vp]
-    lib.regt_debug_gemm_nt_gate.restype = C.c_int
-    lib.regt_debug_gemm_nt_gate.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, vp,
-                                            vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp]
     lib.regt_debug_gemm_tn_tma.restype = C.c_int
     lib.regt_debug_gemm_tn_tma.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                            vp, C.c_int64, vp, vp]

@@ -154,10 +154,11 @@ def auto_micro_batch(mode: int, precision: int, plan: GraphPlanTensors, B: int, 
 
 def run_forward(st: StepState, head: bool = True) -> None:
     lib = _lib.load()
-    st.args.stream = _stream()
-    _lib.check(lib.regt_cell_forward(C.byref(st.args)), "regt_cell_forward")
-    if head:
-        _lib.check(lib.regt_head_forward(C.byref(st.args)), "regt_head_forward")
+    with torch.cuda.device(st.out_hidden.device):     # the model may live on a device that is not the current one
+        st.args.stream = _stream()
+        _lib.check(lib.regt_cell_forward(C.byref(st.args)), "regt_cell_forward")
+        if head:
+            _lib.check(lib.regt_head_forward(C.byref(st.args)), "regt_head_forward")
 
 
 def run_backward(st: StepState, grads: Dict[str, Optional[torch.Tensor]], d_out: Optional[torch.Tensor],
@@ -165,16 +166,17 @@ def run_backward(st: StepState, grads: Dict[str, Optional[torch.Tensor]], d_out:
                  d_h_ext: Optional[torch.Tensor] = None) -> None:
     lib = _lib.load()
     a = st.args
-    a.stream = _stream()
     a.accumulate = 1 if accumulate else 0
     _fill_params(a.g, grads)
     a.d_out = None if d_out is None else d_out.data_ptr()
     a.d_hidden = None if d_hidden is None else d_hidden.data_ptr()
     a.d_h_ext = None if d_h_ext is None else d_h_ext.data_ptr()
     st.keep += [grads, d_out, d_hidden, d_h_ext]
-    # the head backward also seeds the cell gradient (G = d out_hidden) inside the workspace
-    _lib.check(lib.regt_head_backward(C.byref(a)), "regt_head_backward")
-    _lib.check(lib.regt_cell_backward(C.byref(a)), "regt_cell_backward")
+    with torch.cuda.device(st.out_hidden.device):
+        a.stream = _stream()
+        # the head backward also seeds the cell gradient (G = d out_hidden) inside the workspace
+        _lib.check(lib.regt_head_backward(C.byref(a)), "regt_head_backward")
+        _lib.check(lib.regt_cell_backward(C.byref(a)), "regt_cell_backward")
 
 
 class _ModelFn(torch.autograd.Function):

@@ -47,40 +47,92 @@ class SlidingWindows:
         B = starts.numel()
         x = torch.empty(B, self.N, self.F, self.t_in, device=self.data.device)
         y = torch.empty(B, self.N, self.t_out, device=self.data.device)
-        _lib.check(lib.regt_window_gather(self.data.data_ptr(), starts.data_ptr(), B, self.N, self.F, self.T_total, self.t_in,
-                                          self.t_out, self.target, x.data_ptr(), y.data_ptr(), _stream()), "regt_window_gather")
+        with torch.cuda.device(self.data.device):
+            _lib.check(lib.regt_window_gather(self.data.data_ptr(), starts.data_ptr(), B, self.N, self.F, self.T_total, self.t_in,
+                                              self.t_out, self.target, x.data_ptr(), y.data_ptr(), _stream()), "regt_window_gather")
         return x, y
 
 
 class FlatRMSprop:
     """``torch.optim.RMSprop(params, lr, alpha=0.99, eps=1e-8, weight_decay)`` (run.py:145) over ONE flat buffer: parameters and
-    gradients become views of two flat fp32 tensors, the step is a single kernel launch."""
+    gradients become views of two flat fp32 tensors, the step is a single kernel launch.
+
+    ``skip``: parameters that never receive a gradient (the reference's dead ``_weight_att*`` / ``_bias_att*`` / A3TGCN
+    ``linear``; ``model.dead_parameters()``).  ``torch.optim.RMSprop`` leaves a parameter whose ``.grad`` is None untouched --
+    weight decay included -- so these are laid out BEHIND the stepped range and never move.
+    ``exchange``: a ``shard.GradExchange`` whose flat buffer already backs every ``.grad`` (multi-GPU): the optimizer then
+    steps out of that buffer instead of rebinding ``.grad`` to a buffer of its own (which would detach the all-reduce)."""
 
     def __init__(self, params: Sequence[torch.nn.Parameter], lr: float = 1e-3, alpha: float = 0.99, eps: float = 1e-8,
-                 weight_decay: float = 0.0):
-        self.params = [p for p in params if p.requires_grad]
+                 weight_decay: float = 0.0, skip: Sequence[torch.nn.Parameter] = (), exchange=None):
+        skip_ids = {id(p) for p in skip}
+        params = [p for p in params if p.requires_grad]
+        self.exchange = exchange
+        if exchange is not None:
+            if [id(p) for p in exchange.params] != [id(p) for p in params]:
+                raise ValueError("regt_b200: FlatRMSprop(exchange=...) needs the exchange's parameter list, in its order")
+            self.params = params           # layout dictated by the exchange buffer; skipped ranges are masked by segments
+        else:
+            self.params = [p for p in params if id(p) not in skip_ids] + [p for p in params if id(p) in skip_ids]
         self.lr, self.alpha, self.eps, self.wd = lr, alpha, eps, weight_decay
         dev = self.params[0].device
         offs, tot = [], 0
         for p in self.params:
             offs.append(tot)
             tot += (p.numel() + 3) // 4 * 4
+        self._offs = offs
         self.flat_p = torch.zeros(tot, device=dev)
-        self.flat_g = torch.zeros(tot, device=dev)
         self.square_avg = torch.zeros(tot, device=dev)
+        if exchange is not None:
+            self.flat_g = exchange.flat[:tot]
+        else:
+            self.flat_g = torch.zeros(tot, device=dev)
+        # contiguous runs [lo, hi) of stepped (live) elements
+        self.segments = []
+        for p, o in zip(self.params, offs):
+            if id(p) in skip_ids:
+                continue
+            hi = o + (p.numel() + 3) // 4 * 4
+            if self.segments and self.segments[-1][1] == o:
+                self.segments[-1][1] = hi
+            else:
+                self.segments.append([o, hi])
         with torch.no_grad():
             for p, o in zip(self.params, offs):
                 self.flat_p[o:o + p.numel()].copy_(p.reshape(-1))
                 p.data = self.flat_p[o:o + p.numel()].view_as(p)
-                p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+                if exchange is None:
+                    p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+                    p._regt_grad_owner = self
+
+    def attach(self, p: torch.nn.Parameter) -> None:
+        """re-bind a ``.grad`` dropped by ``zero_grad(set_to_none=True)`` to its (zeroed) slice of the flat buffer."""
+        for q, o in zip(self.params, self._offs):
+            if q is p:
+                view = self.flat_g[o:o + p.numel()].view_as(p)
+                view.zero_()
+                p.grad = view
+                return
+        raise RuntimeError("regt_b200: parameter is not owned by this optimizer")
 
     def zero_grad(self) -> None:
-        self.flat_g.zero_()
+        if self.exchange is not None:
+            self.exchange.zero()
+        else:
+            self.flat_g.zero_()
 
     def step(self) -> None:
         lib = _lib.load()
-        _lib.check(lib.regt_rmsprop_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.square_avg.data_ptr(), self.flat_p.numel(),
-                                         self.lr, self.alpha, self.eps, self.wd, _stream()), "regt_rmsprop_step")
+        lo_g, hi_g = self.flat_g.data_ptr(), self.flat_g.data_ptr() + self.flat_g.numel() * 4
+        for p in self.params:
+            if p.grad is not None and not (lo_g <= p.grad.data_ptr() < hi_g):
+                raise RuntimeError("regt_b200: a parameter's .grad is no longer a view of the optimizer's flat gradient buffer "
+                                   "(something rebound it): the step would use stale gradients")
+        with torch.cuda.device(self.flat_p.device):
+            for lo, hi in self.segments:
+                _lib.check(lib.regt_rmsprop_step(self.flat_p.data_ptr() + 4 * lo, self.flat_g.data_ptr() + 4 * lo,
+                                                 self.square_avg.data_ptr() + 4 * lo, hi - lo,
+                                                 self.lr, self.alpha, self.eps, self.wd, _stream()), "regt_rmsprop_step")
 
 
 def train_epoch(model, windows: SlidingWindows, graph_args: Sequence, optimizer, first: int = 0, last: Optional[int] = None,
@@ -122,8 +174,9 @@ def evaluate(model, windows: SlidingWindows, graph_args: Sequence, first: int = 
         out = model(x, *graph_args)[0].contiguous()
         n = out[0].numel()
         part = torch.empty(s1 - s0, 4, device=dev, dtype=torch.float64)
-        _lib.check(lib.regt_eval_metrics(out.data_ptr(), y.contiguous().data_ptr(), s1 - s0, n, q, part.data_ptr(), _stream()),
-                   "regt_eval_metrics")
+        with torch.cuda.device(dev):
+            _lib.check(lib.regt_eval_metrics(out.data_ptr(), y.contiguous().data_ptr(), s1 - s0, n, q, part.data_ptr(), _stream()),
+                       "regt_eval_metrics")
         sums.append(part)
     return reduce_metrics(torch.cat(sums).cpu(), n)
 

@@ -65,10 +65,29 @@ class RegTModelBase(nn.Module):
         raise NotImplementedError
 
     def _prec(self) -> int:
+        """``precision="auto"`` (the default): fp32-equivalent arithmetic on the fastest path that offers it -- the 3xTF32
+        tensor-core kernels when the hidden width allows (hidden % 32 == 0; the reference's 256 does), else the FFMA kernels.
+        Both meet the same 1e-5 parity bound; ``bf16`` (stated tolerance) is opt-in only."""
+        prec = self.precision
+        if prec == "auto":
+            prec = "tf32x3" if (self._hidden % 32 == 0 and self._mode != _lib.MODE_TGCN) else "fp32"
         try:
-            return _lib.PRECISIONS[self.precision]
+            return _lib.PRECISIONS[prec]
         except KeyError:
-            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}")
+            raise ValueError(f"precision must be 'auto' or one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}")
+
+    def dead_parameters(self):
+        """parameters the reference never trains (``attention()`` is never called, models/RegionalTemporalGCN.py:91-111;
+        ``A3TGCN.linear``, models/TemporalGCN.py:70): they exist for checkpoint compatibility and get no gradient, so an
+        optimizer must leave them alone (``FlatRMSprop(skip=model.dead_parameters())``)."""
+        dead = []
+        for name, p in self.named_parameters():
+            leaf = name.split(".")[-1]
+            if leaf in ("_weight_att1", "_weight_att2", "_bias_att1", "_bias_att2"):
+                dead.append(p)
+            elif self._mode == _lib.MODE_A3TGCN and name.startswith("tgnn.linear."):
+                dead.append(p)
+        return dead
 
     @staticmethod
     def _as_batched(x: torch.Tensor):
@@ -101,7 +120,11 @@ class RegTModelBase(nn.Module):
         grads = {}
         for k, p in params.items():
             if p.grad is None:
-                p.grad = torch.zeros_like(p)
+                owner = getattr(p, "_regt_grad_owner", None)   # a GradExchange / FlatRMSprop owns the flat buffer behind .grad
+                if owner is not None:
+                    owner.attach(p)
+                else:
+                    p.grad = torch.zeros_like(p)
             grads[k] = p.grad
         B = xb.shape[0]
         if micro_batch:

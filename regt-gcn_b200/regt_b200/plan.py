@@ -104,12 +104,37 @@ def build_cheb(plan: GraphPlanTensors, edge_lists: Sequence[torch.Tensor],
                   rseg_list=t["rseg_list"][:max(nseg, 1)], region_of=t["region_of"])
 
 
-# ---- cache keyed on the identity of the graph tensors (the graph is static across snapshots) ----
+# ---- plan cache (the graph is static across snapshots) ----
+# Level 1: identity of the graph tensors (no device work, no sync) -- loops that pass the same tensors every step.
+# Level 2: CONTENT of the graph tensors.  The reference's loop does ``batch.to(device)`` per snapshot (run.py:172), which
+# makes a NEW edge_index tensor every time: identity never hits there.  On an identity miss the lists are hashed on the
+# device (two position-weighted int64 sums per tensor, one small D2H read) and the plan is looked up by that; K1 itself
+# runs once per distinct graph.
 _CACHE: dict = {}
+_CONTENT: dict = {}
 
 
 def _key(t: Optional[torch.Tensor]):
     return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+
+
+def _content_key(tensors) -> tuple:
+    parts, shapes = [], []
+    for t in tensors:
+        if t is None:
+            shapes.append(None)
+            continue
+        shapes.append((tuple(t.shape), str(t.dtype)))
+        if t.numel():
+            v = t.reshape(-1)
+            parts.append(v.view(torch.int32).to(torch.int64) if v.dtype == torch.float32 else v.to(torch.int64))
+    if not parts:
+        return (tuple(shapes), ())
+    bits = torch.cat(parts)          # shapes are part of the key, so the concatenation is unambiguous
+    w = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64)
+    # two position-weighted wrap-around int64 sums = a 128-bit fingerprint, one small D2H read
+    fp = torch.stack([(bits * w).sum(), ((bits + w * 2654435761) * (bits ^ (w << 17))).sum()])
+    return (tuple(shapes), tuple(fp.cpu().tolist()))
 
 
 def get_plan(N: int, device: torch.device, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor],
@@ -123,14 +148,26 @@ def get_plan(N: int, device: torch.device, edge_index: torch.Tensor, edge_weight
     hit = _CACHE.get(key)
     if hit is not None:
         return hit[0]
+    ckey = None
+    if not torch.cuda.is_current_stream_capturing():
+        with torch.cuda.device(device):
+            ckey = (N, str(device), need_cheb,
+                    _content_key([edge_index, edge_weight, *reg_edge_index, *reg_edge_weight]))
+        plan = _CONTENT.get(ckey)
+        if plan is not None:
+            return plan
     plan = GraphPlanTensors(device, N)
     build_gcn(plan, edge_index, edge_weight)
     if need_cheb:
         build_cheb(plan, reg_edge_index, reg_edge_weight)
     if len(_CACHE) > 64:
         _CACHE.clear()
+    if len(_CONTENT) > 16:
+        _CONTENT.clear()
     # keep the key tensors alive so data_ptr() cannot be recycled while the entry lives
     _CACHE[key] = (plan, edge_index, edge_weight, list(reg_edge_index), list(reg_edge_weight))
+    if ckey is not None:
+        _CONTENT[ckey] = plan
     return plan
 
 

@@ -285,7 +285,22 @@ class PeerRegion:
         return self.n <= int(self.lib.regt_peer_push_max_floats()) and os.environ.get("REGT_PEER_PULL", "0") != "1"
 
     def error(self) -> int:
+        """non-zero once a kernel of this region gave up waiting for a peer (a rank stalled past the spin limit): the sums
+        of that call are not trustworthy.  Reading the flag synchronises with the device."""
         return int(self.lib.regt_comm_error(self.base))
+
+    def close(self) -> None:
+        """unmap the peers' regions and free this rank's (call after the last all-reduce has completed on every rank)."""
+        if getattr(self, "base", None) is None:
+            return
+        try:
+            torch.cuda.synchronize()
+            for ptr in self.peers:
+                self.lib.regt_comm_unimport(ptr)
+            self.lib.regt_comm_free(self.base)
+        finally:
+            self.peers, self.base, self.data = [], None, None
+
 
 
 class GradExchange:
@@ -323,12 +338,50 @@ class GradExchange:
                 self.region = None
         self.transport = "peer" if self.region is not None else ("nccl" if dev.type == "cuda" else "gloo")
         self.flat = flatten_grads(self.params, None if self.region is None else self.region.data)
+        self._offs, _ = _flat_layout(self.params)
+        self._syncs = 0
+        self.check_every = int(os.environ.get("REGT_EXCHANGE_CHECK_EVERY", "64"))
+        for p in self.params:            # module_base._fused_step re-attaches a detached .grad through this
+            p._regt_grad_owner = self
+
+    def attach(self, p: torch.nn.Parameter) -> None:
+        """``optimizer.zero_grad()`` (set_to_none, run.py:195) drops ``p.grad``: bind it to its slice of the flat buffer
+        again (zeroed), so the next backward writes into the exchange buffer and not into a stray tensor."""
+        for q, o in zip(self.params, self._offs):
+            if q is p:
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.zero_()
+                p.grad = view
+                return
+        raise RuntimeError("regt_b200: parameter is not part of this exchange")
+
+    def _assert_owned(self) -> None:
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * self.flat.element_size()
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None or not (lo <= g.data_ptr() < hi):
+                raise RuntimeError(
+                    f"regt_b200: the gradient of parameter #{i} {tuple(p.shape)} is not a view of the exchange buffer any more "
+                    "(optimizer.zero_grad(set_to_none=True) or another flat optimizer rebound .grad): the all-reduce would sum a "
+                    "stale buffer.  Use exchange.zero() / zero_grad(set_to_none=False), or FlatRMSprop(..., flat_grad=exchange.flat)")
+
+    def check_peers(self) -> None:
+        """raises if a peer-memory kernel of this exchange timed out waiting for another rank (device sync)."""
+        if self.region is not None and self.region.error():
+            raise RuntimeError("regt_b200: a peer all-reduce kernel gave up waiting for another rank (a rank stalled past the spin "
+                               "limit); the gradients of that step are not the global sums")
 
     def add_loss(self, loss: torch.Tensor) -> None:
         self.flat[-4:-3].add_(loss.reshape(1).to(self.flat.dtype))
 
     def sync(self) -> torch.Tensor:
         """returns the global loss accumulated since the last sync and clears the slot."""
+        self._assert_owned()
+        self._syncs += 1
+        if (self.region is not None and self.check_every > 0 and self._syncs % self.check_every == 0
+                and not torch.cuda.is_current_stream_capturing()):
+            self.check_peers()      # the error flag of the PREVIOUS calls (one device sync every check_every steps)
         if self.world > 1:
             if self.region is not None and self.region.push:
                 loss = torch.empty(1, device=self.flat.device)     # the kernel hands back the reduced loss and clears its slot
@@ -345,6 +398,19 @@ class GradExchange:
 
     def zero(self) -> None:
         self.flat.zero_()
+
+    def close(self) -> None:
+        """collective: every rank has finished its last all-reduce (barrier), then the peer mappings and the region go.
+        Not done from ``__del__``: a peer may still be writing into a region whose owner is being garbage-collected."""
+        if self.region is not None:
+            import torch.distributed as dist
+            self.check_peers()
+            dist.barrier(group=self.group)
+            for p in self.params:
+                p.grad = None
+            self.flat = None
+            self.region.close()
+            self.region = None
 
 
 def all_gather_nodes(local: torch.Tensor, shard: RegionShard, group=None) -> torch.Tensor:

@@ -30,6 +30,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.regt_last_error() is not None
 
 
+def test_library_exports_nothing_undeclared():
+    """every regt_* symbol the shared library exports is declared in the header (product entry points or the TEST HOOKS
+    section): no hidden entry points."""
+    import subprocess
+    from regt_b200 import _lib
+    _lib.load()
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("regt_") and " T " in ln}
+    undeclared = sorted(exported - set(_declared_functions()))
+    assert not undeclared, f"exported but not declared in include/regt_b200.h: {undeclared}"
+
+
 def test_ctypes_structs_mirror_header():
     from regt_b200 import _lib
     src = open(HEADER).read()
