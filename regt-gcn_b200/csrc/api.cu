@@ -13,6 +13,8 @@ int cell_forward_tc(const regt_args* a, const Layout& L, cudaStream_t st);
 int cell_backward_tc(const regt_args* a, const Layout& L, cudaStream_t st);
 int cell_forward_g(const regt_args* a, const Layout& L, cudaStream_t st);
 int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_forward_f(const regt_args* a, const Layout& L, cudaStream_t st);
+int cell_backward_f(const regt_args* a, const Layout& L, cudaStream_t st);
 
 Layout make_layout(const regt_args* a, void* base) {
   Layout L{};
@@ -32,7 +34,22 @@ Layout make_layout(const regt_args* a, void* base) {
   L.S = c.take<float>(BN * F * T);
   L.U = c.take<float>((size_t)a->B * (nseg ? nseg : 1) * F * T);
   const bool tcp = a->precision == REGT_PREC_BF16;   // fused tcgen05 kernels (tile-layout planes); tf32x3 uses the fp32 planes
-  if (!tcp) {
+  if (cell_f_usable(a)) {
+    // fused 3xTF32 cell (cell_f.cu): three saved planes in tile layout; the backward kernel writes the gate-gradient
+    // blocks D and h, h*R row major in (t, q) order (q padded to whole 128-row tiles) for the weight-gradient contraction
+    const size_t nqt = (BN + 127) / 128, rowsP = T * nqt * 128;
+    L.tc_img_f = c.take<unsigned char>(F_IMG_BYTES);
+    L.tc_img_b = c.take<unsigned char>(F_IMG_BYTES);
+    L.Zp = c.take<float>(rowsP * H);
+    L.Rp = c.take<float>(rowsP * H);
+    L.Hcp = c.take<float>(rowsP * H);
+    L.Xt = c.take<float>(BN * F * T);
+    L.h = c.take<float>(rowsP * H);
+    L.hR = c.take<float>(rowsP * H);
+    L.D = c.take<float>(rowsP * 4 * H);
+    L.Feat = c.take<float>(rowsP * 32);
+    L.tc_dpp = c.take<float>(T * TC_MAX_CTAS + 64);
+  } else if (!tcp) {
     L.h = c.take<float>(rows * H);
     L.Z = c.take<float>(rows * H);
     L.Rg = c.take<float>(rows * H);
@@ -114,7 +131,7 @@ extern "C" int regt_cell_forward(const regt_args* a) {
   if (a->precision == REGT_PREC_FP32) return cell_forward_fp32(a, L, st);
   if (a->precision == REGT_PREC_TF32X3) {
     REGT_CHECK(a->H % 32 == 0, "precision tf32x3 needs hidden %% 32 == 0 (got %d); use precision fp32", a->H);
-    return cell_forward_g(a, L, st);
+    return cell_f_usable(a) ? cell_forward_f(a, L, st) : cell_forward_g(a, L, st);
   }
   return cell_forward_tc(a, L, st);
 }
@@ -127,7 +144,7 @@ extern "C" int regt_cell_backward(const regt_args* a) {
   if (a->precision == REGT_PREC_FP32) return cell_backward_fp32(a, L, st);
   if (a->precision == REGT_PREC_TF32X3) {
     REGT_CHECK(a->H % 32 == 0, "precision tf32x3 needs hidden %% 32 == 0 (got %d); use precision fp32", a->H);
-    return cell_backward_g(a, L, st);
+    return cell_f_usable(a) ? cell_backward_f(a, L, st) : cell_backward_g(a, L, st);
   }
   return cell_backward_tc(a, L, st);
 }

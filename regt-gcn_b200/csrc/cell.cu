@@ -365,8 +365,15 @@ __global__ void k_m1_chunks(const int32_t* __restrict__ rseg_ptr, int R, int B, 
   }
 }
 
+// element strides of the two operands (two plane layouts feed this kernel):
+//   dhp(b, node, t)[n] = dhp[(b*N + node) * d_qs + t * d_ts + n]      U(b, seg, f, t) = U[b * u_bs + seg * u_ss + f * u_fs + t * u_ts]
+//   row = (b*N+n)*T + t planes (cell.cu, cell_g.cu): d_qs = T*ldd, d_ts = ldd ; U [B][nseg][F][T]: u_bs = nseg*F*T, u_ss = F*T, u_fs = T, u_ts = 1
+//   period-major planes (cell_f.cu), row = t*BNp + q:  d_qs = ldd, d_ts = BNp*ldd ; Ut [T][B*nseg][F]: u_bs = nseg*F, u_ss = F, u_fs = 1, u_ts = B*nseg*F
+struct M1Strides {
+  long long d_qs, d_ts, u_bs, u_ss, u_fs, u_ts;
+};
 template <int TT>   // TT = periods held in flight per pass (T is processed in groups of TT)
-__global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ dhp, long long ldd, const float* __restrict__ U,
+__global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ dhp, M1Strides sd, const float* __restrict__ U,
                                                   const int32_t* __restrict__ rseg_ptr, const int32_t* __restrict__ rseg_list,
                                                   const int32_t* __restrict__ seg_node, const int32_t* __restrict__ chunk_ptr,
                                                   int B, int N, int T, int H, int R, int nseg, int per,
@@ -395,18 +402,18 @@ __global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ dhp,
     const int s = rseg_list[s0 + (int)(i / B)];
     const int b = (int)(i % B);
     const int node = seg_node[s];
-    const float* ur = U + ((size_t)b * nseg + s) * F * T;
-    const float* dr = dhp + (((size_t)b * N + node) * T) * ldd + n;
+    const float* ur = U + (size_t)b * sd.u_bs + (size_t)s * sd.u_ss;
+    const float* dr = dhp + ((size_t)b * N + node) * sd.d_qs + n;
     for (int t0 = 0; t0 < T; t0 += TT) {
       float4 d[TT];
 #pragma unroll
       for (int k = 0; k < TT; ++k)
-        d[k] = (n_ok && t0 + k < T) ? __ldg(reinterpret_cast<const float4*>(dr + (size_t)(t0 + k) * ldd)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[k] = (n_ok && t0 + k < T) ? __ldg(reinterpret_cast<const float4*>(dr + (size_t)(t0 + k) * sd.d_ts)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int f = 0; f < F; ++f) {
 #pragma unroll
         for (int k = 0; k < TT; ++k) {
-          const float u = (t0 + k < T) ? __ldg(ur + f * T + t0 + k) : 0.f;
+          const float u = (t0 + k < T) ? __ldg(ur + f * sd.u_fs + (t0 + k) * sd.u_ts) : 0.f;
           acc[0][f] = fmaf(d[k].x, u, acc[0][f]);
           acc[1][f] = fmaf(d[k].y, u, acc[1][f]);
           acc[2][f] = fmaf(d[k].z, u, acc[2][f]);
@@ -613,8 +620,12 @@ static int run_bwd(const CellK& k, cudaStream_t st) {
 }
 
 // dM1[r] = sum over the (node, region r) segments of dhp^T U  -- shared with cell_g.cu; dhp = rows of `ldd` floats
-int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, long long ldd, cudaStream_t st) {
+int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, long long ldd, cudaStream_t st, int period_major,
+                         long long BNp) {
   const int H = a->H, T = a->T, R = a->plan.R;
+  const long long nsg = a->plan.nseg;
+  const M1Strides sd = period_major ? M1Strides{ldd, BNp * ldd, nsg * F, F, 1, (long long)a->B * nsg * F}
+                                    : M1Strides{(long long)T * ldd, ldd, nsg * F * T, (long long)F * T, T, 1};
   REGT_CHECK(H % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)dhp % 16) == 0, "wgrad_m1: H and the row pitch must be multiples of 4 floats");
   const long long total = (long long)a->plan.nseg * a->B;
   const int per = (int)max(8ll, (total + M1_TARGET_CHUNKS - 1) / M1_TARGET_CHUNKS);
@@ -623,10 +634,10 @@ int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, 
   k_m1_chunks<<<1, 1024, 0, st>>>(a->plan.rseg_ptr, R, a->B, per, L.m1cp);
   REGT_LAUNCHED("k_m1_chunks", st);
   if (T % 6 == 0)
-    k_wgrad_m1<6><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, ldd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
+    k_wgrad_m1<6><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, sd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
                                                                 L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
   else
-    k_wgrad_m1<4><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, ldd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
+    k_wgrad_m1<4><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, sd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
                                                                 L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
   REGT_LAUNCHED("k_wgrad_m1", st);
   k_m1_reduce<<<R, 256, 0, st>>>(L.part, L.m1cp, H * F, L.dM1);
@@ -634,7 +645,7 @@ int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, 
   return 0;
 }
 int launch_wgrad_m1(const regt_args* a, const Layout& L, cudaStream_t st) {
-  return launch_wgrad_m1_from(a, L, L.D + 3 * (size_t)a->H, 4ll * a->H, st);
+  return launch_wgrad_m1_from(a, L, L.D + 3 * (size_t)a->H, 4ll * a->H, st, 0, 0);
 }
 
 // F-wide weight gradients (dP_g = D_g^T S, dM0 = D_3^T X, biases = column sums, dM1 per region)

@@ -1,0 +1,838 @@
+// Fused fp32-parity (3xTF32) cell for hidden = 128 / 64: the tensor-core gate GEMMs, the GRU nonlinearities, the
+// period-attention sum and their backward data gradients in TWO persistent kernels (one CTA per SM), instead of the
+// five GEMM launches + seven elementwise passes of cell_g.cu.  Per (b,n,t) row the forward writes three H-wide planes
+// (Z, R, H~) and nothing else; the unfused path moves ~17 plane passes forward and ~27 backward.
+//
+// What makes H = 128 fit (cell_tc.cu's design needs the weights resident in shared memory: 442 KB here):
+//   * the A operand (h, then h*R; the gate gradients in the backward) lives in TENSOR MEMORY as tf32 hi | lo column
+//     blocks -- written by the epilogue threads with tcgen05.st, read by "TS" MMAs -- so shared memory holds no A tile;
+//   * the split weights stream from L2 through a ring of 32 KB stages ([128 n][32 k] hi | lo, SW128 K-major, already in
+//     UMMA layout in a per-step global image): a producer thread cycles the same 12 stages per (tile, period) with the
+//     bulk-copy engine and runs ahead of the MMAs by the depth of the ring, across tile boundaries;
+//   * TMEM = 512 columns exactly: A hi | A lo (2H) + two H-wide accumulators that are re-used within a step
+//     (forward: z | r, then the candidate in r's columns; backward: dHR | dhg).
+//
+// Work item = 128 rows (b,n) x ALL T periods: thread (row, H/2 columns) keeps  sum_t probs[t] H'_t  in registers.
+//
+// Forward step (tile, t):            P   h = act(X_t M0 + U_t M1[r] + c0) on the CUDA cores -> TMEM A (hi | lo); S_t tile -> smem
+//   MMA z : acc_z = [h | S] Wz       E1z Z = sigmoid(.), save Z, acc += p Z h                 (under MMA r)
+//   MMA r : acc_r = [h | S] Wr       E1r R = sigmoid(.), save R, h*R -> TMEM A
+//   MMA c : acc_c = [h*R | S] Wc     P(next step) as soon as MMA c is done -> MMA z(next) starts, then
+//                                    E2  H~ = tanh(.), save H~, acc += p (1 - Z) H~          (under MMA z of the next step)
+// Backward step: E0 recompute h, read Z,R,H~,G -> Dc (TMEM A), Dz (registers), planes h, h*R, Dz, Dc, d probs
+//   M1 dHR = Dc B_h ; Dz -> A ; M2z dhg = Dz B_z (E1 under it: Dr = dHR h R(1-R), t1 = dHR R kept in TMEM) ; Dr -> A ;
+//   M2r dhg += Dr B_r ; E2 d h_pre = act'(h)(p G Z + t1 + dhg).  The four gate-gradient blocks D, h and h*R go to HBM row
+//   major (row = t * BNp + q) for the weight-gradient row contraction (gemm_tma.cu), which cannot live here: its
+//   accumulators alone (3 H x H + 4H x 32 fp32) exceed TMEM.
+// Reference arithmetic replaced: models/utils.py:168-188, models/RegionalTemporalGCN.py:134-148, models/TemporalGCN.py:84-90.
+#include <stdlib.h>
+
+#include "cell_tc.cuh"
+
+namespace regt {
+using namespace tc;
+
+namespace {
+constexpr int F = REGT_F;
+constexpr int NEPI_W = 8;                 // epilogue warps: 4 TMEM lane quarters x 2 column halves
+constexpr int W_MMA = NEPI_W;             // issues every tcgen05.mma (one elected lane), owns the TMEM allocation
+// warp NEPI_W + 1: weight-stage producer (bulk copies)
+constexpr int NTHR = (NEPI_W + 2) * 32;
+constexpr int SMEM_MAX = 227 * 1024;
+
+template <int HH>
+struct FCfg {
+  static constexpr int NCH = HH / 32;                 // K chunks (32 tf32 = one 128-byte swizzle row) of an H-wide block
+  static constexpr int TILE = HH * 128;               // [HH n][32 k] tf32, SW128 K-major
+  static constexpr int STAGE = 2 * TILE;              // hi | lo
+  static constexpr int NSTEP = 3 * NCH;               // stages consumed per (tile, period): three H x H blocks
+  static constexpr int RING_IMG = NSTEP * STAGE;
+  static constexpr int SW_TILE = 2 * HH * 16;         // F-wide (S) part of one gate: chunk tile [2 chunks][HH n][16 B]
+  static constexpr int SW_IMG = 3 * 2 * SW_TILE;      // 3 gates x (hi | lo)
+  static constexpr int C_CZR = 0, C_CC = 2 * HH, C_C0 = 3 * HH, C_M0 = 4 * HH, C_M1 = 12 * HH, C_PROBS = 20 * HH,
+                       C_FLOATS = 20 * HH + 64;
+  static constexpr int TAIL = SW_IMG + C_FLOATS * 4;  // resident part of the image (copied once per CTA)
+  static constexpr int IMG = RING_IMG + TAIL;
+  static constexpr int S_TILE = 2 * TC_ROWS * 16;     // A operand of the F-wide part: S_t (8 tf32) per row, chunk tile
+  static constexpr int FIXED = ((TAIL + 1023) & ~1023) + 2 * S_TILE;
+  static constexpr int NS_FIT = (SMEM_MAX - 1024 - FIXED) / STAGE;
+  static constexpr int NS = NS_FIT < 2 * NSTEP ? NS_FIT : 2 * NSTEP;   // ring depth
+  static constexpr int SMEM = 1024 + NS * STAGE + FIXED;
+  static constexpr int CWF = HH / 2;                  // columns per epilogue thread
+  static constexpr int TCOLS = 4 * HH;                // TMEM columns: A hi | A lo | acc0 | acc1
+  static_assert(HH % 32 == 0 && TCOLS <= 512 && NS >= 3, "unsupported hidden width");
+};
+
+struct FArgs {
+  int BN, BNp, N, T, nseg, mode, Bsz, nqt;
+  const float *Xt, *St, *Ut;       // period-major F-wide features [T][rows][F]
+  const int32_t *seg_ptr, *seg_reg;
+  const float* M1t;                // [R][F][H] fp32 (region 0 is also in the image)
+  const uint8_t* img;
+  float *Zp, *Rp, *Hcp;            // saved planes, tile layout [T][nqt][H/4][128][4]
+  float* out_hidden;               // [BN][H]
+  // backward
+  const float* G;                  // [BN][H] gradient wrt out_hidden
+  float *D, *hpl, *hRpl;           // [T*BNp][4H], [T*BNp][H], [T*BNp][H] row major, row = t*BNp + q
+  float* dpp;                      // [grid][T] attention-gradient partials
+};
+
+__device__ __forceinline__ uint32_t tf32_rn_bits(float a) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
+  return u;
+}
+__device__ __forceinline__ float sigm(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+
+// 16 fp32 values of this thread's row -> tf32 hi | lo columns [col, col+16) of the TMEM A operand
+template <int HH>
+__device__ __forceinline__ void put_a16(uint32_t tlane, int col, const float (&v)[16]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hi[i] = tf32_rn_bits(v[i]);
+    lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+  }
+  tmem_st16(tlane + col, hi);
+  tmem_st16(tlane + HH + col, lo);
+}
+template <int HH>
+__device__ __forceinline__ void get_a16(uint32_t tlane, int col, float (&v)[16]) {
+  float lo[16];
+  tmem_ld16(tlane + col, v);
+  tmem_ld16(tlane + HH + col, lo);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += lo[i];
+}
+__device__ __forceinline__ void st_f32x16(uint32_t taddr, const float (&v)[16]) {
+  uint32_t u[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(v[i]);
+  tmem_st16(taddr, u);
+}
+
+// re-read of a 16-byte piece this thread stored earlier in the kernel (plain coherent load, never the read-only path)
+__device__ __forceinline__ float4 ld_own4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// byte offset of the 16-byte piece holding columns [c, c+4) of row r inside a saved-plane tile [H/4][128][4]
+__device__ __forceinline__ size_t piece(int r, int c) { return ((size_t)(c >> 2) * TC_ROWS + r) * 16; }
+
+struct Row {
+  long long q;
+  int b, s0, s1;
+  bool valid;
+  __device__ __forceinline__ void set(const FArgs& a, int qt, int r) {
+    q = (long long)qt * TC_ROWS + r;
+    valid = q < a.BN;
+    b = valid ? (int)(q / a.N) : 0;
+    s0 = s1 = 0;
+    if (valid && a.mode != REGT_MODE_TGCN) {
+      const int n = (int)(q - (long long)b * a.N);
+      s0 = a.seg_ptr[n];
+      s1 = a.seg_ptr[n + 1];
+    }
+  }
+};
+
+struct Feats {
+  float x[8], u[8];
+};
+__device__ __forceinline__ void load8(const float* p, float (&v)[8], float m) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = m * a.x; v[1] = m * a.y; v[2] = m * a.z; v[3] = m * a.w; v[4] = m * b.x; v[5] = m * b.y; v[6] = m * b.z; v[7] = m * b.w;
+}
+__device__ __forceinline__ void load_feats(const FArgs& a, const Row& ri, int t, Feats& f) {
+  const float m = ri.valid ? 1.f : 0.f;
+  load8(a.Xt + ((size_t)t * a.BN + (ri.valid ? ri.q : 0)) * F, f.x, m);
+  if (ri.s1 > ri.s0) load8(a.Ut + (((size_t)t * a.Bsz + ri.b) * a.nseg + ri.s0) * F, f.u, 1.f);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f.u[i] = 0.f;
+  }
+}
+// h[16] for columns [c, c+16) of one row at period t: the regional combine on the F-wide features
+// (models/RegionalTemporalGCN.py:136-143 collapsed: X_t M0 + sum_seg U_seg,t M1[region] + c0, leaky_relu)
+template <int HH>
+__device__ __forceinline__ void h16(const FArgs& a, const float* consts, const Row& ri, const Feats& f, int t, int c, float (&h)[16]) {
+  using C = FCfg<HH>;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i] = consts[C::C_C0 + c + i];
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(consts + C::C_M0 + k * HH + c + i);
+      h[i] = fmaf(f.x[k], w.x, h[i]); h[i + 1] = fmaf(f.x[k], w.y, h[i + 1]);
+      h[i + 2] = fmaf(f.x[k], w.z, h[i + 2]); h[i + 3] = fmaf(f.x[k], w.w, h[i + 3]);
+    }
+  }
+  for (int s = ri.s0; s < ri.s1; ++s) {
+    const int reg = a.seg_reg[s];
+    float uv[8];
+    if (s == ri.s0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) uv[i] = f.u[i];
+    } else {   // a node that appears in several regional lists (random decomposition)
+      load8(a.Ut + (((size_t)t * a.Bsz + ri.b) * a.nseg + s) * F, uv, 1.f);
+    }
+    if (reg == 0) {
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(consts + C::C_M1 + k * HH + c + i);
+          h[i] = fmaf(uv[k], w.x, h[i]); h[i + 1] = fmaf(uv[k], w.y, h[i + 1]);
+          h[i + 2] = fmaf(uv[k], w.z, h[i + 2]); h[i + 3] = fmaf(uv[k], w.w, h[i + 3]);
+        }
+      }
+    } else {
+      const float* m = a.M1t + (size_t)reg * F * HH + c;
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(m + k * HH + i));
+          h[i] = fmaf(uv[k], w.x, h[i]); h[i + 1] = fmaf(uv[k], w.y, h[i + 1]);
+          h[i + 2] = fmaf(uv[k], w.z, h[i + 2]); h[i + 3] = fmaf(uv[k], w.w, h[i + 3]);
+        }
+      }
+    }
+  }
+  if (a.mode == REGT_MODE_REGIONAL) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = h[i] > 0.f ? h[i] : 0.01f * h[i];   // F.leaky_relu
+  }
+}
+
+// one H x H block: acc (+)= A(TMEM, hi|lo) . W_g^T over the NCH ring stages of gate block g, three tf32 products
+// (hi*hi + lo*hi + hi*lo).  Called by the whole MMA warp; lane 0 issues.
+template <int HH>
+__device__ __forceinline__ void mma_block(uint32_t tmem, uint32_t acc_col, uint32_t ring0, uint64_t* bar_full, uint64_t* bar_empty,
+                                          long long& gs, int lane, bool accumulate) {
+  using C = FCfg<HH>;
+  const uint32_t idesc = make_idesc(FMT_TF32, 128, HH, 0, 0);
+#pragma unroll 1
+  for (int kc = 0; kc < C::NCH; ++kc, ++gs) {
+    const int st = (int)(gs % C::NS);
+    mbar_wait(&bar_full[st], (uint32_t)((gs / C::NS) & 1));
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t bt = ring0 + st * C::STAGE;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const uint32_t ap = tmem + (p == 1 ? HH : 0) + kc * 32, bp = bt + (p == 2 ? C::TILE : 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ts_tf32(tmem + acc_col, ap + 8 * k, make_desc(bp + k * 32, 16, 1024, LAYOUT_SW128), idesc,
+                       (accumulate || kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_empty[st]);   // the stage may be refilled once these MMAs have read it
+    }
+    __syncwarp();
+  }
+}
+// the F-wide part of a gate: acc += S_t (smem chunk tile, hi|lo) . Ws_g^T   (K = 8: one MMA per product)
+template <int HH>
+__device__ __forceinline__ void mma_spart(uint32_t tmem, uint32_t acc_col, uint32_t stile, uint32_t sw_g, int lane) {
+  using C = FCfg<HH>;
+  if (lane == 0) {
+    const uint32_t idesc = make_idesc(FMT_TF32, 128, HH, 0, 0);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      umma<FMT_TF32>(tmem + acc_col, make_desc(stile + (p == 1 ? C::S_TILE : 0), TC_ROWS * 16, 128, LAYOUT_NONE),
+                     make_desc(sw_g + (p == 2 ? C::SW_TILE : 0), HH * 16, 128, LAYOUT_NONE), idesc, 1u);
+  }
+  __syncwarp();
+}
+
+// weight-stage producer: cycles the NSTEP stages of the image for every (tile, period) of this CTA
+template <int HH>
+__device__ __forceinline__ void produce(const uint8_t* img, uint8_t* ring, uint64_t* bar_full, uint64_t* bar_empty, long long total) {
+  using C = FCfg<HH>;
+  for (long long gs = 0; gs < total; ++gs) {
+    const int st = (int)(gs % C::NS);
+    if (gs >= C::NS) mbar_wait(&bar_empty[st], (uint32_t)((gs / C::NS - 1) & 1));
+    mbar_arrive_expect_tx(&bar_full[st], C::STAGE);
+    const uint8_t* src = img + (size_t)(gs % C::NSTEP) * C::STAGE;
+#pragma unroll
+    for (int o = 0; o < C::STAGE; o += 16384) bulk_g2s(ring + (size_t)st * C::STAGE + o, src + o, 16384, &bar_full[st]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int HH>
+__global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
+  using C = FCfg<HH>;
+  constexpr int CWF = C::CWF;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = sm;
+  uint8_t* tail = ring + C::NS * C::STAGE;                    // S-part weights | constants
+  uint8_t* stile = tail + ((C::TAIL + 1023) & ~1023);         // S_t operand tile (hi | lo)
+  __shared__ uint64_t bar_full[C::NS], bar_empty[C::NS], bar_tail, bar_a, bar_z, bar_r, bar_a2, bar_c, bar_cfree;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_items = (a.nqt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int S = n_items * a.T;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::NS; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_tail, 1);
+    mbar_init(&bar_a, NEPI_W * 32);
+    mbar_init(&bar_z, 1);
+    mbar_init(&bar_r, 1);
+    mbar_init(&bar_a2, NEPI_W * 32);
+    mbar_init(&bar_c, 1);
+    mbar_init(&bar_cfree, NEPI_W * 32);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar_tail, C::TAIL);
+    for (int o = 0; o < C::TAIL; o += 16384) bulk_g2s(tail + o, a.img + C::RING_IMG + o, min(16384, C::TAIL - o), &bar_tail);
+  }
+  if (warp == W_MMA) tmem_alloc(&tmem_base_s, C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const float* consts = reinterpret_cast<const float*>(tail + C::SW_IMG);
+
+  if (warp < NEPI_W) {
+    // ================= epilogue threads: thread = (row r = TMEM lane, CWF columns) =================
+    mbar_wait(&bar_tail, 0);
+    const int qd = warp & 3, ch = warp >> 2;
+    const int r = qd * 32 + lane, c0 = ch * CWF;
+    const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
+    const uint32_t tZ = tl + 2 * HH, tR = tl + 3 * HH;
+    float acc[CWF];
+#pragma unroll
+    for (int j = 0; j < CWF; ++j) acc[j] = 0.f;
+    Row ri;
+    // P(s): h of step s -> TMEM A, S_t tile -> smem, then bar_a
+    auto P = [&](int s) {
+      const int k = s / a.T, t = s - k * a.T;
+      const int qt = (int)blockIdx.x + k * (int)gridDim.x;
+      if (t == 0) ri.set(a, qt, r);
+      Feats f;
+      load_feats(a, ri, t, f);
+      if (ch == 0) {   // the F-wide gate operand S_t of this row: two 16-byte chunks, hi | lo
+        float sv[8];
+        load8(a.St + ((size_t)t * a.BN + (ri.valid ? ri.q : 0)) * F, sv, ri.valid ? 1.f : 0.f);
+        float hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          hi[i] = __uint_as_float(tf32_rn_bits(sv[i]));
+          lo[i] = sv[i] - hi[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          *reinterpret_cast<float4*>(stile + chunk_off(r, c, TC_ROWS)) = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+          *reinterpret_cast<float4*>(stile + C::S_TILE + chunk_off(r, c, TC_ROWS)) = make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        }
+        fence_proxy_async();
+      }
+#pragma unroll 1
+      for (int j = 0; j < CWF; j += 16) {
+        float h[16];
+        h16<HH>(a, consts, ri, f, t, c0 + j, h);
+        put_a16<HH>(tl, c0 + j, h);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_a);
+    };
+    if (S > 0) P(0);
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      const int k = s / a.T, t = s - k * a.T;
+      const int qt = (int)blockIdx.x + k * (int)gridDim.x;
+      const long long q_cur = (long long)qt * TC_ROWS + r;
+      const float p = consts[C::C_PROBS + t];
+      uint8_t* zt = reinterpret_cast<uint8_t*>(a.Zp) + ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      uint8_t* rt = reinterpret_cast<uint8_t*>(a.Rp) + ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      uint8_t* ct = reinterpret_cast<uint8_t*>(a.Hcp) + ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      // ---- E1z: update gate (runs while the r-gate MMAs are in flight) ----
+      mbar_wait(&bar_z, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16], h[16];
+        tmem_ld16(tZ + c0 + j, v);
+        get_a16<HH>(tl, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = sigm(v[i] + consts[C::C_CZR + c0 + j + i]);
+          acc[j + i] = fmaf(p * v[i], h[i], acc[j + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(zt + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      // ---- E1r: reset gate, h*R -> A operand of the candidate GEMM ----
+      mbar_wait(&bar_r, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16], h[16];
+        tmem_ld16(tR + c0 + j, v);
+        get_a16<HH>(tl, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = sigm(v[i] + consts[C::C_CZR + HH + c0 + j + i]);
+          h[i] *= v[i];
+        }
+        put_a16<HH>(tl, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(rt + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_a2);
+      // ---- candidate GEMM done: A is free -> h of the next step first (its z-gate MMAs start), then E2 under them ----
+      mbar_wait(&bar_c, ph);
+      tc_fence_after();
+      if (s + 1 < S) P(s + 1);
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16];
+        tmem_ld16(tR + c0 + j, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 z = ld_own4(zt + piece(r, c0 + j + i));   // this thread's own store above
+          const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float hc = tanh_(v[i + e] + consts[C::C_CC + c0 + j + i + e]);
+            v[i + e] = hc;
+            acc[j + i + e] = fmaf(p * (1.0f - zz[e]), hc, acc[j + i + e]);
+          }
+          *reinterpret_cast<float4*>(ct + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_cfree);
+      if (t + 1 == a.T) {   // item done: out_hidden = sum_t probs[t] H'_t
+        if (q_cur < a.BN) {
+          float* o = a.out_hidden + (size_t)q_cur * HH + c0;
+#pragma unroll
+          for (int j = 0; j < CWF; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < CWF; ++j) acc[j] = 0.f;
+      }
+    }
+    tc_fence_before();
+  } else if (warp == W_MMA) {
+    mbar_wait(&bar_tail, 0);
+    const uint32_t ring0 = smem_u32(ring), sw0 = smem_u32(tail), st0 = smem_u32(stile);
+    long long gs = 0;
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      mbar_wait(&bar_a, ph);
+      tc_fence_after();
+      mma_block<HH>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false);
+      mma_spart<HH>(tmem, 2 * HH, st0, sw0, lane);
+      if (lane == 0) umma_commit(&bar_z);
+      __syncwarp();
+      if (s > 0) {   // acc_c of the previous step (same columns as acc_r) has been read
+        mbar_wait(&bar_cfree, (uint32_t)((s - 1) & 1));
+        tc_fence_after();
+      }
+      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false);
+      mma_spart<HH>(tmem, 3 * HH, st0, sw0 + 2 * C::SW_TILE, lane);
+      if (lane == 0) umma_commit(&bar_r);
+      __syncwarp();
+      mbar_wait(&bar_a2, ph);
+      tc_fence_after();
+      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false);
+      mma_spart<HH>(tmem, 3 * HH, st0, sw0 + 4 * C::SW_TILE, lane);
+      if (lane == 0) umma_commit(&bar_c);
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else if (lane == 0) {
+    produce<HH>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
+  }
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, C::TCOLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (data gradients; the weight gradients are row contractions over what this kernel writes)
+// ------------------------------------------------------------------------------------------
+template <int HH>
+__global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
+  using C = FCfg<HH>;
+  constexpr int CWF = C::CWF;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = sm;
+  uint8_t* tail = ring + C::NS * C::STAGE;
+  __shared__ uint64_t bar_full[C::NS], bar_empty[C::NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[NEPI_W][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_items = (a.nqt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int S = n_items * a.T;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::NS; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_tail, 1);
+    mbar_init(&bar_a, NEPI_W * 32);
+    mbar_init(&bar_1, 1);
+    mbar_init(&bar_az, NEPI_W * 32);
+    mbar_init(&bar_2z, 1);
+    mbar_init(&bar_ar, NEPI_W * 32);
+    mbar_init(&bar_2r, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar_tail, C::TAIL);
+    for (int o = 0; o < C::TAIL; o += 16384) bulk_g2s(tail + o, a.img + C::RING_IMG + o, min(16384, C::TAIL - o), &bar_tail);
+  }
+  for (int i = tid; i < NEPI_W * 64; i += NTHR) (&red[0][0])[i] = 0.f;
+  if (warp == W_MMA) tmem_alloc(&tmem_base_s, C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const float* consts = reinterpret_cast<const float*>(tail + C::SW_IMG);
+
+  if (warp < NEPI_W) {
+    mbar_wait(&bar_tail, 0);
+    const int qd = warp & 3, ch = warp >> 2;
+    const int r = qd * 32 + lane, c0 = ch * CWF;
+    const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
+    const uint32_t t1c = tl + 2 * HH, t2c = tl + 3 * HH;   // acc1 = dHR (then dHR * R), acc2 = dhg
+    Row ri;
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      const int k = s / a.T, t = s - k * a.T;
+      const int qt = (int)blockIdx.x + k * (int)gridDim.x;
+      if (t == 0) ri.set(a, qt, r);
+      const float p = consts[C::C_PROBS + t];
+      const size_t toff = ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      const uint8_t* zt = reinterpret_cast<const uint8_t*>(a.Zp) + toff;
+      const uint8_t* rt = reinterpret_cast<const uint8_t*>(a.Rp) + toff;
+      const uint8_t* ct = reinterpret_cast<const uint8_t*>(a.Hcp) + toff;
+      const size_t rowp = (size_t)t * a.BNp + (size_t)qt * TC_ROWS + r;
+      float* Dr_ = a.D + rowp * 4 * HH;
+      float* hrow = a.hpl + rowp * HH;
+      float* hRrow = a.hRpl + rowp * HH;
+      const float* grow = a.G + (size_t)(ri.valid ? ri.q : 0) * HH;
+      const float gm = ri.valid ? 1.f : 0.f;     // padded rows of the last tile: zero gradient everywhere
+      // ---- E0: recompute h; gate gradients from the saved planes ----
+      Feats f;
+      load_feats(a, ri, t, f);
+      float dz[CWF];
+      float dp = 0.f;
+      unsigned long long neg = 0ull;             // h <= 0 per column (leaky_relu slope of the regional combine)
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float h[16], dc[16];
+        h16<HH>(a, consts, ri, f, t, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const int c = c0 + j + i;
+          const float4 z4 = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c)));
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + piece(r, c)));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + c));
+          const float z[4] = {z4.x, z4.y, z4.z, z4.w}, rg[4] = {r4.x, r4.y, r4.z, r4.w}, hc[4] = {c4.x, c4.y, c4.z, c4.w};
+          const float g[4] = {gm * g4.x, gm * g4.y, gm * g4.z, gm * g4.w};
+          float hr[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float hh = h[i + e];
+            const float gg = p * g[e];                                        // dH' = probs[t] * d out_hidden
+            dp = fmaf(g[e], z[e] * hh + (1.0f - z[e]) * hc[e], dp);
+            dz[j + i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
+            dc[i + e] = gg * (1.0f - z[e]) * (1.0f - hc[e] * hc[e]);
+            hr[e] = hh * rg[e];
+            if (!(hh > 0.f)) neg |= 1ull << (j + i + e);
+          }
+          *reinterpret_cast<float4*>(Dr_ + c) = make_float4(dz[j + i], dz[j + i + 1], dz[j + i + 2], dz[j + i + 3]);
+          *reinterpret_cast<float4*>(Dr_ + 2 * HH + c) = make_float4(dc[i], dc[i + 1], dc[i + 2], dc[i + 3]);
+          *reinterpret_cast<float4*>(hrow + c) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+          *reinterpret_cast<float4*>(hRrow + c) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+        }
+        put_a16<HH>(tl, c0 + j, dc);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_a);
+      // attention gradient d probs[t] += sum G * H'_t : fixed-order warp sum, one smem slot per (warp, period)
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
+      if (lane == 0) red[warp][t] += dp;
+      // ---- M1 done (dHR in acc1): Dz -> A, M2z starts ----
+      mbar_wait(&bar_1, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+        put_a16<HH>(tl, c0 + j, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_az);
+      // ---- E1 (under M2z): Dr = dHR h R (1-R) (registers, reusing dz), t1 = dHR R -> acc1 in place ----
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16];
+        tmem_ld16(t1c + c0 + j, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const int c = c0 + j + i;
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
+          const float4 h4 = ld_own4(hrow + c);     // this thread's own store above
+          const float rg[4] = {r4.x, r4.y, r4.z, r4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dz[j + i + e] = v[i + e] * hh[e] * rg[e] * (1.0f - rg[e]);
+            v[i + e] *= rg[e];
+          }
+          *reinterpret_cast<float4*>(Dr_ + HH + c) = make_float4(dz[j + i], dz[j + i + 1], dz[j + i + 2], dz[j + i + 3]);
+        }
+        st_f32x16(t1c + c0 + j, v);
+      }
+      tmem_st_wait();
+      // ---- M2z done (A free): Dr -> A, M2r ----
+      mbar_wait(&bar_2z, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+        put_a16<HH>(tl, c0 + j, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_ar);
+      // ---- E2: d h_pre = act'(h) (p G Z + dHR R + dhg) ----
+      mbar_wait(&bar_2r, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float v[16], u[16];
+        tmem_ld16(t2c + c0 + j, v);
+        tmem_ld16(t1c + c0 + j, u);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const int c = c0 + j + i;
+          const float4 z4 = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c)));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + c));
+          const float z[4] = {z4.x, z4.y, z4.z, z4.w}, g[4] = {gm * g4.x, gm * g4.y, gm * g4.z, gm * g4.w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float d = fmaf(p * g[e], z[e], u[i + e]) + v[i + e];
+            if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i + e)) & 1ull)) d *= 0.01f;
+            o[e] = d;
+          }
+          *reinterpret_cast<float4*>(Dr_ + 3 * HH + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == W_MMA) {
+    const uint32_t ring0 = smem_u32(ring);
+    long long gs = 0;
+    for (int s = 0; s < S; ++s) {
+      const uint32_t ph = s & 1;
+      mbar_wait(&bar_a, ph);       // also: E2 of the previous step has read acc1 / acc2 (program order of the epilogue threads)
+      tc_fence_after();
+      mma_block<HH>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false);     // dHR = Dc . B_h
+      if (lane == 0) umma_commit(&bar_1);
+      __syncwarp();
+      mbar_wait(&bar_az, ph);
+      tc_fence_after();
+      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false);     // dhg = Dz . B_z
+      if (lane == 0) umma_commit(&bar_2z);
+      __syncwarp();
+      mbar_wait(&bar_ar, ph);
+      tc_fence_after();
+      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, true);      // dhg += Dr . B_r
+      if (lane == 0) umma_commit(&bar_2r);
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else if (lane == 0) {
+    produce<HH>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
+  }
+  __syncthreads();
+  if (tid < a.T) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NEPI_W; ++w) s += red[w][tid];
+    a.dpp[(size_t)blockIdx.x * a.T + tid] = s;
+  }
+  if (warp == W_MMA) tmem_dealloc(tmem, C::TCOLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-step weight images (forward: [S|h] gate weights; backward: B_g transposed for the data gradients)
+// ------------------------------------------------------------------------------------------
+template <int HH>
+__device__ __forceinline__ void put_stage(uint8_t* img, int g, int n, int k, float v) {
+  using C = FCfg<HH>;
+  uint8_t* st = img + (size_t)(g * C::NCH + (k >> 5)) * C::STAGE;
+  const uint32_t off = sw128_off(n, (k & 31) * 4, HH);
+  const float hi = __uint_as_float(tf32_rn_bits(v));
+  *reinterpret_cast<float*>(st + off) = hi;
+  *reinterpret_cast<float*>(st + C::TILE + off) = v - hi;
+}
+// Wzr [F+H][2H], Wc [F+H][H] (rows 0..F-1: S part, rows F..: h part); lin_w[g] [H][2H]
+template <int HH>
+__global__ void k_pack_f(const float* __restrict__ Wzr, const float* __restrict__ Wc, const float* __restrict__ czr,
+                         const float* __restrict__ cc, const float* __restrict__ c0, const float* __restrict__ M0t,
+                         const float* __restrict__ M1t, const float* __restrict__ probs, int T, const float* __restrict__ lw0,
+                         const float* __restrict__ lw1, const float* __restrict__ lw2, uint8_t* __restrict__ img_f,
+                         uint8_t* __restrict__ img_b) {
+  using C = FCfg<HH>;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < 3 * HH * HH) {      // forward H-wide part: gate g, output n, input k
+    const int g = j / (HH * HH), rem = j % (HH * HH), n = rem / HH, k = rem % HH;
+    const float v = g < 2 ? Wzr[(size_t)(F + k) * 2 * HH + g * HH + n] : Wc[(size_t)(F + k) * HH + n];
+    put_stage<HH>(img_f, g, n, k, v);
+    // backward: dHR = Dc . B_h, dhg = Dz . B_z + Dr . B_r  ->  stage order  B_h, B_z, B_r ; tile rows = input index k_in,
+    // K = gate output index:  Bt_g[k_in][n_out] = linear_g.weight[n_out][H + k_in]
+    const int gb = (g == 0) ? 1 : (g == 1 ? 2 : 0);     // this thread's g indexes lw: z -> slot 1, r -> slot 2, h -> slot 0
+    const float* lw = g == 0 ? lw0 : (g == 1 ? lw1 : lw2);
+    put_stage<HH>(img_b, gb, /*row k_in=*/n, /*K index n_out=*/k, lw[(size_t)k * 2 * HH + HH + n]);
+    return;
+  }
+  j -= 3 * HH * HH;
+  if (j < 3 * HH * 8) {       // forward F-wide part: chunk tile [2][HH][16 B] per gate, hi | lo
+    const int g = j / (HH * 8), rem = j % (HH * 8), n = rem / 8, f = rem % 8;
+    const float v = g < 2 ? Wzr[(size_t)f * 2 * HH + g * HH + n] : Wc[(size_t)f * HH + n];
+    uint8_t* t0 = img_f + C::RING_IMG + (size_t)g * 2 * C::SW_TILE;
+    const uint32_t off = chunk_off(n, f >> 2, HH) + (f & 3) * 4;
+    const float hi = __uint_as_float(tf32_rn_bits(v));
+    *reinterpret_cast<float*>(t0 + off) = hi;
+    *reinterpret_cast<float*>(t0 + C::SW_TILE + off) = v - hi;
+    return;
+  }
+  j -= 3 * HH * 8;
+  if (j < C::C_FLOATS) {
+    float v = 0.f;
+    if (j < C::C_CC) v = czr[j];
+    else if (j < C::C_C0) v = cc[j - C::C_CC];
+    else if (j < C::C_M0) v = c0 ? c0[j - C::C_C0] : 0.f;
+    else if (j < C::C_M1) v = M0t ? M0t[j - C::C_M0] : 0.f;
+    else if (j < C::C_PROBS) v = M1t ? M1t[j - C::C_M1] : 0.f;
+    else v = (j - C::C_PROBS) < T ? probs[j - C::C_PROBS] : 0.f;
+    reinterpret_cast<float*>(img_f + C::RING_IMG + C::SW_IMG)[j] = v;
+    reinterpret_cast<float*>(img_b + C::RING_IMG + C::SW_IMG)[j] = v;
+  }
+}
+
+// Feat[t * BNp + q] = S_t | X_t | 1 | 0  (32 floats): second operand of the weight-gradient row contraction, same row
+// order as the backward kernel's D / h / h*R; padded rows (q >= BN) are zero
+__global__ void __launch_bounds__(256) k_feat_f(const float* __restrict__ Xt, const float* __restrict__ St, int BN, int BNp, int T,
+                                                float* __restrict__ Feat) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = i >> 3;
+  if (row >= (long long)T * BNp) return;
+  const int c4 = (int)(i & 7);
+  const int t = (int)(row / BNp), q = (int)(row - (long long)t * BNp);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < BN) {
+    if (c4 < 2) v = __ldg(reinterpret_cast<const float4*>(St + ((size_t)t * BN + q) * F) + c4);
+    else if (c4 < 4) v = __ldg(reinterpret_cast<const float4*>(Xt + ((size_t)t * BN + q) * F) + (c4 - 2));
+    else if (c4 == 4) v.x = 1.0f;
+  }
+  reinterpret_cast<float4*>(Feat)[i] = v;
+}
+
+template <int HH>
+FArgs make_fargs(const regt_args* a, const Layout& L) {
+  FArgs k{};
+  k.BN = a->B * a->N; k.N = a->N; k.T = a->T; k.nseg = a->plan.nseg; k.mode = a->mode; k.Bsz = a->B;
+  k.nqt = (k.BN + TC_ROWS - 1) / TC_ROWS;
+  k.BNp = k.nqt * TC_ROWS;
+  k.Xt = L.Xt; k.St = L.S; k.Ut = L.U;
+  k.seg_ptr = a->plan.seg_ptr; k.seg_reg = a->plan.seg_reg;
+  k.M1t = L.M1t;
+  k.Zp = L.Zp; k.Rp = L.Rp; k.Hcp = L.Hcp;
+  k.out_hidden = a->out_hidden;
+  k.G = L.G; k.D = L.D; k.hpl = L.h; k.hRpl = L.hR; k.dpp = L.tc_dpp;
+  return k;
+}
+int num_sms_f() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int HH>
+int run_fwd(const regt_args* a, const Layout& L, cudaStream_t st) {
+  using C = FCfg<HH>;
+  static_assert(C::IMG <= F_IMG_BYTES, "weight image too large");
+  const int n_pack = 3 * HH * HH + 3 * HH * 8 + C::C_FLOATS;
+  k_pack_f<HH><<<cdiv(n_pack, 256), 256, 0, st>>>(L.Wzr, L.Wc, L.czr, L.cc, L.c0, L.M0t, L.M1t, L.probs, a->T, a->p.lin_w[0],
+                                                  a->p.lin_w[1], a->p.lin_w[2], L.tc_img_f, L.tc_img_b);
+  REGT_LAUNCHED("k_pack_f", st);
+  return 0;
+}
+template <int HH>
+int run_fwd_kernel(const regt_args* a, const Layout& L, cudaStream_t st) {
+  using C = FCfg<HH>;
+  FArgs k = make_fargs<HH>(a, L);
+  k.img = L.tc_img_f;
+  REGT_CUDA(cudaFuncSetAttribute(k_cell_fwd_f<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  k_cell_fwd_f<HH><<<min(num_sms_f(), k.nqt), NTHR, C::SMEM, st>>>(k);
+  REGT_LAUNCHED("k_cell_fwd_f", st);
+  return 0;
+}
+template <int HH>
+int run_bwd_kernel(const regt_args* a, const Layout& L, cudaStream_t st, int* grid_out) {
+  using C = FCfg<HH>;
+  FArgs k = make_fargs<HH>(a, L);
+  k.img = L.tc_img_b;
+  const int grid = min(num_sms_f(), k.nqt);
+  REGT_CHECK(grid <= TC_MAX_CTAS, "fused backward: grid %d exceeds the partial buffers", grid);
+  REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd_f<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  k_cell_bwd_f<HH><<<grid, NTHR, C::SMEM, st>>>(k);
+  REGT_LAUNCHED("k_cell_bwd_f", st);
+  *grid_out = grid;
+  return 0;
+}
+}  // namespace
+
+bool cell_f_usable(const regt_args* a) {
+  const char* e = getenv("REGT_UNFUSED");      // "1": the GEMM-by-GEMM path of cell_g.cu (kept for H = 256 and as the A/B baseline)
+  const bool off = e && e[0] == '1';
+  return !off && a->precision == REGT_PREC_TF32X3 && (a->H == 128 || a->H == 64) && a->mode != REGT_MODE_TGCN && a->T <= 64;
+}
+int launch_pack_f(const regt_args* a, const Layout& L, cudaStream_t st) {
+  return a->H == 128 ? run_fwd<128>(a, L, st) : run_fwd<64>(a, L, st);
+}
+int launch_cell_fwd_f(const regt_args* a, const Layout& L, cudaStream_t st) {
+  return a->H == 128 ? run_fwd_kernel<128>(a, L, st) : run_fwd_kernel<64>(a, L, st);
+}
+int launch_cell_bwd_f(const regt_args* a, const Layout& L, cudaStream_t st, int* grid) {
+  return a->H == 128 ? run_bwd_kernel<128>(a, L, st, grid) : run_bwd_kernel<64>(a, L, st, grid);
+}
+int launch_feat_f(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int BN = a->B * a->N, BNp = (BN + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+  const long long n = (long long)a->T * BNp * 8;
+  k_feat_f<<<cdiv(n, 256), 256, 0, st>>>(L.Xt, L.S, BN, BNp, a->T, L.Feat);
+  REGT_LAUNCHED("k_feat_f", st);
+  return 0;
+}
+
+}  // namespace regt

@@ -450,4 +450,66 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   return launch_chain(a, L, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// fused 3xTF32 cell (kernels in cell_f.cu): hidden 128 / 64
+// ------------------------------------------------------------------------------------------
+int launch_feat_tc(const regt_graph_plan& p, const float* x, int B, int xN, int T, float* Xt, float* St, float* Ut, cudaStream_t st);
+int launch_pack_f(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_cell_fwd_f(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_cell_bwd_f(const regt_args* a, const Layout& L, cudaStream_t st, int* grid);
+int launch_feat_f(const regt_args* a, const Layout& L, cudaStream_t st);
+int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, long long ldd, cudaStream_t st, int period_major,
+                         long long BNp);
+
+int cell_forward_f(const regt_args* a, const Layout& L, cudaStream_t st) {
+  // features (graph + x) and collapsed weights (parameters) are independent: two streams
+  cudaStream_t side = fork_side(st);
+  cudaStream_t fs = side ? side : st;
+  if (launch_feat_tc(a->plan, a->x, a->B, a->x_rows > 0 ? a->x_rows : a->N, a->T, L.Xt, L.S, L.U, fs)) return -1;
+  if (launch_feat_f(a, L, fs)) return -1;     // feature plane of the weight-gradient contractions (cell and head backward)
+  if (launch_prep(a, L, st)) return -1;
+  if (launch_pack_f(a, L, st)) return -1;
+  if (side && join_side(st)) return -1;
+  return launch_cell_fwd_f(a, L, st);
+}
+
+int cell_backward_f(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int H = a->H, T = a->T;
+  const long long BN = (long long)a->B * a->N, BNp = (BN + 127) / 128 * 128, rowsP = BNp * T;
+  int grid = 0;
+  if (launch_cell_bwd_f(a, L, st, &grid)) return -1;
+  k_g_sum_parts<<<cdiv(T, 32), dim3(32, 8), 0, st>>>(L.tc_dpp, T, grid, T, L.dprobs);
+  REGT_LAUNCHED("k_g_sum_parts", st);
+  // weight gradients: ONE row contraction over the four gate-gradient blocks of D (z | r against h, h~ against h*R,
+  // h_pre against the feature plane only; every block also against [S | X | 1]), rows in (t, q) order
+  float* part = L.part;
+  const bool merged = H % 128 == 0;
+  const int ctas_per_split = (4 * H / 128) * (H / 128);
+  const int splits = merged ? (int)max(1ll, min((long long)min(WGRAD_SPLITS, cdiv(148, ctas_per_split)), rowsP / 512))
+                            : (int)max(1ll, min((long long)WGRAD_SPLITS, rowsP / 512));
+  float* pB = part;                                          // [splits][2H][H]  dB_z | dB_r
+  float* pBh = pB + (size_t)splits * 2 * H * H;              // [splits][H][H]   dB_h
+  float* pF = pBh + (size_t)splits * H * H;                  // [splits][4H][32] D^T Feat
+  const long long fsplit = 4ll * H * 32;
+  if (merged) {
+    const int k0[3] = {0, 2 * H, 3 * H}, sb[3] = {0, 1, -1};
+    float* cs[3] = {pB, pBh, nullptr};
+    const float* bs[2] = {L.h, L.hR};
+    const long long lds[2] = {H, H};
+    if (launch_gemm_tn_tma(L.D, 4 * H, rowsP, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, L.Feat, 32, pF, fsplit, st, 0)) return -1;
+  } else {
+    if (launch_gemm_tn_auto(L.D, 4 * H, L.h, H, pB, rowsP, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit, 0)) return -1;
+    if (launch_gemm_tn_auto(L.D + 2 * H, 4 * H, L.hR, H, pBh, rowsP, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit, 0)) return -1;
+    if (launch_gemm_tn_auto(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rowsP, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit, 0)) return -1;
+  }
+  if (launch_reduce_splits(pB, L.dB, 2ll * H * H, splits, 0, st)) return -1;
+  if (launch_reduce_splits(pBh, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
+  k_g_fw_scatter<<<cdiv(4ll * H * 32, 32), dim3(32, 8), 0, st>>>(pF, splits, H, L.dP, L.dcg, L.dM0, L.dc0);
+  REGT_LAUNCHED("k_g_fw_scatter", st);
+  if (a->plan.nseg > 0) {   // dM1[r]: per-region sums over the (node, region) segments
+    if (launch_wgrad_m1_from(a, L, L.D + 3 * (size_t)H, 4ll * H, st, 1, BNp)) return -1;
+  }
+  return launch_chain(a, L, st);
+}
+
 }  // namespace regt

@@ -124,6 +124,8 @@ struct Layout {
 };
 constexpr int TC_MAX_CTAS = 160;
 constexpr int TC_IMG_BYTES = 160 * 1024;
+constexpr int F_IMG_BYTES = 432 * 1024;   // fused 3xTF32 cell (cell_f.cu): 12 ring stages of 32 KB + F-wide weights + constants at H = 128
+bool cell_f_usable(const regt_args* a);   // precision tf32x3, hidden 128 / 64, not the bare TGCN cell
 
 Layout make_layout(const regt_args* a, void* base);
 size_t gemm_nt_scratch_floats(int N, int K);

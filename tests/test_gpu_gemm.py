@@ -146,181 +146,3 @@ def test_gemm_tn_tma_stage_reuse_stress(M, K, N, splits):
         _lib.check(rc, "regt_debug_gemm_tn_tma")
         assert float((Cp.double().sum(0) - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
         assert float((Cp2.double().sum(0) - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max())
-
-
-"The generic 3xTF32 tcgen05 GEMMs (csrc/gemm_tc.cu) against fp64 matmul: fp32-equivalent accuracy
-(1e-5 normwise would already fail a single-pass tf32 product, whose error is ~5e-4)."""
-import pytest
-import torch
-
-from parity_util import relerr
-
-pytestmark = pytest.mark.gpu
-
-
-def _st():
-    return torch.cuda.current_stream().cuda_stream
-
-
-@pytest.mark.parametrize("M,N,K,pad", [(128, 128, 32, 0), (300, 256, 128, 0), (1000, 64, 256, 8), (77, 512, 64, 4), (129, 16, 96, 0),
-                                       (4096, 128, 136, 0)])
-def test_gemm_nt_tf32x3(M, N, K, pad):
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.rand(M, K + pad, generator=g) - 0.5).cuda()
-    Bt = (torch.rand(N, K + pad, generator=g) - 0.5).cuda()
-    C = torch.full((M, N + pad), float("nan"), device="cuda")
-    rc = lib.regt_debug_gemm_nt(A.data_ptr(), K + pad, Bt.data_ptr(), K + pad, C.data_ptr(), N + pad, M, N, K, _st())
-    _lib.check(rc, "regt_debug_gemm_nt")
-    ref = A[:, :K].double() @ Bt[:, :K].double().t()
-    assert relerr(C[:, :N], ref) <= 1e-5
-    if pad:
-        assert torch.isnan(C[:, N:]).all()      # nothing written outside the N columns
-
-
-@pytest.mark.parametrize("M,K,N,splits", [(32, 32, 16, 1), (256, 128, 128, 1), (1000, 256, 64, 4), (5000, 512, 128, 7), (70, 64, 32, 3),
-                                          (4097, 128, 272, 5)])
-def test_gemm_tn_tf32x3(M, K, N, splits):
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.rand(M, K + 4, generator=g) - 0.5).cuda()
-    B = (torch.rand(M, N + 8, generator=g) - 0.5).cuda()
-    Cp = torch.full((splits, K, N), float("nan"), device="cuda")
-    rc = lib.regt_debug_gemm_tn(A.data_ptr(), K + 4, B.data_ptr(), N + 8, Cp.data_ptr(), M, K, N, splits, _st())
-    _lib.check(rc, "regt_debug_gemm_tn")
-    ref = A[:, :K].double().t() @ B[:, :N].double()
-    assert relerr(Cp.double().sum(0), ref) <= 1e-5
-
-
-@pytest.mark.parametrize("M,K,N,splits", [(1000, 256, 128, 4), (3000, 128, 256, 3), (777, 64, 0, 2)])
-def test_gemm_tn_with_second_operand(M, K, N, splits):
-    """one pass over A contracts it with B [M,N] AND with a 32-column plane B2 (the F-wide weight gradients)."""
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.rand(M, K + 4, generator=g) - 0.5).cuda()
-    B = (torch.rand(M, max(N, 4), generator=g) - 0.5).cuda()
-    B2 = (torch.rand(M, 32, generator=g) - 0.5).cuda()
-    Cp = torch.full((splits, K, max(N, 1)), float("nan"), device="cuda")
-    Cp2 = torch.full((splits, K, 32), float("nan"), device="cuda")
-    rc = lib.regt_debug_gemm_tn2(A.data_ptr(), K + 4, B.data_ptr() if N else None, max(N, 4), Cp.data_ptr() if N else None, M, K, N,
-                                 splits, B2.data_ptr(), 32, Cp2.data_ptr(), _st())
-    _lib.check(rc, "regt_debug_gemm_tn2")
-    if N:
-        assert relerr(Cp.double().sum(0), A[:, :K].double().t() @ B[:, :N].double()) <= 1e-5
-    assert relerr(Cp2.double().sum(0), A[:, :K].double().t() @ B2.double()) <= 1e-5
-
-
-# ---- TMA-fed second generation (csrc/gemm_tma.cu): same contracts ----------------------------------------------
-
-@pytest.mark.parametrize("M,N,K,pad", [(128, 128, 32, 0), (300, 256, 128, 0), (1000, 64, 256, 8), (640, 512, 64, 4), (129, 16, 96, 0),
-                                       (4096, 128, 136, 0), (50000, 128, 128, 0), (20011, 64, 64, 0), (30000, 256, 256, 0)])
-def test_gemm_nt_tma(M, N, K, pad):
-    """resident weights (N, K <= 128), streamed weights, ragged M / N / K tails, many tiles per CTA (stage-ring wrap)."""
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.rand(M, K + pad, generator=g) - 0.5).cuda()
-    Bt = (torch.rand(N, K + pad, generator=g) - 0.5).cuda()
-    C = torch.full((M, N + pad), float("nan"), device="cuda")
-    scratch = torch.empty(2 * ((N + 127) // 128 * 128) * ((K + 31) // 32 * 32), device="cuda")
-    rc = lib.regt_debug_gemm_nt_tma(A.data_ptr(), K + pad, Bt.data_ptr(), K + pad, C.data_ptr(), N + pad, M, N, K,
-                                    scratch.data_ptr(), _st())
-    _lib.check(rc, "regt_debug_gemm_nt_tma")
-    ref = A[:, :K].double() @ Bt[:, :K].double().t()
-    assert relerr(C[:, :N], ref) <= 1e-5
-    if pad:
-        assert torch.isnan(C[:, N:]).all()
-
-
-@pytest.mark.parametrize("M,K,N,splits", [(256, 128, 128, 1), (1000, 256, 64, 4), (5000, 512, 128, 7), (70, 64, 32, 3),
-                                          (4097, 128, 288, 5), (777, 64, 0, 2), (40000, 128, 128, 37)])
-def test_gemm_tn_tma(M, K, N, splits):
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.rand(M, K + 4, generator=g) - 0.5).cuda()
-    B = (torch.rand(M, max(N, 4) + 8, generator=g) - 0.5).cuda()
-    B2 = (torch.rand(M, 32, generator=g) - 0.5).cuda()
-    Cp = torch.full((splits, K, max(N, 1)), float("nan"), device="cuda")
-    Cp2 = torch.full((splits, K, 32), float("nan"), device="cuda")
-    rc = lib.regt_debug_gemm_tn_tma(A.data_ptr(), K + 4, B.data_ptr() if N else None, max(N, 4) + 8, Cp.data_ptr() if N else None, M, K, N,
-                                    splits, B2.data_ptr(), 32, Cp2.data_ptr(), _st())
-    _lib.check(rc, "regt_debug_gemm_tn_tma")
-    if N:
-        assert relerr(Cp.double().sum(0), A[:, :K].double().t() @ B[:, :N].double()) <= 1e-5
-    assert relerr(Cp2.double().sum(0), A[:, :K].double().t() @ B2.double()) <= 1e-5
-
-
-@pytest.mark.parametrize("M,H,splits", [(3000, 128, 5), (20000, 256, 10), (40000, 128, 37)])
-def test_gemm_tn_multi_segment(M, H, splits):
-    """the cell backward's single launch: D [M, 4H] against h (z | r blocks), h*R (h~ block) and the feature plane (all blocks)."""
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + H)
-    D = (torch.rand(M, 4 * H, generator=g) - 0.5).cuda()
-    h = (torch.rand(M, H, generator=g) - 0.5).cuda()
-    hR = (torch.rand(M, H, generator=g) - 0.5).cuda()
-    F = (torch.rand(M, 32, generator=g) - 0.5).cuda()
-    C0 = torch.full((splits, 2 * H, H), float("nan"), device="cuda")
-    C1 = torch.full((splits, H, H), float("nan"), device="cuda")
-    C2 = torch.full((splits, 4 * H, 32), float("nan"), device="cuda")
-    rc = lib.regt_debug_gemm_tn_multi(D.data_ptr(), 4 * H, M, H, h.data_ptr(), hR.data_ptr(), C0.data_ptr(), C1.data_ptr(), splits,
-                                      F.data_ptr(), C2.data_ptr(), _st())
-    _lib.check(rc, "regt_debug_gemm_tn_multi")
-    Dd = D.double()
-    assert relerr(C0.double().sum(0), Dd[:, :2 * H].t() @ h.double()) <= 1e-5
-    assert relerr(C1.double().sum(0), Dd[:, 2 * H:3 * H].t() @ hR.double()) <= 1e-5
-    assert relerr(C2.double().sum(0), Dd.t() @ F.double()) <= 1e-5
-
-
-@pytest.mark.parametrize("M,K,N,splits", [(5000, 512, 128, 1), (5000, 512, 128, 3), (20000, 1024, 256, 10)])
-def test_gemm_tn_tma_stage_reuse_stress(M, K, N, splits):
-    """regression: the raw TMA stage must not be released before the converters' shared-memory loads have returned
-    (an mbarrier arrive does not wait for earlier loads: the tail loads of a warp once read the next chunk's bytes,
-    a few times per hundred launches).  Many chunks per CTA, repeated launches, exact per-split check."""
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(1)
-    A = (torch.rand(M, K, generator=g) - 0.5).cuda()
-    B = (torch.rand(M, N, generator=g) - 0.5).cuda()
-    B2 = (torch.rand(M, 32, generator=g) - 0.5).cuda()
-    ref = A.double().t() @ B.double()
-    ref2 = A.double().t() @ B2.double()
-    for _ in range(8):
-        Cp = torch.full((splits, K, N), float("nan"), device="cuda")
-        Cp2 = torch.full((splits, K, 32), float("nan"), device="cuda")
-        rc = lib.regt_debug_gemm_tn_tma(A.data_ptr(), K, B.data_ptr(), N, Cp.data_ptr(), M, K, N, splits, B2.data_ptr(), 32, Cp2.data_ptr(), _st())
-        _lib.check(rc, "regt_debug_gemm_tn_tma")
-        assert float((Cp.double().sum(0) - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
-        assert float((Cp2.double().sum(0) - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max())
-
-
-@pytest.mark.parametrize("M,H,with_aux", [(1000, 128, False), (4099, 128, True), (3000, 256, True), (20000, 64, True)])
-def test_gemm_nt_gate_epilogue(M, H, with_aux):
-    """the gate GEMMs of the tf32x3 forward: sigmoid(h B^T + S W_s + c) computed in the epilogue warps (F-wide term as
-    fp32 FMAs on the accumulator, S from the feature plane), h * R written next to R."""
-    from regt_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(M + H)
-    A = (torch.rand(M, H, generator=g) - 0.5).cuda()
-    W = (torch.rand(H, 2 * H, generator=g) - 0.5).cuda()        # linear_g.weight: the GEMM uses columns H..2H
-    Ws = (torch.rand(8, 2 * H, generator=g) - 0.5).cuda()       # [F][2H] collapsed F-wide weights, this gate = columns H..
-    cb = (torch.rand(2 * H, generator=g) - 0.5).cuda()
-    feat = torch.rand(M, 32, generator=g).cuda()
-    C = torch.full((M, H), float("nan"), device="cuda")
-    C2 = torch.full((M, H), float("nan"), device="cuda")
-    scratch = torch.empty(2 * ((H + 127) // 128 * 128) * H, device="cuda")
-    Bt = W[:, H:]
-    rc = lib.regt_debug_gemm_nt_gate(A.data_ptr(), H, Bt.data_ptr(), 2 * H, C.data_ptr(), H, M, H, H, scratch.data_ptr(),
-                                     Ws[:, H:].data_ptr(), 2 * H, cb[H:].data_ptr(), feat.data_ptr(),
-                                     A.data_ptr() if with_aux else None, H, C2.data_ptr() if with_aux else None, H, _st())
-    _lib.check(rc, "regt_debug_gemm_nt_gate")
-    ref = torch.sigmoid(A.double() @ Bt.double().t() + feat[:, :8].double() @ Ws[:, H:].double() + cb[H:].double())
-    assert relerr(C, ref) <= 1e-5
-    if with_aux:
-        assert relerr(C2, A.double() * ref) <= 1e-5
-    else:
-        assert torch.isnan(C2).all()
