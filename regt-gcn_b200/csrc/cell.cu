@@ -445,6 +445,85 @@ __global__ void __launch_bounds__(128) k_wgrad_m1(const float* __restrict__ dhp,
     }
   }
 }
+// period-major variant (planes of cell_f.cu: row = t*BNp + q, Ut [T][B*nseg][F]): the F values of an item's period are two
+// warp-uniform 128-bit loads (the strided layout above needs 8 scalar loads per period), TT periods in flight
+template <int TT>
+__global__ void __launch_bounds__(128) k_wgrad_m1_pm(const float* __restrict__ dhp, long long ldd, long long d_ts,
+                                                     const float* __restrict__ Ut, long long u_ts,
+                                                     const int32_t* __restrict__ rseg_ptr, const int32_t* __restrict__ rseg_list,
+                                                     const int32_t* __restrict__ seg_node, const int32_t* __restrict__ chunk_ptr,
+                                                     int B, int N, int T, int H, int R, int nseg, int per, float* __restrict__ part) {
+  __shared__ float red[3][32][4 * F + 1];
+  const int c = blockIdx.x;
+  if (c >= chunk_ptr[R]) return;
+  int lo = 0, hi = R;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk_ptr[mid] <= c) lo = mid; else hi = mid;
+  }
+  const int r = lo;
+  const int s0 = rseg_ptr[r];
+  const long long items = (long long)(rseg_ptr[r + 1] - s0) * B;
+  const long long i0 = (long long)(c - chunk_ptr[r]) * per, i1 = min(items, i0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y * 128 + lane * 4;
+  const bool n_ok = n < H;
+  float acc[4][F];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[e][f] = 0.f;
+  for (long long i = i0 + warp; i < i1; i += 4) {
+    const int s = rseg_list[s0 + (int)(i / B)];
+    const int b = (int)(i % B);
+    const int node = seg_node[s];
+    const float4* ur = reinterpret_cast<const float4*>(Ut + ((size_t)b * nseg + s) * F);
+    const float* dr = dhp + ((size_t)b * N + node) * ldd + n;
+    for (int t0 = 0; t0 < T; t0 += TT) {
+      float4 d[TT], ua[TT], ub[TT];
+#pragma unroll
+      for (int k = 0; k < TT; ++k) {
+        const bool ok = t0 + k < T;
+        d[k] = (n_ok && ok) ? __ldg(reinterpret_cast<const float4*>(dr + (size_t)(t0 + k) * d_ts)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* up = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ur) + (size_t)(ok ? t0 + k : 0) * u_ts);
+        ua[k] = __ldg(up);
+        ub[k] = __ldg(up + 1);
+      }
+#pragma unroll
+      for (int k = 0; k < TT; ++k) {
+        const float u[F] = {ua[k].x, ua[k].y, ua[k].z, ua[k].w, ub[k].x, ub[k].y, ub[k].z, ub[k].w};
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          acc[0][f] = fmaf(d[k].x, u[f], acc[0][f]);
+          acc[1][f] = fmaf(d[k].y, u[f], acc[1][f]);
+          acc[2][f] = fmaf(d[k].z, u[f], acc[2][f]);
+          acc[3][f] = fmaf(d[k].w, u[f], acc[3][f]);
+        }
+      }
+    }
+  }
+  if (warp > 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < F; ++f) red[warp - 1][lane][e * F + f] = acc[e][f];
+  }
+  __syncthreads();
+  if (warp == 0 && n_ok) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[e][f] += red[w][lane][e * F + f];
+    float* o = part + ((size_t)c * H + n) * F;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      *reinterpret_cast<float4*>(o + e * F) = make_float4(acc[e][0], acc[e][1], acc[e][2], acc[e][3]);
+      *reinterpret_cast<float4*>(o + e * F + 4) = make_float4(acc[e][4], acc[e][5], acc[e][6], acc[e][7]);
+    }
+  }
+}
 // dM1[r][n][f] = sum of the region's chunk partials, in chunk order (zero for a region without segments)
 __global__ void __launch_bounds__(256) k_m1_reduce(const float* __restrict__ part, const int32_t* __restrict__ chunk_ptr, int HF,
                                                    float* __restrict__ dM1) {
@@ -633,7 +712,15 @@ int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, 
   REGT_CHECK((size_t)max_chunks * H * F <= L.part_floats, "wgrad_m1: partial buffer too small (%d chunks)", max_chunks);
   k_m1_chunks<<<1, 1024, 0, st>>>(a->plan.rseg_ptr, R, a->B, per, L.m1cp);
   REGT_LAUNCHED("k_m1_chunks", st);
-  if (T % 6 == 0)
+  if (period_major) {
+    const long long u_ts = (long long)a->B * nsg * F;
+    if (T % 6 == 0)
+      k_wgrad_m1_pm<6><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, ldd, BNp * ldd, L.U, u_ts, a->plan.rseg_ptr, a->plan.rseg_list,
+                                                                     a->plan.seg_node, L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
+    else
+      k_wgrad_m1_pm<4><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, ldd, BNp * ldd, L.U, u_ts, a->plan.rseg_ptr, a->plan.rseg_list,
+                                                                     a->plan.seg_node, L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
+  } else if (T % 6 == 0)
     k_wgrad_m1<6><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, sd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
                                                                 L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
   else

@@ -34,10 +34,19 @@ using namespace tc;
 
 namespace {
 constexpr int F = REGT_F;
-constexpr int NEPI_W = 8;                 // epilogue warps: 4 TMEM lane quarters x 2 column halves
+// 16 epilogue warps = 4 TMEM lane quarters x 4 column groups.  With 8 warps (two per scheduler) the epilogue phases were
+// latency-bound chains -- ncu: 50-60 % of the samples on long-scoreboard stalls, tensor pipe 24 % busy forward / 13 % backward
+// (profiles/r02_cell_f_v1_ncu.md) -- so the thread count doubled (4 warps per scheduler, half the columns per thread).
+constexpr int NEPI_W = 16;
+// Register split (setmaxnreg): the launch gives every warp the same count -- 96 at 640 threads (5 warps per scheduler
+// partition x 96 x 32 <= 16 K registers) -- which spills in the epilogue threads.  The fifth warpgroup (MMA issuer, weight
+// producer, two idle warps) drops to REGS_AUX and each epilogue warp grows to REGS_EPI: 4 x 112 + 48 = 496 <= 512 per partition.
+constexpr int REGS_EPI = 112, REGS_AUX = 48;
+__device__ __forceinline__ void regs_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI)); }
+__device__ __forceinline__ void regs_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX)); }
 constexpr int W_MMA = NEPI_W;             // issues every tcgen05.mma (one elected lane), owns the TMEM allocation
-// warp NEPI_W + 1: weight-stage producer (bulk copies)
-constexpr int NTHR = (NEPI_W + 2) * 32;
+constexpr int W_PROD = NEPI_W + 1;        // weight-stage producer (bulk copies); warps NEPI_W + 2, + 3 only complete the warpgroup
+constexpr int NTHR = (NEPI_W + 4) * 32;
 constexpr int SMEM_MAX = 227 * 1024;
 
 template <int HH>
@@ -54,11 +63,12 @@ struct FCfg {
   static constexpr int TAIL = SW_IMG + C_FLOATS * 4;  // resident part of the image (copied once per CTA)
   static constexpr int IMG = RING_IMG + TAIL;
   static constexpr int S_TILE = 2 * TC_ROWS * 16;     // A operand of the F-wide part: S_t (8 tf32) per row, chunk tile
-  static constexpr int FIXED = ((TAIL + 1023) & ~1023) + 2 * S_TILE;
-  static constexpr int NS_FIT = (SMEM_MAX - 1024 - FIXED) / STAGE;
+  static constexpr int FIXED = ((TAIL + 1023) & ~1023) + 2 * S_TILE + 4 * 8 * HH * 4;   // + M1 cache (M1C, declared below)
+  static constexpr int NS_FIT = (SMEM_MAX - 2048 - FIXED) / STAGE;
   static constexpr int NS = NS_FIT < 2 * NSTEP ? NS_FIT : 2 * NSTEP;   // ring depth
   static constexpr int SMEM = 1024 + NS * STAGE + FIXED;
-  static constexpr int CWF = HH / 2;                  // columns per epilogue thread
+  static constexpr int CWF = HH / 4;                  // columns per epilogue thread
+  static constexpr int M1C = 4 * REGT_F * HH * 4;     // bytes of the 4-slot cache of per-region M1 blocks
   static constexpr int TCOLS = 4 * HH;                // TMEM columns: A hi | A lo | acc0 | acc1
   static_assert(HH % 32 == 0 && TCOLS <= 512 && NS >= 3, "unsupported hidden width");
 };
@@ -156,8 +166,35 @@ __device__ __forceinline__ void load_feats(const FArgs& a, const Row& ri, int t,
 }
 // h[16] for columns [c, c+16) of one row at period t: the regional combine on the F-wide features
 // (models/RegionalTemporalGCN.py:136-143 collapsed: X_t M0 + sum_seg U_seg,t M1[region] + c0, leaky_relu)
+// per-CTA cache of the M1 blocks of the regions a tile touches (shared memory, 4 direct-mapped slots keyed by region & 3):
+// rows of a 128-row tile lie in one or two consecutive regions, so every lookup hits; anything else (a node in several
+// regional lists, the random decomposition) falls back to the global copy
+struct M1Cache {
+  const float* data;      // [4][F][HH]
+  const int* tag;         // [4] region held by the slot, -1 = empty
+};
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// called by ALL epilogue threads at the first period of an item, with the row's first regional segment (or -1)
 template <int HH>
-__device__ __forceinline__ void h16(const FArgs& a, const float* consts, const Row& ri, const Feats& f, int t, int c, float (&h)[16]) {
+__device__ __forceinline__ void m1_cache_fill(const FArgs& a, const Row& ri, float* data, int* tag, int etid) {
+  constexpr int NEPI = NEPI_W * 32;
+  if (a.mode != REGT_MODE_REGIONAL && a.nseg == 0) return;
+  if (ri.s1 > ri.s0) {
+    const int reg = a.seg_reg[ri.s0];
+    tag[reg & 3] = reg;                 // racy on purpose: any row of the slot may win, the copy below uses the winner
+  }
+  named_bar(1, NEPI);
+  constexpr int SLOT4 = F * HH / 4;     // float4 per slot
+  for (int i = etid; i < 4 * SLOT4; i += NEPI) {
+    const int slot = i / SLOT4, reg = tag[slot];
+    if (reg >= 0)
+      reinterpret_cast<float4*>(data)[i] = __ldg(reinterpret_cast<const float4*>(a.M1t) + (size_t)reg * SLOT4 + (i - slot * SLOT4));
+  }
+  named_bar(1, NEPI);
+}
+template <int HH>
+__device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M1Cache& mc, const Row& ri, const Feats& f, int t, int c,
+                                    float (&h)[16]) {
   using C = FCfg<HH>;
 #pragma unroll
   for (int i = 0; i < 16; ++i) h[i] = consts[C::C_C0 + c + i];
@@ -179,12 +216,13 @@ __device__ __forceinline__ void h16(const FArgs& a, const float* consts, const R
     } else {   // a node that appears in several regional lists (random decomposition)
       load8(a.Ut + (((size_t)t * a.Bsz + ri.b) * a.nseg + s) * F, uv, 1.f);
     }
-    if (reg == 0) {
+    if (mc.tag[reg & 3] == reg) {
+      const float* m = mc.data + (reg & 3) * F * HH + c;
 #pragma unroll
       for (int k = 0; k < F; ++k) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(consts + C::C_M1 + k * HH + c + i);
+          const float4 w = *reinterpret_cast<const float4*>(m + k * HH + i);
           h[i] = fmaf(uv[k], w.x, h[i]); h[i + 1] = fmaf(uv[k], w.y, h[i + 1]);
           h[i + 2] = fmaf(uv[k], w.z, h[i + 2]); h[i + 3] = fmaf(uv[k], w.w, h[i + 3]);
         }
@@ -275,8 +313,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
   uint8_t* ring = sm;
   uint8_t* tail = ring + C::NS * C::STAGE;                    // S-part weights | constants
   uint8_t* stile = tail + ((C::TAIL + 1023) & ~1023);         // S_t operand tile (hi | lo)
+  float* m1data = reinterpret_cast<float*>(stile + 2 * C::S_TILE);
   __shared__ uint64_t bar_full[C::NS], bar_empty[C::NS], bar_tail, bar_a, bar_z, bar_r, bar_a2, bar_c, bar_cfree;
   __shared__ uint32_t tmem_base_s;
+  __shared__ int m1tag[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = (a.nqt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int S = n_items * a.T;
@@ -293,6 +333,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     mbar_init(&bar_a2, NEPI_W * 32);
     mbar_init(&bar_c, 1);
     mbar_init(&bar_cfree, NEPI_W * 32);
+    m1tag[0] = m1tag[1] = m1tag[2] = m1tag[3] = -1;
     fence_barrier_init();
     mbar_arrive_expect_tx(&bar_tail, C::TAIL);
     for (int o = 0; o < C::TAIL; o += 16384) bulk_g2s(tail + o, a.img + C::RING_IMG + o, min(16384, C::TAIL - o), &bar_tail);
@@ -304,6 +345,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(tail + C::SW_IMG);
 
+  if (warp < NEPI_W) regs_grow(); else regs_shrink();
   if (warp < NEPI_W) {
     // ================= epilogue threads: thread = (row r = TMEM lane, CWF columns) =================
     mbar_wait(&bar_tail, 0);
@@ -315,11 +357,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 #pragma unroll
     for (int j = 0; j < CWF; ++j) acc[j] = 0.f;
     Row ri;
+    const M1Cache mc{m1data, m1tag};
     // P(s): h of step s -> TMEM A, S_t tile -> smem, then bar_a
     auto P = [&](int s) {
       const int k = s / a.T, t = s - k * a.T;
       const int qt = (int)blockIdx.x + k * (int)gridDim.x;
-      if (t == 0) ri.set(a, qt, r);
+      if (t == 0) {
+        ri.set(a, qt, r);
+        // every epilogue thread has finished the previous item's last P before any of them gets here (bar_a2 / bar_c chain)
+        m1_cache_fill<HH>(a, ri, m1data, m1tag, tid);
+      }
       Feats f;
       load_feats(a, ri, t, f);
       if (ch == 0) {   // the F-wide gate operand S_t of this row: two 16-byte chunks, hi | lo
@@ -341,7 +388,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 #pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
         float h[16];
-        h16<HH>(a, consts, ri, f, t, c0 + j, h);
+        h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
         put_a16<HH>(tl, c0 + j, h);
       }
       tmem_st_wait();
@@ -456,7 +503,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
       __syncwarp();
     }
     tc_fence_before();
-  } else if (lane == 0) {
+  } else if (warp == W_PROD && lane == 0) {
     produce<HH>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
   }
   __syncthreads();
@@ -466,23 +513,114 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 // ------------------------------------------------------------------------------------------
 // backward (data gradients; the weight gradients are row contractions over what this kernel writes)
 // ------------------------------------------------------------------------------------------
+// TMEM gives every epilogue thread one ROW (lane) of the tile, but the row-major arrays the weight-gradient contraction
+// reads (D [.][4H], h, h*R) and the head's G want the lanes of a warp along the COLUMNS: a warp-wide 16-byte access with a
+// row per lane touches 32 different 128-byte lines (32 LSU wavefronts, half-written 32-byte sectors that L2 has to fill
+// from DRAM).  Every such access therefore goes through a per-warp staging tile in shared memory, [32 rows][16 + 4 floats]:
+// row-per-lane on one side, 8 rows x 64 bytes per instruction on the global side (first version without it: 262 ms per
+// step at config 5 for this kernel, 65 us per (tile, period)).
+constexpr int STG_LD = 20;                          // floats per staged row (16 + 4 pad: conflict-free 128-bit phases)
+constexpr int STG_BYTES = 32 * STG_LD * 4;          // per warp
+// this lane's 16 values -> global [32 rows][16 cols] block at base (row pitch ld floats)
+__device__ __forceinline__ void stage_store(float* stg, int lane, float* base, long long ld, const float (&v)[16]) {
+  float4* mine = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = k * 8 + (lane >> 2), c4 = lane & 3;
+    *reinterpret_cast<float4*>(base + (size_t)row * ld + c4 * 4) = *reinterpret_cast<const float4*>(stg + row * STG_LD + c4 * 4);
+  }
+  __syncwarp();
+}
+// global [32 rows][16 cols] block -> this lane's 16 values (row = lane)
+__device__ __forceinline__ void stage_load(float* stg, int lane, const float* base, long long ld, float (&v)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = k * 8 + (lane >> 2), c4 = lane & 3;
+    *reinterpret_cast<float4*>(stg + row * STG_LD + c4 * 4) = ld_own4(base + (size_t)row * ld + c4 * 4);
+  }
+  __syncwarp();
+  const float4* mine = reinterpret_cast<const float4*>(stg + lane * STG_LD);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 x = mine[i];
+    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+  }
+  __syncwarp();
+}
+
+template <int HH>
+struct BCfg {   // shared-memory plan of the backward: ring | resident tail | staging tiles
+  using C = FCfg<HH>;
+  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + NEPI_W * STG_BYTES + C::M1C;
+  static constexpr int NS_FIT = (SMEM_MAX - 4096 - FIXED) / C::STAGE;
+  static constexpr int NS = NS_FIT < 2 * C::NSTEP ? NS_FIT : 2 * C::NSTEP;
+  static constexpr int SMEM = 1024 + NS * C::STAGE + FIXED;
+  static_assert(NS >= 3, "backward ring too shallow");
+};
+
+template <int HH, int NS>
+__device__ __forceinline__ void mma_block_n(uint32_t tmem, uint32_t acc_col, uint32_t ring0, uint64_t* bar_full, uint64_t* bar_empty,
+                                            long long& gs, int lane, bool accumulate) {
+  using C = FCfg<HH>;
+  const uint32_t idesc = make_idesc(FMT_TF32, 128, HH, 0, 0);
+#pragma unroll 1
+  for (int kc = 0; kc < C::NCH; ++kc, ++gs) {
+    const int st = (int)(gs % NS);
+    mbar_wait(&bar_full[st], (uint32_t)((gs / NS) & 1));
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t bt = ring0 + st * C::STAGE;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const uint32_t ap = tmem + (p == 1 ? HH : 0) + kc * 32, bp = bt + (p == 2 ? C::TILE : 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ts_tf32(tmem + acc_col, ap + 8 * k, make_desc(bp + k * 32, 16, 1024, LAYOUT_SW128), idesc,
+                       (accumulate || kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_empty[st]);
+    }
+    __syncwarp();
+  }
+}
+template <int HH, int NS>
+__device__ __forceinline__ void produce_n(const uint8_t* img, uint8_t* ring, uint64_t* bar_full, uint64_t* bar_empty, long long total) {
+  using C = FCfg<HH>;
+  for (long long gs = 0; gs < total; ++gs) {
+    const int st = (int)(gs % NS);
+    if (gs >= NS) mbar_wait(&bar_empty[st], (uint32_t)((gs / NS - 1) & 1));
+    mbar_arrive_expect_tx(&bar_full[st], C::STAGE);
+    const uint8_t* src = img + (size_t)(gs % C::NSTEP) * C::STAGE;
+#pragma unroll
+    for (int o = 0; o < C::STAGE; o += 16384) bulk_g2s(ring + (size_t)st * C::STAGE + o, src + o, 16384, &bar_full[st]);
+  }
+}
+
 template <int HH>
 __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   using C = FCfg<HH>;
+  using BC = BCfg<HH>;
   constexpr int CWF = C::CWF;
+  constexpr int NS = BC::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = sm;
-  uint8_t* tail = ring + C::NS * C::STAGE;
-  __shared__ uint64_t bar_full[C::NS], bar_empty[C::NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
+  uint8_t* tail = ring + NS * C::STAGE;
+  float* stg_all = reinterpret_cast<float*>(tail + ((C::TAIL + 1023) & ~1023));
+  float* m1data = stg_all + NEPI_W * (STG_BYTES / 4);
+  __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
   __shared__ uint32_t tmem_base_s;
+  __shared__ int m1tag[4];
   __shared__ float red[NEPI_W][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = (a.nqt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int S = n_items * a.T;
 
   if (tid == 0) {
-    for (int s = 0; s < C::NS; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
@@ -493,6 +631,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
     mbar_init(&bar_2z, 1);
     mbar_init(&bar_ar, NEPI_W * 32);
     mbar_init(&bar_2r, 1);
+    m1tag[0] = m1tag[1] = m1tag[2] = m1tag[3] = -1;
     fence_barrier_init();
     mbar_arrive_expect_tx(&bar_tail, C::TAIL);
     for (int o = 0; o < C::TAIL; o += 16384) bulk_g2s(tail + o, a.img + C::RING_IMG + o, min(16384, C::TAIL - o), &bar_tail);
@@ -505,65 +644,72 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   const uint32_t tmem = tmem_base_s;
   const float* consts = reinterpret_cast<const float*>(tail + C::SW_IMG);
 
+  if (warp < NEPI_W) regs_grow(); else regs_shrink();
   if (warp < NEPI_W) {
     mbar_wait(&bar_tail, 0);
     const int qd = warp & 3, ch = warp >> 2;
     const int r = qd * 32 + lane, c0 = ch * CWF;
+    float* stg = stg_all + warp * (STG_BYTES / 4);
     const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
-    const uint32_t t1c = tl + 2 * HH, t2c = tl + 3 * HH;   // acc1 = dHR (then dHR * R), acc2 = dhg
+    const uint32_t t1c = tl + 2 * HH, t2c = tl + 3 * HH;   // acc1 = dHR (then dHR * R), acc2 = p G Z + dhg
     Row ri;
+    const M1Cache mc{m1data, m1tag};
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       const int k = s / a.T, t = s - k * a.T;
       const int qt = (int)blockIdx.x + k * (int)gridDim.x;
-      if (t == 0) ri.set(a, qt, r);
+      if (t == 0) {
+        ri.set(a, qt, r);
+        m1_cache_fill<HH>(a, ri, m1data, m1tag, tid);   // all threads are past the previous item's E0 (bar_ar / bar_2r chain)
+      }
       const float p = consts[C::C_PROBS + t];
       const size_t toff = ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
       const uint8_t* zt = reinterpret_cast<const uint8_t*>(a.Zp) + toff;
       const uint8_t* rt = reinterpret_cast<const uint8_t*>(a.Rp) + toff;
       const uint8_t* ct = reinterpret_cast<const uint8_t*>(a.Hcp) + toff;
-      const size_t rowp = (size_t)t * a.BNp + (size_t)qt * TC_ROWS + r;
-      float* Dr_ = a.D + rowp * 4 * HH;
-      float* hrow = a.hpl + rowp * HH;
-      float* hRrow = a.hRpl + rowp * HH;
-      const float* grow = a.G + (size_t)(ri.valid ? ri.q : 0) * HH;
-      const float gm = ri.valid ? 1.f : 0.f;     // padded rows of the last tile: zero gradient everywhere
+      // first row of this warp's 32-row group in the row-major (t, q) planes and in G (G is padded to whole tiles)
+      const size_t row0 = (size_t)t * a.BNp + (size_t)qt * TC_ROWS + qd * 32;
+      float* D0 = a.D + row0 * 4 * HH + c0;
+      float* h0 = a.hpl + row0 * HH + c0;
+      float* hR0 = a.hRpl + row0 * HH + c0;
+      const float* G0 = a.G + ((size_t)qt * TC_ROWS + qd * 32) * HH + c0;
       // ---- E0: recompute h; gate gradients from the saved planes ----
       Feats f;
       load_feats(a, ri, t, f);
-      float dz[CWF];
       float dp = 0.f;
       unsigned long long neg = 0ull;             // h <= 0 per column (leaky_relu slope of the regional combine)
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
-        float h[16], dc[16];
-        h16<HH>(a, consts, ri, f, t, c0 + j, h);
+        // register plan (96 per thread): h -> h*R in place, G -> p G Z in place, plus Dz and Dc
+        float h[16], g[16], dc[16], dz[16];
+        h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
+        stage_store(stg, lane, h0 + j, HH, h);
+        stage_load(stg, lane, G0 + j, HH, g);
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           const int c = c0 + j + i;
           const float4 z4 = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c)));
           const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
           const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + piece(r, c)));
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + c));
           const float z[4] = {z4.x, z4.y, z4.z, z4.w}, rg[4] = {r4.x, r4.y, r4.z, r4.w}, hc[4] = {c4.x, c4.y, c4.z, c4.w};
-          const float g[4] = {gm * g4.x, gm * g4.y, gm * g4.z, gm * g4.w};
-          float hr[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float hh = h[i + e];
-            const float gg = p * g[e];                                        // dH' = probs[t] * d out_hidden
-            dp = fmaf(g[e], z[e] * hh + (1.0f - z[e]) * hc[e], dp);
-            dz[j + i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
+            const float gv = ri.valid ? g[i + e] : 0.f;                       // padded rows of the last tile: zero gradient
+            const float gg = p * gv;                                          // dH' = probs[t] * d out_hidden
+            dp = fmaf(gv, z[e] * hh + (1.0f - z[e]) * hc[e], dp);
+            dz[i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
             dc[i + e] = gg * (1.0f - z[e]) * (1.0f - hc[e] * hc[e]);
-            hr[e] = hh * rg[e];
+            g[i + e] = gg * z[e];
+            h[i + e] = hh * rg[e];
             if (!(hh > 0.f)) neg |= 1ull << (j + i + e);
           }
-          *reinterpret_cast<float4*>(Dr_ + c) = make_float4(dz[j + i], dz[j + i + 1], dz[j + i + 2], dz[j + i + 3]);
-          *reinterpret_cast<float4*>(Dr_ + 2 * HH + c) = make_float4(dc[i], dc[i + 1], dc[i + 2], dc[i + 3]);
-          *reinterpret_cast<float4*>(hrow + c) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
-          *reinterpret_cast<float4*>(hRrow + c) = make_float4(hr[0], hr[1], hr[2], hr[3]);
         }
         put_a16<HH>(tl, c0 + j, dc);
+        st_f32x16(t2c + c0 + j, g);               // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
+        stage_store(stg, lane, D0 + 2 * HH + j, 4 * HH, dc);
+        stage_store(stg, lane, D0 + j, 4 * HH, dz);
+        stage_store(stg, lane, hR0 + j, HH, h);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -572,76 +718,65 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
       if (lane == 0) red[warp][t] += dp;
-      // ---- M1 done (dHR in acc1): Dz -> A, M2z starts ----
+      // ---- M1 done (dHR in acc1): Dz (re-read from the D plane this warp just wrote: L2) -> A, M2z starts ----
       mbar_wait(&bar_1, ph);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+        stage_load(stg, lane, D0 + j, 4 * HH, v);
         put_a16<HH>(tl, c0 + j, v);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_az);
-      // ---- E1 (under M2z): Dr = dHR h R (1-R) (registers, reusing dz), t1 = dHR R -> acc1 in place ----
-#pragma unroll
+      // ---- E1 (under M2z): Dr = dHR h R (1-R) -> D plane, t1 = dHR R -> acc1 in place ----
+#pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
-        float v[16];
+        float v[16], hh[16], dr[16];
         tmem_ld16(t1c + c0 + j, v);
+        stage_load(stg, lane, h0 + j, HH, hh);     // written by this warp in E0 (stage_store ends with __syncwarp)
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const int c = c0 + j + i;
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
-          const float4 h4 = ld_own4(hrow + c);     // this thread's own store above
-          const float rg[4] = {r4.x, r4.y, r4.z, r4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c0 + j + i)));
+          const float rg[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            dz[j + i + e] = v[i + e] * hh[e] * rg[e] * (1.0f - rg[e]);
+            dr[i + e] = v[i + e] * hh[i + e] * rg[e] * (1.0f - rg[e]);
             v[i + e] *= rg[e];
           }
-          *reinterpret_cast<float4*>(Dr_ + HH + c) = make_float4(dz[j + i], dz[j + i + 1], dz[j + i + 2], dz[j + i + 3]);
         }
         st_f32x16(t1c + c0 + j, v);
+        stage_store(stg, lane, D0 + HH + j, 4 * HH, dr);
       }
       tmem_st_wait();
       // ---- M2z done (A free): Dr -> A, M2r ----
       mbar_wait(&bar_2z, ph);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+        stage_load(stg, lane, D0 + HH + j, 4 * HH, v);
         put_a16<HH>(tl, c0 + j, v);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_ar);
-      // ---- E2: d h_pre = act'(h) (p G Z + dHR R + dhg) ----
+      // ---- E2: d h_pre = act'(h) (p G Z + dhg + dHR R) ----
       mbar_wait(&bar_2r, ph);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
         float v[16], u[16];
         tmem_ld16(t2c + c0 + j, v);
         tmem_ld16(t1c + c0 + j, u);
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const int c = c0 + j + i;
-          const float4 z4 = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c)));
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + c));
-          const float z[4] = {z4.x, z4.y, z4.z, z4.w}, g[4] = {gm * g4.x, gm * g4.y, gm * g4.z, gm * g4.w};
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float d = fmaf(p * g[e], z[e], u[i + e]) + v[i + e];
-            if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i + e)) & 1ull)) d *= 0.01f;
-            o[e] = d;
-          }
-          *reinterpret_cast<float4*>(Dr_ + 3 * HH + c) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 16; ++i) {
+          float d = v[i] + u[i];
+          if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i)) & 1ull)) d *= 0.01f;
+          v[i] = d;
         }
+        stage_store(stg, lane, D0 + 3 * HH + j, 4 * HH, v);
       }
       tc_fence_before();
     }
@@ -652,23 +787,23 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       const uint32_t ph = s & 1;
       mbar_wait(&bar_a, ph);       // also: E2 of the previous step has read acc1 / acc2 (program order of the epilogue threads)
       tc_fence_after();
-      mma_block<HH>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false);     // dHR = Dc . B_h
+      mma_block_n<HH, NS>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false);     // dHR = Dc . B_h
       if (lane == 0) umma_commit(&bar_1);
       __syncwarp();
       mbar_wait(&bar_az, ph);
       tc_fence_after();
-      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false);     // dhg = Dz . B_z
+      mma_block_n<HH, NS>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, true);      // acc2 = p G Z + Dz . B_z
       if (lane == 0) umma_commit(&bar_2z);
       __syncwarp();
       mbar_wait(&bar_ar, ph);
       tc_fence_after();
-      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, true);      // dhg += Dr . B_r
+      mma_block_n<HH, NS>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, true);      // acc2 += Dr . B_r
       if (lane == 0) umma_commit(&bar_2r);
       __syncwarp();
     }
     tc_fence_before();
-  } else if (lane == 0) {
-    produce<HH>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
+  } else if (warp == W_PROD && lane == 0) {
+    produce_n<HH, NS>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
   }
   __syncthreads();
   if (tid < a.T) {
@@ -805,8 +940,8 @@ int run_bwd_kernel(const regt_args* a, const Layout& L, cudaStream_t st, int* gr
   k.img = L.tc_img_b;
   const int grid = min(num_sms_f(), k.nqt);
   REGT_CHECK(grid <= TC_MAX_CTAS, "fused backward: grid %d exceeds the partial buffers", grid);
-  REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd_f<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  k_cell_bwd_f<HH><<<grid, NTHR, C::SMEM, st>>>(k);
+  REGT_CUDA(cudaFuncSetAttribute(k_cell_bwd_f<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<HH>::SMEM));
+  k_cell_bwd_f<HH><<<grid, NTHR, BCfg<HH>::SMEM, st>>>(k);
   REGT_LAUNCHED("k_cell_bwd_f", st);
   *grid_out = grid;
   return 0;

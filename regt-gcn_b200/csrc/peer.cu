@@ -192,7 +192,9 @@ using namespace regt;
 // ---- communication region: [ 64 KiB flags + counters | data: n floats | scratch: n floats ] ---------------------------
 extern "C" size_t regt_comm_region_bytes(int64_t n_floats) {
   const size_t n = ((size_t)n_floats + 3) / 4 * 4;
-  size_t bytes = PEER_FLAG_BYTES + 2 * align_up(n * sizeof(float), 256);
+  // scratch holds world * ceil(n4 / world) float4 slots: up to (world - 1) slots more than n4 when world does not divide n4
+  // (world sizes 3, 5, 6, 7), so it is sized for the worst case of PEER_MAXW ranks
+  size_t bytes = PEER_FLAG_BYTES + align_up(n * sizeof(float), 256) + align_up((n + 4 * PEER_MAXW) * sizeof(float), 256);
   if ((long long)n <= PEER_LL_MAX) bytes += 2 * PEER_MAXW * n * sizeof(unsigned long long);   // push-path receive slots
   return bytes;
 }
@@ -261,7 +263,8 @@ extern "C" int regt_peer_allreduce_f32(void* const* regions, int32_t rank, int32
   }
   if ((long long)n <= PEER_LL_MAX && !force_pull) {
     for (int r = 0; r < world; ++r)
-      a.slots[r] = (unsigned long long*)((char*)regions[r] + PEER_FLAG_BYTES + 2 * align_up(n * sizeof(float), 256));
+      a.slots[r] = (unsigned long long*)((char*)regions[r] + PEER_FLAG_BYTES + align_up(n * sizeof(float), 256) +
+                                         align_up((n + 4 * PEER_MAXW) * sizeof(float), 256));
     a.counter += PEER_MAXB;   // the push kernel's blocks keep their own epochs (its grid differs from the pull kernel's)
     const int blocks = (int)((n / 2 + PEER_THREADS - 1) / PEER_THREADS);
     k_peer_allreduce_ll<<<blocks, PEER_THREADS, 0, (cudaStream_t)stream>>>(a);

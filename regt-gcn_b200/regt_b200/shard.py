@@ -360,7 +360,8 @@ class GradExchange:
         hi = lo + self.flat.numel() * self.flat.element_size()
         for i, p in enumerate(self.params):
             g = p.grad
-            if g is None or not (lo <= g.data_ptr() < hi):
+            # None is fine: nothing was accumulated since zero_grad(set_to_none=True); fused_step re-attaches before it writes
+            if g is not None and not (lo <= g.data_ptr() < hi):
                 raise RuntimeError(
                     f"regt_b200: the gradient of parameter #{i} {tuple(p.shape)} is not a view of the exchange buffer any more "
                     "(optimizer.zero_grad(set_to_none=True) or another flat optimizer rebound .grad): the all-reduce would sum a "

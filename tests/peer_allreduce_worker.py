@@ -19,7 +19,9 @@ def main(rank, world, port):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from regt_b200 import shard as S
-        for n in (37_000, 4, 1_000_003 // 4 * 4 + 4):      # one block, a sliver, many blocks with a grid-stride tail
+        # one block, a sliver, many blocks with a grid-stride tail, and a two-stage size whose float4 count (65 552) is not
+        # divisible by 3, 5, 6 or 7 ranks: the last rank's reduce-scatter slot then extends past n floats of scratch
+        for n in (37_000, 4, 1_000_003 // 4 * 4 + 4, 262_208):
             region = S.PeerRegion(n, dev, rank, world)
             g = torch.Generator(device="cpu").manual_seed(1000 * n % 9973 + rank)
             every = torch.empty(world, n, device=dev)
@@ -56,6 +58,8 @@ def main(rank, world, port):
             assert torch.equal(region.data, ref), f"rank {rank} n={n}: graph replay differs"
             assert region.error() == 0
             dist.barrier()
+            region.close()                                   # unmaps the peers' regions, frees the own one
+            dist.barrier()
         # the flat gradient buffer of a model rides the same path
         lin = torch.nn.Linear(64, 64).to(dev)
         ex = S.GradExchange(list(lin.parameters()), world)
@@ -66,7 +70,16 @@ def main(rank, world, port):
         torch.cuda.synchronize()
         tot = world * (world + 1) / 2
         assert float(loss) == tot + 2.0 * world and float(lin.weight.grad.min()) == tot == float(lin.bias.grad.max())
-        dist.barrier()
+        # something rebinds .grad to a tensor of its own: sync() must refuse to all-reduce a buffer nobody writes into
+        lin.weight.grad = torch.zeros_like(lin.weight)
+        try:
+            ex.sync()
+            raise AssertionError("sync() accepted a detached gradient")
+        except RuntimeError as e:
+            assert "exchange buffer" in str(e)
+        ex.attach(lin.weight)
+        ex.sync()
+        ex.close()
     finally:
         dist.destroy_process_group()
 

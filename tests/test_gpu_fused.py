@@ -1,0 +1,195 @@
+"""The fused 3xTF32 cell (csrc/cell_f.cu, hidden 128 / 64) against the fp64 oracle, A/B against the GEMM-by-GEMM path of
+cell_g.cu (REGT_UNFUSED=1), and the round-2 boundary behaviour: reference call pattern (run.py:115-120,170-192), plan
+cache by content, optimizer / exchange ownership of the flat gradient buffer, dead parameters left alone."""
+import copy
+import os
+
+import pytest
+import torch
+
+from parity_util import W, build_cuda, is_dead, oracle_step, relerr, to_dev, twin_limits
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernels_of_one_step(m, x, y, g):
+    from regt_b200 import _lib
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    lib.regt_profile(1, torch.cuda.current_stream().cuda_stream)
+    res = m.fused_step(x, y, *g)
+    torch.cuda.synchronize()
+    names = {n for n, _ in _lib.profile_read()}
+    lib.regt_profile(0, None)
+    return res, names
+
+
+def _cases():
+    return [
+        # several tiles per CTA (165 tiles > 148 SMs), five regions, rows of a tile in two regions / two snapshots
+        (W.tiny_workload("RegionalTemporalGCN", N=700, T=4, H=128, O=4, R=5, B=30, seed=9), 30),
+        # adversarial lists: a node in two regional lists (two segments), self-loops, duplicates, isolated node
+        (W.tiny_workload("RegionalTemporalGCN", N=60, T=12, H=128, O=6, R=3, B=2, seed=8, adversarial=True), 2),
+        (W.tiny_workload("RegionalTemporalGCN", N=23, T=4, H=64, O=3, R=3, B=2, seed=22, adversarial=True), 2),
+        (W.tiny_workload("TemporalGCN", N=150, T=12, H=64, O=12, R=0, B=3, seed=7, k_intra=5), 3),
+        (W.tiny_workload("TemporalGCN", N=19, T=3, H=128, O=2, R=0, B=2, seed=21, adversarial=True), 2),
+    ]
+
+
+@pytest.mark.parametrize("unfused", [False, True], ids=["fused", "unfused"])
+@pytest.mark.parametrize("w,B", _cases(), ids=lambda v: v.name if hasattr(v, "name") else str(v))
+def test_fused_cell_matches_oracle(w, B, unfused, monkeypatch):
+    """forward, loss and every live parameter gradient: 1e-5 normwise, or 4x the error of the oracle's own fp32 twin where
+    that is larger; both code paths under the same bound, and the intended kernels are the ones that ran."""
+    monkeypatch.setenv("REGT_UNFUSED", "1" if unfused else "0")
+    ref = oracle_step(w, B)
+    m = build_cuda(w, ref["state"], precision="tf32x3")
+    x, y = w.inputs(B)
+    (loss, out, hid), names = _kernels_of_one_step(m, x.cuda(), y.cuda(), to_dev(w.graph_args(), "cuda"))
+    assert ("k_cell_fwd_f" in names and "k_cell_bwd_f" in names) == (not unfused), names
+    assert ("k_gemm_nt_tma_ts" in names or "k_gemm_nt_tf32x3" in names) == unfused, names
+    assert relerr(hid, ref["hid"]) <= 1e-5 and relerr(out, ref["out"]) <= 1e-5
+    assert abs(float(loss) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    lim, twin = twin_limits(w, B, ref)
+    for k, g in ref["grads"].items():
+        if not is_dead(w.model, k):
+            e = relerr(m.get_parameter(k).grad, g)
+            assert e <= max(lim[k], 2e-5 if B >= 30 else 1e-5), f"grad {k}: {e:.3e} (fp32 twin {twin[k]:.3e})"
+
+
+def test_fused_cell_autograd_surface():
+    """the reference's call sites use model(...) + loss.backward(): same kernels behind the autograd Function."""
+    w = W.tiny_workload("RegionalTemporalGCN", N=300, T=6, H=128, O=12, R=7, B=2, seed=25, k_intra=4)
+    ref = oracle_step(w, 2)
+    m = build_cuda(w, ref["state"], precision="auto")       # the default: tf32x3 at hidden 128
+    x, y = w.inputs(2)
+    out, hid = m(x.cuda(), *to_dev(w.graph_args(), "cuda"))
+    ((out - y.cuda()) ** 2).mean(dim=(1, 2)).sum().backward()
+    assert relerr(hid, ref["hid"]) <= 1e-5 and relerr(out, ref["out"]) <= 1e-5
+    lim, _ = twin_limits(w, 2, ref)
+    for k, g in ref["grads"].items():
+        if not is_dead(w.model, k):
+            assert relerr(m.get_parameter(k).grad, g) <= lim[k], k
+
+
+def test_reference_call_pattern_run_py():
+    """run.py:115-120,170-192 replayed literally on the TPIMS graph with the scripts' values (scripts/RegionalTemporalGCN.sh:
+    --num_timesteps_in 6 --num_timesteps_out 1): reference constructor and defaults (hidden 256, 5 regions), a state_dict with
+    the checkpoint's 26 keys loaded strict, one [N,8,T] snapshot per call through the 12 positional tensors, snapshot and
+    graph tensors moved with .to(device) every iteration, loss.cpu() per snapshot, gradients accumulated over the epoch."""
+    from models import RegionalTemporalGCN
+    from oracle import regt_oracle as O
+    full, rei, rea, N = W.tpims_graph()
+    T_in, T_out = 6, 1
+    torch.manual_seed(0)
+    ref = O.RegionalTemporalGCN(8, N, T_in, T_out).double()
+    W.init_params_synthetic(ref, 77)
+    state = copy.deepcopy(ref.state_dict())
+    assert len(state) == 26
+    device = torch.device("cuda:0")
+    model = RegionalTemporalGCN(node_features=8, num_nodes=N, periods=T_in, output_dim=T_out).to(device)      # run.py:116
+    model.load_state_dict({k: v.float() for k, v in state.items()})                                         # run.py:141 (strict)
+    g = torch.Generator().manual_seed(5)
+    snaps = [(torch.rand(N, 8, T_in, generator=g), torch.rand(N, T_out, generator=g)) for _ in range(4)]
+    tot_ref = 0.0
+    for x, y in snaps:
+        out, _ = ref(x.double(), full, *rei, *[a.double() for a in rea])
+        loss = torch.mean((out - y.double()) ** 2)
+        loss.backward()
+        tot_ref += float(loss)
+    tot = 0.0
+    for x, y in snaps:
+        xb, yb = x.to(device), y.to(device)                                                                  # run.py:172
+        ei = full.to(device)
+        r_ei = [e.to(device) for e in rei]
+        r_ea = [a.to(device) for a in rea]
+        y_hat, hidden = model(xb, ei, r_ei[0], r_ei[1], r_ei[2], r_ei[3], r_ei[4],
+                              r_ea[0], r_ea[1], r_ea[2], r_ea[3], r_ea[4])                                    # run.py:178-179
+        assert tuple(y_hat.shape) == (N, T_out) and tuple(hidden.shape) == (N, 256)
+        loss = torch.mean((y_hat - yb) ** 2).cpu()                                                           # run.py:180
+        loss.backward()                                                                                      # run.py:190
+        tot += float(loss)
+    assert abs(tot - tot_ref) <= 1e-5 * abs(tot_ref)
+    for k, p in ref.named_parameters():
+        if not is_dead("RegionalTemporalGCN", k):
+            # d_attention: a difference of nearly equal dot products, stated bound 1e-4 (tests/test_gpu_tc.py)
+            assert relerr(model.get_parameter(k).grad, p.grad) <= (1e-4 if k.endswith("_attention") else 1e-5), k
+        else:
+            assert model.get_parameter(k).grad is None, f"dead parameter {k} received a gradient"
+    # new graph tensors every snapshot, one K1 run: the plan cache hit by content
+    from regt_b200 import plan as P
+    assert len(P._CONTENT) >= 1
+
+
+def test_plan_cache_by_content_distinguishes_graphs():
+    from regt_b200 import plan as P
+    w = W.tiny_workload("TemporalGCN", N=40, T=3, H=32, O=2, R=0, B=1, seed=4)
+    ei, ea = w.edge_index.cuda(), w.edge_attr.cuda()
+    p1 = P.get_plan(w.N, ei.device, ei, ea, [ei], [ea])
+    p2 = P.get_plan(w.N, ei.device, ei.clone(), ea.clone(), [ei.clone()], [ea.clone()])
+    assert p2 is p1                                          # same content, different tensors
+    ea2 = ea.clone()
+    ea2[3] += 0.5
+    p3 = P.get_plan(w.N, ei.device, ei.clone(), ea2, [ei.clone()], [ea2])
+    assert p3 is not p1                                      # one weight changed
+    ei2 = ei.clone()
+    ei2[:, [0, 1]] = ei2[:, [1, 0]]                          # two edges swapped: same multiset, different order (CSR eids differ)
+    p4 = P.get_plan(w.N, ei.device, ei2, ea.clone(), [ei2], [ea.clone()])
+    assert p4 is not p1
+
+
+def test_flat_rmsprop_leaves_dead_parameters_alone():
+    """torch.optim.RMSprop skips parameters whose .grad is None (the reference's dead _weight_att* / _bias_att*): with weight
+    decay they must not move (run.py:145 default --decay 1e-4)."""
+    from regt_b200.loop import FlatRMSprop
+    w = W.tiny_workload("RegionalTemporalGCN", N=40, T=3, H=32, O=2, R=4, B=2, seed=5)
+    ref = oracle_step(w, 2)
+    m = build_cuda(w, ref["state"], precision="fp32")
+    dead = m.dead_parameters()
+    assert len(dead) == 4
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    opt = FlatRMSprop(list(m.parameters()), lr=1e-2, weight_decay=0.1, skip=dead)
+    x, y = w.inputs(2)
+    opt.zero_grad()
+    m.fused_step(x.cuda(), y.cuda(), *to_dev(w.graph_args(), "cuda"))
+    opt.step()
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        if is_dead(w.model, k):
+            assert torch.equal(p.detach(), before[k]), f"dead parameter {k} moved"
+        else:
+            assert not torch.equal(p.detach(), before[k]), f"live parameter {k} did not move"
+
+
+def test_gradient_buffer_ownership():
+    """reference-style optimizer.zero_grad() (set_to_none) drops .grad: fused_step re-attaches it to the owner's flat buffer,
+    and a foreign rebinding is refused by sync() / step() instead of silently using a stale buffer."""
+    from regt_b200.loop import FlatRMSprop
+    from regt_b200.shard import GradExchange
+    w = W.tiny_workload("TemporalGCN", N=30, T=3, H=32, O=2, R=0, B=2, seed=3)
+    ref = oracle_step(w, 2)
+    m = build_cuda(w, ref["state"], precision="fp32")
+    params = [p for p in m.parameters() if p.requires_grad]
+    ex = GradExchange(params, 1)
+    x, y = w.inputs(2)
+    g = to_dev(w.graph_args(), "cuda")
+    for p in params:
+        p.grad = None                                        # torch.optim zero_grad(set_to_none=True)
+    m.fused_step(x.cuda(), y.cuda(), *g)
+    lo, hi = ex.flat.data_ptr(), ex.flat.data_ptr() + ex.flat.numel() * 4
+    live = [p for k, p in m.named_parameters() if not is_dead(w.model, k)]
+    assert all(lo <= p.grad.data_ptr() < hi for p in live)
+    ex.sync()
+    for k, gr in ref["grads"].items():
+        if not is_dead(w.model, k):
+            assert relerr(m.get_parameter(k).grad, gr) <= 1e-5, k
+    # an optimizer that steps out of the exchange buffer keeps the views intact
+    opt = FlatRMSprop(params, lr=1e-3, exchange=ex, skip=m.dead_parameters())
+    assert all(lo <= p.grad.data_ptr() < hi for p in live)
+    opt.step()
+    # a foreign rebinding is detected
+    params[0].grad = torch.zeros_like(params[0])
+    with pytest.raises(RuntimeError, match="exchange buffer"):
+        ex.sync()
+    with pytest.raises(RuntimeError, match="flat gradient buffer"):
+        opt.step()

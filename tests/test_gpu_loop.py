@@ -29,18 +29,24 @@ def test_window_gather_bit_exact():
         assert torch.equal(x[b].cpu(), feats[s]) and torch.equal(y[b].cpu(), targ[s])
 
 
+@pytest.mark.parametrize("skip_one", [False, True])
 @pytest.mark.parametrize("wd", [0.0, 0.01])
-def test_flat_rmsprop_matches_torch(wd):
+def test_flat_rmsprop_matches_torch(wd, skip_one):
+    """incl. a parameter that never receives a gradient (torch skips it, weight decay and all: the reference's dead parameters)"""
     from regt_b200.loop import FlatRMSprop
     torch.manual_seed(3)
     ref = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Linear(17, 5))
     mine = copy.deepcopy(ref).cuda()
     opt_ref = torch.optim.RMSprop(ref.parameters(), lr=1e-3, weight_decay=wd)
-    opt = FlatRMSprop(list(mine.parameters()), lr=1e-3, weight_decay=wd)
+    skipped = [list(mine.parameters())[1]] if skip_one else []
+    opt = FlatRMSprop(list(mine.parameters()), lr=1e-3, weight_decay=wd, skip=skipped)
     for it in range(4):
         g = torch.Generator().manual_seed(10 + it)
-        for pr, pm in zip(ref.parameters(), mine.parameters()):
+        for i, (pr, pm) in enumerate(zip(ref.parameters(), mine.parameters())):
             gr = torch.randn(pr.shape, generator=g)
+            if skip_one and i == 1:
+                pr.grad = None
+                continue
             pr.grad = gr.clone()
             pm.grad.copy_(gr)
         opt_ref.step()

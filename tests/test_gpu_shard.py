@@ -118,12 +118,16 @@ def test_two_process_nccl_region_shards(tmp_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_peer_memory_allreduce_bit_exact_and_graph_capturable():
+@pytest.mark.parametrize("world", [0, 3])
+def test_peer_memory_allreduce_bit_exact_and_graph_capturable(world):
     """csrc/peer.cu: the one-kernel NVLink all-reduce sums in rank order (bit-identical to the explicit sum on every
     rank), survives repeated calls (device-side epochs) and CUDA-graph replay, and carries GradExchange's flat buffer."""
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_allreduce_worker.py")
-    world = min(torch.cuda.device_count(), 8)
-    port = 31700 + os.getpid() % 2000
+    if world == 0:
+        world = min(torch.cuda.device_count(), 8)       # every GPU of the box
+    elif torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")               # 3 ranks: a world size that does not divide the buffer
+    port = 31700 + os.getpid() % 2000 + world
     procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), str(port)]) for r in range(world)]
     try:
         for p in procs:
