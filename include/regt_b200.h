@@ -144,7 +144,9 @@ typedef struct regt_args {
                           /*    column indices address (1-hop neighbours owned by other ranks). */
   int32_t loss_nodes;     /* region shards: node count of the loss mean (0 means N), so that   */
                           /*    the per-rank losses and gradients ADD to the full-graph ones    */
-  int32_t _reserved;
+  int32_t inference;      /* 1: forward only, as under torch.no_grad() at run.py:208-216 / predict.py:151-172:    */
+                          /*    the fused kernels save no activations (the workspace shrinks accordingly) and     */
+                          /*    regt_head_backward / regt_cell_backward must not follow                           */
   regt_graph_plan plan;
   const float* x;         /* [B,x_rows,F,T] f32, T innermost (load_dataset.py:456)        */
   const float* y;         /* [B,N,O] or NULL: if set head_forward also writes loss, d_out  */
@@ -241,6 +243,8 @@ int regt_profile_read(char* names, size_t names_len, float* ms, int max_n);
  *   gemm_nt*:  C[M][N]   = A[M][K] . Bt[N][K]^T                       (scratch: 2 * ceil128(N) * ceil32(K) floats)
  *   gemm_tn*:  Cp[z]     = sum over the rows of split z of A[r][:K]^T . B[r][:N]      (+ a second, 32-wide operand B2)
  *   gemm_tn_multi: the four-gate-block form of the cell backward, A = D [M][4H]
+ *   gemm_kt: the same contraction over transposed tiles A^T [ntile][4H][128], B^T [ntile][H][128], F^T [ntile][32][128]
+ *            (what the fused cell backward of cell_f.cu writes); H = 128 or 64
  *   umma_selftest: one 128 x N x K MMA on operand tiles written by CUDA-core threads (fmt 1 = bf16, 2 = tf32)         */
 int regt_debug_gemm_nt(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
                        int32_t N, int32_t K, regt_stream_t stream);
@@ -254,6 +258,8 @@ int regt_debug_gemm_tn_tma(const float* A, int64_t lda, const float* B, int64_t 
                            int32_t N, int32_t splits, const float* B2, int64_t ldb2, float* Cp2, regt_stream_t stream);
 int regt_debug_gemm_tn_multi(const float* A, int64_t lda, int64_t M, int32_t H, const float* B0, const float* B1,
                              float* C0, float* C1, int32_t splits, const float* B2, float* C2, regt_stream_t stream);
+int regt_debug_gemm_kt(const float* AT, int64_t ntile, int32_t H, const float* B0T, const float* B1T, const float* FT,
+                       float* C0, float* C1, float* C2, int32_t splits, regt_stream_t stream);
 int regt_debug_umma_selftest(int fmt, int variant, const float* A, const float* B, float* D, int N, int K,
                              regt_stream_t stream);
 

@@ -36,19 +36,21 @@ Layout make_layout(const regt_args* a, void* base) {
   const bool tcp = a->precision == REGT_PREC_BF16;   // fused tcgen05 kernels (tile-layout planes); tf32x3 uses the fp32 planes
   if (cell_f_usable(a)) {
     // fused 3xTF32 cell (cell_f.cu): three saved planes in tile layout; the backward kernel writes the gate-gradient
-    // blocks D and h, h*R row major in (t, q) order (q padded to whole 128-row tiles) for the weight-gradient contraction
+    // blocks D and h, h*R as TRANSPOSED tiles [T*nqt][cols][128 rows] for the weight-gradient contraction (gemm_kt)
     const size_t nqt = (BN + 127) / 128, rowsP = T * nqt * 128;
+    const bool inf = a->inference != 0;     // forward only: one Z tile per CTA (re-read by its own epilogue), nothing else saved
     L.tc_img_f = c.take<unsigned char>(F_IMG_BYTES);
     L.tc_img_b = c.take<unsigned char>(F_IMG_BYTES);
-    L.Zp = c.take<float>(rowsP * H);
-    L.Rp = c.take<float>(rowsP * H);
-    L.Hcp = c.take<float>(rowsP * H);
+    L.Zp = c.take<float>(inf ? (size_t)TC_MAX_CTAS * 128 * H : rowsP * H);
+    L.Rp = c.take<float>(inf ? 4 : rowsP * H);
+    L.Hcp = c.take<float>(inf ? 4 : rowsP * H);
     L.Xt = c.take<float>(BN * F * T);
-    L.h = c.take<float>(rowsP * H);
-    L.hR = c.take<float>(rowsP * H);
-    L.D = c.take<float>(rowsP * 4 * H);
-    L.Feat = c.take<float>(rowsP * 32);
-    L.tc_dpp = c.take<float>(T * TC_MAX_CTAS + 64);
+    L.h = c.take<float>(inf ? 4 : rowsP * H);
+    L.hR = c.take<float>(inf ? 4 : rowsP * H);
+    L.D = c.take<float>(inf ? 4 : rowsP * 4 * H);
+    L.Feat = c.take<float>(inf ? 4 : nqt * 128 * 32);      // the head's ones column (row major, BNp rows)
+    L.FeatT = c.take<float>(inf ? 4 : rowsP * 32);
+    L.tc_dpp = c.take<float>(2 * (T * TC_MAX_CTAS + 64));   // fp64 attention-gradient partials
   } else if (!tcp) {
     L.h = c.take<float>(rows * H);
     L.Z = c.take<float>(rows * H);
@@ -84,7 +86,7 @@ Layout make_layout(const regt_args* a, void* base) {
   L.dprobs = c.take<float>(T);
   size_t pf = (size_t)3 * WGRAD_SPLITS * H * H;                    // H x H split-K partials
   pf = max(pf, (size_t)WGRAD_SPLITS * 4 * H * 32);                  // F-wide partials ([4H][F+1] fp32 path, [4H][32] tf32x3 GEMM)
-  pf = max(pf, (size_t)3 * H * H + 1024 * 64);                      // tf32x3: packed B^T operands + attention partials
+  pf = max(pf, (size_t)3 * H * H + 2 * 1024 * 64);                     // tf32x3: packed B^T operands + attention partials
   pf = max(pf, (size_t)WGRAD_SPLITS * (3 * H * H + 4 * H * 32));    // tf32x3: H x H and F-wide weight-gradient partials side by side
   pf = max(pf, (size_t)(2048 + R + 2) * H * F);                     // per-region dM1 partials: <= 2048 + R chunks (cell.cu)
   pf = max(pf, (size_t)128 * T);                                    // attention partials
@@ -138,6 +140,7 @@ extern "C" int regt_cell_forward(const regt_args* a) {
 
 extern "C" int regt_cell_backward(const regt_args* a) {
   if (validate(a, "regt_cell_backward")) return -1;
+  REGT_CHECK(!a->inference, "regt_cell_backward: the forward ran with inference=1 (no activations were saved)");
   Layout L = make_layout(a, a->workspace);
   cudaStream_t st = (cudaStream_t)a->stream;
   prof_mark("<begin>", st);
@@ -159,6 +162,7 @@ extern "C" int regt_head_forward(const regt_args* a) {
 
 extern "C" int regt_head_backward(const regt_args* a) {
   if (validate(a, "regt_head_backward")) return -1;
+  REGT_CHECK(!a->inference, "regt_head_backward: the forward ran with inference=1 (no activations were saved)");
   Layout L = make_layout(a, a->workspace);
   prof_mark("<begin>", (cudaStream_t)a->stream);
   return head_backward_fp32(a, L, (cudaStream_t)a->stream);

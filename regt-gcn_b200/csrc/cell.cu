@@ -524,6 +524,71 @@ __global__ void __launch_bounds__(128) k_wgrad_m1_pm(const float* __restrict__ d
     }
   }
 }
+// transposed variant (planes of cell_f.cu v2): dhp lives in D^T tiles [tp][4H][128 rows] (tp = t * nqt + qt), Ut is period
+// major.  Lanes run along the SEGMENTS of a region (= consecutive nodes = consecutive rows of a tile: 128-byte lines of every
+// D^T column), a warp owns NPW gate columns, a thread keeps NPW x F running sums over all its rows and the 32 row lanes
+// are summed once per chunk (butterfly, fixed order).  Chunk = (region, group of bper snapshots): part[chunk][H][F].
+template <int NPW>
+__global__ void __launch_bounds__(512) k_wgrad_m1_kt(const float* __restrict__ DT, int Ktot, int col0, const float* __restrict__ Ut,
+                                                     const int32_t* __restrict__ rseg_ptr, const int32_t* __restrict__ rseg_list,
+                                                     const int32_t* __restrict__ seg_node, int B, int N, int T, int nqt, int nseg,
+                                                     int nbg, int bper, int H, float* __restrict__ part) {
+  const int c = blockIdx.x, r = c / nbg, bg = c - r * nbg;
+  const int b0 = bg * bper, b1 = min(B, b0 + bper);
+  const int s0 = rseg_ptr[r], s1 = rseg_ptr[r + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = warp * NPW;
+  float acc[NPW][F];
+#pragma unroll
+  for (int k = 0; k < NPW; ++k)
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[k][f] = 0.f;
+  if (n0 < H) {
+    for (int b = b0; b < b1; ++b) {
+      for (int si = s0 + lane; si < s1; si += 32) {
+        const int s = __ldg(rseg_list + si);
+        const long long q = (long long)b * N + __ldg(seg_node + s);
+        const int qt = (int)(q >> 7), rr = (int)(q & 127);
+        const float* dcol = DT + ((size_t)qt * Ktot + col0 + n0) * 128 + rr;
+        const float* urow = Ut + ((size_t)b * nseg + s) * F;
+#pragma unroll 2
+        for (int t = 0; t < T; ++t) {
+          const float4 ua = __ldg(reinterpret_cast<const float4*>(urow + (size_t)t * B * nseg * F));
+          const float4 ub = __ldg(reinterpret_cast<const float4*>(urow + (size_t)t * B * nseg * F) + 1);
+          const float u[F] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+          const float* dp = dcol + (size_t)t * nqt * Ktot * 128;
+          float d[NPW];
+#pragma unroll
+          for (int k = 0; k < NPW; ++k) d[k] = __ldg(dp + (size_t)k * 128);
+#pragma unroll
+          for (int k = 0; k < NPW; ++k)
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[k][f] = fmaf(d[k], u[f], acc[k][f]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NPW; ++k)
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      float v = acc[k][f];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      acc[k][f] = v;
+    }
+  if (lane == 0 && n0 < H) {
+    float* o = part + ((size_t)c * H + n0) * F;
+#pragma unroll
+    for (int k = 0; k < NPW; ++k) {
+      *reinterpret_cast<float4*>(o + k * F) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      *reinterpret_cast<float4*>(o + k * F + 4) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+    }
+  }
+}
+__global__ void k_m1_chunks_even(int R, int nbg, int32_t* __restrict__ chunk_ptr) {
+  for (int r = threadIdx.x; r <= R; r += blockDim.x) chunk_ptr[r] = r * nbg;
+}
 // dM1[r][n][f] = sum of the region's chunk partials, in chunk order (zero for a region without segments)
 __global__ void __launch_bounds__(256) k_m1_reduce(const float* __restrict__ part, const int32_t* __restrict__ chunk_ptr, int HF,
                                                    float* __restrict__ dM1) {
@@ -727,6 +792,29 @@ int launch_wgrad_m1_from(const regt_args* a, const Layout& L, const float* dhp, 
     k_wgrad_m1<4><<<dim3(max_chunks, cdiv(H, 128)), 128, 0, st>>>(dhp, sd, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node,
                                                                 L.m1cp, a->B, a->N, T, H, R, a->plan.nseg, per, L.part);
   REGT_LAUNCHED("k_wgrad_m1", st);
+  k_m1_reduce<<<R, 256, 0, st>>>(L.part, L.m1cp, H * F, L.dM1);
+  REGT_LAUNCHED("k_m1_reduce", st);
+  return 0;
+}
+// dM1 from the transposed gate-gradient tiles of the fused backward: DT [T * nqt][Ktot = 4H][128], dhp = columns [3H, 4H)
+int launch_wgrad_m1_kt(const regt_args* a, const Layout& L, cudaStream_t st) {
+  const int H = a->H, T = a->T, R = a->plan.R, B = a->B;
+  REGT_CHECK(H % 16 == 0 && H <= 128, "wgrad_m1_kt: hidden %d not supported", H);
+  const long long BN = (long long)B * a->N;
+  const int nqt = (int)((BN + 127) / 128);
+  int nbg = min(B, max(1, 2048 / max(R, 1)));
+  const int bper = (B + nbg - 1) / nbg;
+  nbg = (B + bper - 1) / bper;
+  REGT_CHECK((size_t)R * nbg * H * F <= L.part_floats, "wgrad_m1_kt: partial buffer too small");
+  k_m1_chunks_even<<<1, 256, 0, st>>>(R, nbg, L.m1cp);
+  REGT_LAUNCHED("k_m1_chunks", st);
+  if (H == 128)
+    k_wgrad_m1_kt<8><<<R * nbg, 512, 0, st>>>(L.D, 4 * H, 3 * H, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node, B, a->N, T,
+                                              nqt, a->plan.nseg, nbg, bper, H, L.part);
+  else
+    k_wgrad_m1_kt<4><<<R * nbg, 512, 0, st>>>(L.D, 4 * H, 3 * H, L.U, a->plan.rseg_ptr, a->plan.rseg_list, a->plan.seg_node, B, a->N, T,
+                                              nqt, a->plan.nseg, nbg, bper, H, L.part);
+  REGT_LAUNCHED("k_wgrad_m1_kt", st);
   k_m1_reduce<<<R, 256, 0, st>>>(L.part, L.m1cp, H * F, L.dM1);
   REGT_LAUNCHED("k_m1_reduce", st);
   return 0;

@@ -29,6 +29,12 @@
 
 #include "cell_tc.cuh"
 
+// build-time switch (tools/build_variants.py, A/B on B200): 1 = h of the next step is computed under the candidate MMAs and
+// waits in registers (32 more live registers per epilogue thread), 0 = computed after them
+#ifndef REGT_F_PRE
+#define REGT_F_PRE 0
+#endif
+
 namespace regt {
 using namespace tc;
 
@@ -40,8 +46,8 @@ constexpr int F = REGT_F;
 constexpr int NEPI_W = 16;
 // Register split (setmaxnreg): the launch gives every warp the same count -- 96 at 640 threads (5 warps per scheduler
 // partition x 96 x 32 <= 16 K registers) -- which spills in the epilogue threads.  The fifth warpgroup (MMA issuer, weight
-// producer, two idle warps) drops to REGS_AUX and each epilogue warp grows to REGS_EPI: 4 x 112 + 48 = 496 <= 512 per partition.
-constexpr int REGS_EPI = 112, REGS_AUX = 48;
+// producer, two idle warps) drops to REGS_AUX and each epilogue warp grows to REGS_EPI: the pool is per CTA: 16 warps x (112 - 96) = 4 warps x (96 - 32).
+constexpr int REGS_EPI = 112, REGS_AUX = 32;
 __device__ __forceinline__ void regs_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI)); }
 __device__ __forceinline__ void regs_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX)); }
 constexpr int W_MMA = NEPI_W;             // issues every tcgen05.mma (one elected lane), owns the TMEM allocation
@@ -81,10 +87,11 @@ struct FArgs {
   const uint8_t* img;
   float *Zp, *Rp, *Hcp;            // saved planes, tile layout [T][nqt][H/4][128][4]
   float* out_hidden;               // [BN][H]
+  int save;                        // 0: forward only -- Z goes to a per-CTA scratch tile (Zp = [grid][128][H]), R and H~ nowhere
   // backward
-  const float* G;                  // [BN][H] gradient wrt out_hidden
-  float *D, *hpl, *hRpl;           // [T*BNp][4H], [T*BNp][H], [T*BNp][H] row major, row = t*BNp + q
-  float* dpp;                      // [grid][T] attention-gradient partials
+  const float* G;                  // gradient wrt out_hidden, tile layout [nqt][H/4][128][4] (the head writes it that way)
+  float *D, *hpl, *hRpl;           // transposed tiles [T*nqt][4H][128], [T*nqt][H][128], [T*nqt][H][128]
+  double* dpp;                     // [grid][T] attention-gradient partials
 };
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(float a) {
@@ -122,6 +129,11 @@ __device__ __forceinline__ void st_f32x16(uint32_t taddr, const float (&v)[16]) 
   tmem_st16(taddr, u);
 }
 
+__device__ __forceinline__ float ld_own1(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 // re-read of a 16-byte piece this thread stored earlier in the kernel (plain coherent load, never the read-only path)
 __device__ __forceinline__ float4 ld_own4(const void* p) {
   float4 v;
@@ -358,25 +370,35 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     for (int j = 0; j < CWF; ++j) acc[j] = 0.f;
     Row ri;
     const M1Cache mc{m1data, m1tag};
-    // P(s): h of step s -> TMEM A, S_t tile -> smem, then bar_a
-    auto P = [&](int s) {
+    // P(s) in two halves: Pcompute (h of step s on the CUDA cores, into registers; runs under the candidate MMAs of step
+    // s - 1) and Pstore (registers -> TMEM A, S_t tile -> smem, bar_a; as soon as those MMAs have released A)
+    float hn[CWF], svn[8];
+    auto Pcompute = [&](int s) {
       const int k = s / a.T, t = s - k * a.T;
       const int qt = (int)blockIdx.x + k * (int)gridDim.x;
       if (t == 0) {
         ri.set(a, qt, r);
-        // every epilogue thread has finished the previous item's last P before any of them gets here (bar_a2 / bar_c chain)
+        // every epilogue thread has finished the previous item's last Pcompute before any of them gets here (bar_a2 chain)
         m1_cache_fill<HH>(a, ri, m1data, m1tag, tid);
       }
       Feats f;
       load_feats(a, ri, t, f);
+      if (ch == 0) load8(a.St + ((size_t)t * a.BN + (ri.valid ? ri.q : 0)) * F, svn, ri.valid ? 1.f : 0.f);
+#pragma unroll
+      for (int j = 0; j < CWF; j += 16) {
+        float h[16];
+        h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hn[j + i] = h[i];
+      }
+    };
+    auto Pstore = [&]() {
       if (ch == 0) {   // the F-wide gate operand S_t of this row: two 16-byte chunks, hi | lo
-        float sv[8];
-        load8(a.St + ((size_t)t * a.BN + (ri.valid ? ri.q : 0)) * F, sv, ri.valid ? 1.f : 0.f);
         float hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          hi[i] = __uint_as_float(tf32_rn_bits(sv[i]));
-          lo[i] = sv[i] - hi[i];
+          hi[i] = __uint_as_float(tf32_rn_bits(svn[i]));
+          lo[i] = svn[i] - hi[i];
         }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -385,26 +407,32 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
         }
         fence_proxy_async();
       }
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float h[16];
-        h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = hn[j + i];
         put_a16<HH>(tl, c0 + j, h);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_a);
     };
-    if (S > 0) P(0);
+    if (S > 0) {
+      Pcompute(0);
+      Pstore();
+    }
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       const int k = s / a.T, t = s - k * a.T;
       const int qt = (int)blockIdx.x + k * (int)gridDim.x;
       const long long q_cur = (long long)qt * TC_ROWS + r;
       const float p = consts[C::C_PROBS + t];
-      uint8_t* zt = reinterpret_cast<uint8_t*>(a.Zp) + ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
-      uint8_t* rt = reinterpret_cast<uint8_t*>(a.Rp) + ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
-      uint8_t* ct = reinterpret_cast<uint8_t*>(a.Hcp) + ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      const size_t toff = ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      // forward only (inference): Z makes its round trip through a per-CTA tile that never leaves L2
+      uint8_t* zt = reinterpret_cast<uint8_t*>(a.Zp) + (a.save ? toff : (size_t)blockIdx.x * (size_t)(TC_ROWS * HH * 4));
+      uint8_t* rt = reinterpret_cast<uint8_t*>(a.Rp) + toff;
+      uint8_t* ct = reinterpret_cast<uint8_t*>(a.Hcp) + toff;
       // ---- E1z: update gate (runs while the r-gate MMAs are in flight) ----
       mbar_wait(&bar_z, ph);
       tc_fence_after();
@@ -435,16 +463,24 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
           h[i] *= v[i];
         }
         put_a16<HH>(tl, c0 + j, h);
+        if (a.save) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(rt + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(rt + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_a2);
-      // ---- candidate GEMM done: A is free -> h of the next step first (its z-gate MMAs start), then E2 under them ----
+#if REGT_F_PRE
+      if (s + 1 < S) Pcompute(s + 1);      // under the candidate MMAs (h of the next step waits in registers)
+#endif
+      // ---- candidate GEMM done: A is free -> h of the next step goes in first (its z-gate MMAs start), then E2 under them ----
       mbar_wait(&bar_c, ph);
       tc_fence_after();
-      if (s + 1 < S) P(s + 1);
+#if !REGT_F_PRE
+      if (s + 1 < S) Pcompute(s + 1);
+#endif
+      if (s + 1 < S) Pstore();
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
@@ -459,7 +495,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
             v[i + e] = hc;
             acc[j + i + e] = fmaf(p * (1.0f - zz[e]), hc, acc[j + i + e]);
           }
-          *reinterpret_cast<float4*>(ct + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          if (a.save) *reinterpret_cast<float4*>(ct + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
       tc_fence_before();
@@ -513,49 +549,19 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 // ------------------------------------------------------------------------------------------
 // backward (data gradients; the weight gradients are row contractions over what this kernel writes)
 // ------------------------------------------------------------------------------------------
-// TMEM gives every epilogue thread one ROW (lane) of the tile, but the row-major arrays the weight-gradient contraction
-// reads (D [.][4H], h, h*R) and the head's G want the lanes of a warp along the COLUMNS: a warp-wide 16-byte access with a
-// row per lane touches 32 different 128-byte lines (32 LSU wavefronts, half-written 32-byte sectors that L2 has to fill
-// from DRAM).  Every such access therefore goes through a per-warp staging tile in shared memory, [32 rows][16 + 4 floats]:
-// row-per-lane on one side, 8 rows x 64 bytes per instruction on the global side (first version without it: 262 ms per
-// step at config 5 for this kernel, 65 us per (tile, period)).
-constexpr int STG_LD = 20;                          // floats per staged row (16 + 4 pad: conflict-free 128-bit phases)
-constexpr int STG_BYTES = 32 * STG_LD * 4;          // per warp
-// this lane's 16 values -> global [32 rows][16 cols] block at base (row pitch ld floats)
-__device__ __forceinline__ void stage_store(float* stg, int lane, float* base, long long ld, const float (&v)[16]) {
-  float4* mine = reinterpret_cast<float4*>(stg + lane * STG_LD);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int row = k * 8 + (lane >> 2), c4 = lane & 3;
-    *reinterpret_cast<float4*>(base + (size_t)row * ld + c4 * 4) = *reinterpret_cast<const float4*>(stg + row * STG_LD + c4 * 4);
-  }
-  __syncwarp();
-}
-// global [32 rows][16 cols] block -> this lane's 16 values (row = lane)
-__device__ __forceinline__ void stage_load(float* stg, int lane, const float* base, long long ld, float (&v)[16]) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int row = k * 8 + (lane >> 2), c4 = lane & 3;
-    *reinterpret_cast<float4*>(stg + row * STG_LD + c4 * 4) = ld_own4(base + (size_t)row * ld + c4 * 4);
-  }
-  __syncwarp();
-  const float4* mine = reinterpret_cast<const float4*>(stg + lane * STG_LD);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 x = mine[i];
-    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-  }
-  __syncwarp();
-}
-
+// TMEM gives every epilogue thread one ROW (lane) of the tile, so a warp-wide access with "row per lane" into a ROW-major
+// plane touches 32 different 128-byte lines.  v0 did exactly that (65 us per (tile, period): 32 LSU wavefronts and 32
+// half-written sectors per store instruction), v1 transposed through per-warp shared-memory staging tiles (40 us, LSU pipe
+// 61 % busy).  v2 (this one) stores what the weight-gradient contraction reads TRANSPOSED, per (tile, period):
+//     DT [tp][4H][128]   hT, hRT [tp][H][128]        (tp = t * nqt + qt; 128 = the rows of the tile)
+// Lane = row makes every store of one column a contiguous 128-byte line, no staging at all -- and a [column][row] tile is
+// exactly the K-major operand the row contraction wants (K = rows): gemm_tma.cu reads these tiles with plain TMA boxes and
+// no transposing converters.
 template <int HH>
-struct BCfg {   // shared-memory plan of the backward: ring | resident tail | staging tiles
+struct BCfg {   // shared-memory plan of the backward: ring | resident tail | M1 cache
   using C = FCfg<HH>;
-  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + NEPI_W * STG_BYTES + C::M1C;
-  static constexpr int NS_FIT = (SMEM_MAX - 4096 - FIXED) / C::STAGE;
+  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C;
+  static constexpr int NS_FIT = (SMEM_MAX - 12288 - FIXED) / C::STAGE;
   static constexpr int NS = NS_FIT < 2 * C::NSTEP ? NS_FIT : 2 * C::NSTEP;
   static constexpr int SMEM = 1024 + NS * C::STAGE + FIXED;
   static_assert(NS >= 3, "backward ring too shallow");
@@ -609,12 +615,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = sm;
   uint8_t* tail = ring + NS * C::STAGE;
-  float* stg_all = reinterpret_cast<float*>(tail + ((C::TAIL + 1023) & ~1023));
-  float* m1data = stg_all + NEPI_W * (STG_BYTES / 4);
+  float* m1data = reinterpret_cast<float*>(tail + ((C::TAIL + 1023) & ~1023));
   __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
   __shared__ uint32_t tmem_base_s;
   __shared__ int m1tag[4];
-  __shared__ float red[NEPI_W][64];
+  __shared__ double red[NEPI_W][64];      // attention-gradient partials: fp64 sums (see below)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = (a.nqt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int S = n_items * a.T;
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
     mbar_arrive_expect_tx(&bar_tail, C::TAIL);
     for (int o = 0; o < C::TAIL; o += 16384) bulk_g2s(tail + o, a.img + C::RING_IMG + o, min(16384, C::TAIL - o), &bar_tail);
   }
-  for (int i = tid; i < NEPI_W * 64; i += NTHR) (&red[0][0])[i] = 0.f;
+  for (int i = tid; i < NEPI_W * 64; i += NTHR) (&red[0][0])[i] = 0.0;
   if (warp == W_MMA) tmem_alloc(&tmem_base_s, C::TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -649,7 +654,6 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
     mbar_wait(&bar_tail, 0);
     const int qd = warp & 3, ch = warp >> 2;
     const int r = qd * 32 + lane, c0 = ch * CWF;
-    float* stg = stg_all + warp * (STG_BYTES / 4);
     const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
     const uint32_t t1c = tl + 2 * HH, t2c = tl + 3 * HH;   // acc1 = dHR (then dHR * R), acc2 = p G Z + dhg
     Row ri;
@@ -663,100 +667,108 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
         m1_cache_fill<HH>(a, ri, m1data, m1tag, tid);   // all threads are past the previous item's E0 (bar_ar / bar_2r chain)
       }
       const float p = consts[C::C_PROBS + t];
-      const size_t toff = ((size_t)t * a.nqt + qt) * (size_t)(TC_ROWS * HH * 4);
+      const size_t tp = (size_t)t * a.nqt + qt;
+      const size_t toff = tp * (size_t)(TC_ROWS * HH * 4);
       const uint8_t* zt = reinterpret_cast<const uint8_t*>(a.Zp) + toff;
       const uint8_t* rt = reinterpret_cast<const uint8_t*>(a.Rp) + toff;
       const uint8_t* ct = reinterpret_cast<const uint8_t*>(a.Hcp) + toff;
-      // first row of this warp's 32-row group in the row-major (t, q) planes and in G (G is padded to whole tiles)
-      const size_t row0 = (size_t)t * a.BNp + (size_t)qt * TC_ROWS + qd * 32;
-      float* D0 = a.D + row0 * 4 * HH + c0;
-      float* h0 = a.hpl + row0 * HH + c0;
-      float* hR0 = a.hRpl + row0 * HH + c0;
-      const float* G0 = a.G + ((size_t)qt * TC_ROWS + qd * 32) * HH + c0;
+      const uint8_t* gt = reinterpret_cast<const uint8_t*>(a.G) + (size_t)qt * (size_t)(TC_ROWS * HH * 4);   // G tile of this item
+      // transposed outputs of this (tile, period): element (column c, row r) at c * 128 + r
+      float* DT = a.D + tp * (size_t)(4 * HH * TC_ROWS) + r;
+      float* hT = a.hpl + tp * (size_t)(HH * TC_ROWS) + r;
+      float* hRT = a.hRpl + tp * (size_t)(HH * TC_ROWS) + r;
       // ---- E0: recompute h; gate gradients from the saved planes ----
       Feats f;
       load_feats(a, ri, t, f);
-      float dp = 0.f;
-      unsigned long long neg = 0ull;             // h <= 0 per column (leaky_relu slope of the regional combine)
-#pragma unroll 1
+      float dz[CWF];
+      double dp = 0.0;
+      unsigned int neg = 0u;                     // h <= 0 per column (leaky_relu slope of the regional combine)
+#pragma unroll
       for (int j = 0; j < CWF; j += 16) {
-        // register plan (96 per thread): h -> h*R in place, G -> p G Z in place, plus Dz and Dc
-        float h[16], g[16], dc[16], dz[16];
+        float h[16], dc[16], gz[16];
         h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
-        stage_store(stg, lane, h0 + j, HH, h);
-        stage_load(stg, lane, G0 + j, HH, g);
+        float dpc = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           const int c = c0 + j + i;
           const float4 z4 = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c)));
           const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
           const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + piece(r, c)));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gt + piece(r, c)));
           const float z[4] = {z4.x, z4.y, z4.z, z4.w}, rg[4] = {r4.x, r4.y, r4.z, r4.w}, hc[4] = {c4.x, c4.y, c4.z, c4.w};
+          const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float hh = h[i + e];
-            const float gv = ri.valid ? g[i + e] : 0.f;                       // padded rows of the last tile: zero gradient
+            const float gv = ri.valid ? g[e] : 0.f;                           // padded rows of the last tile: zero gradient
             const float gg = p * gv;                                          // dH' = probs[t] * d out_hidden
-            dp = fmaf(gv, z[e] * hh + (1.0f - z[e]) * hc[e], dp);
-            dz[i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
+            dpc = fmaf(gv, z[e] * hh + (1.0f - z[e]) * hc[e], dpc);
+            dz[j + i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
             dc[i + e] = gg * (1.0f - z[e]) * (1.0f - hc[e] * hc[e]);
-            g[i + e] = gg * z[e];
-            h[i + e] = hh * rg[e];
-            if (!(hh > 0.f)) neg |= 1ull << (j + i + e);
+            gz[i + e] = gg * z[e];
+            hT[(size_t)(c + e) * TC_ROWS] = hh;
+            hRT[(size_t)(c + e) * TC_ROWS] = hh * rg[e];
+            DT[(size_t)(c + e) * TC_ROWS] = dz[j + i + e];
+            DT[(size_t)(2 * HH + c + e) * TC_ROWS] = dc[i + e];
+            if (!(hh > 0.f)) neg |= 1u << (j + i + e);
           }
         }
+        dp += (double)dpc;
         put_a16<HH>(tl, c0 + j, dc);
-        st_f32x16(t2c + c0 + j, g);               // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
-        stage_store(stg, lane, D0 + 2 * HH + j, 4 * HH, dc);
-        stage_store(stg, lane, D0 + j, 4 * HH, dz);
-        stage_store(stg, lane, hR0 + j, HH, h);
+        st_f32x16(t2c + c0 + j, gz);              // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_a);
-      // attention gradient d probs[t] += sum G * H'_t : fixed-order warp sum, one smem slot per (warp, period)
+      // attention gradient d probs[t] += sum G * H'_t.  The softmax Jacobian takes differences of these nearly equal sums
+      // (models/RegionalTemporalGCN.py:134), so everything above 16 terms is summed in fp64: fixed-order warp sum, one
+      // shared-memory slot per (warp, period)
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
       if (lane == 0) red[warp][t] += dp;
-      // ---- M1 done (dHR in acc1): Dz (re-read from the D plane this warp just wrote: L2) -> A, M2z starts ----
+      // ---- M1 done (dHR in acc1): Dz -> A, M2z starts ----
       mbar_wait(&bar_1, ph);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
-        stage_load(stg, lane, D0 + j, 4 * HH, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
         put_a16<HH>(tl, c0 + j, v);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_az);
-      // ---- E1 (under M2z): Dr = dHR h R (1-R) -> D plane, t1 = dHR R -> acc1 in place ----
-#pragma unroll 1
+      // ---- E1 (under M2z): Dr = dHR h R (1-R) (registers, reusing dz), t1 = dHR R -> acc1 in place ----
+#pragma unroll
       for (int j = 0; j < CWF; j += 16) {
-        float v[16], hh[16], dr[16];
+        float v[16];
         tmem_ld16(t1c + c0 + j, v);
-        stage_load(stg, lane, h0 + j, HH, hh);     // written by this warp in E0 (stage_store ends with __syncwarp)
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c0 + j + i)));
+          const int c = c0 + j + i;
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
           const float rg[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            dr[i + e] = v[i + e] * hh[i + e] * rg[e] * (1.0f - rg[e]);
+            const float hh = ld_own1(hT + (size_t)(c + e) * TC_ROWS);        // this thread's own store in E0
+            const float dr = v[i + e] * hh * rg[e] * (1.0f - rg[e]);
+            dz[j + i + e] = dr;
+            DT[(size_t)(HH + c + e) * TC_ROWS] = dr;
             v[i + e] *= rg[e];
           }
         }
         st_f32x16(t1c + c0 + j, v);
-        stage_store(stg, lane, D0 + HH + j, 4 * HH, dr);
       }
       tmem_st_wait();
       // ---- M2z done (A free): Dr -> A, M2r ----
       mbar_wait(&bar_2z, ph);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
-        stage_load(stg, lane, D0 + HH + j, 4 * HH, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
         put_a16<HH>(tl, c0 + j, v);
       }
       tmem_st_wait();
@@ -765,7 +777,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       // ---- E2: d h_pre = act'(h) (p G Z + dhg + dHR R) ----
       mbar_wait(&bar_2r, ph);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16], u[16];
         tmem_ld16(t2c + c0 + j, v);
@@ -773,10 +785,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float d = v[i] + u[i];
-          if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i)) & 1ull)) d *= 0.01f;
-          v[i] = d;
+          if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i)) & 1u)) d *= 0.01f;
+          DT[(size_t)(3 * HH + c0 + j + i) * TC_ROWS] = d;
         }
-        stage_store(stg, lane, D0 + 3 * HH + j, 4 * HH, v);
       }
       tc_fence_before();
     }
@@ -807,7 +818,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   }
   __syncthreads();
   if (tid < a.T) {
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NEPI_W; ++w) s += red[w][tid];
     a.dpp[(size_t)blockIdx.x * a.T + tid] = s;
@@ -872,22 +883,34 @@ __global__ void k_pack_f(const float* __restrict__ Wzr, const float* __restrict_
   }
 }
 
-// Feat[t * BNp + q] = S_t | X_t | 1 | 0  (32 floats): second operand of the weight-gradient row contraction, same row
-// order as the backward kernel's D / h / h*R; padded rows (q >= BN) are zero
-__global__ void __launch_bounds__(256) k_feat_f(const float* __restrict__ Xt, const float* __restrict__ St, int BN, int BNp, int T,
-                                                float* __restrict__ Feat) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long row = i >> 3;
-  if (row >= (long long)T * BNp) return;
-  const int c4 = (int)(i & 7);
-  const int t = (int)(row / BNp), q = (int)(row - (long long)t * BNp);
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (q < BN) {
-    if (c4 < 2) v = __ldg(reinterpret_cast<const float4*>(St + ((size_t)t * BN + q) * F) + c4);
-    else if (c4 < 4) v = __ldg(reinterpret_cast<const float4*>(Xt + ((size_t)t * BN + q) * F) + (c4 - 2));
-    else if (c4 == 4) v.x = 1.0f;
+// F^T tiles of the weight-gradient contraction, [tp][32][128]: rows 0..7 = S_t, 8..15 = X_t, 16 = 1, 17..31 = 0 of the 128 rows
+// of tile tp = t * nqt + qt (padded rows q >= BN: all zero).  One thread per (tile, row): its 32-byte S and X rows are
+// contiguous across the warp, every store of one feature is a 128-byte line.
+__global__ void __launch_bounds__(128) k_featT_f(const float* __restrict__ Xt, const float* __restrict__ St, int BN, int nqt,
+                                                 float* __restrict__ FT) {
+  const int tp = blockIdx.x, r = threadIdx.x;
+  const int t = tp / nqt, qt = tp - t * nqt;
+  const long long q = (long long)qt * TC_ROWS + r;
+  const bool ok = q < BN;
+  float s[8], x[8];
+  load8(St + ((size_t)t * BN + (ok ? q : 0)) * F, s, ok ? 1.f : 0.f);
+  load8(Xt + ((size_t)t * BN + (ok ? q : 0)) * F, x, ok ? 1.f : 0.f);
+  float* o = FT + (size_t)tp * 32 * TC_ROWS + r;
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    o[(size_t)f * TC_ROWS] = s[f];
+    o[(size_t)(8 + f) * TC_ROWS] = x[f];
   }
-  reinterpret_cast<float4*>(Feat)[i] = v;
+  o[(size_t)16 * TC_ROWS] = ok ? 1.f : 0.f;
+#pragma unroll
+  for (int f = 17; f < 32; ++f) o[(size_t)f * TC_ROWS] = 0.f;
+}
+// the head's weight-gradient contraction (head.cu) takes its bias column sums from a ones column: Feat [BNp][32], column 16
+__global__ void __launch_bounds__(256) k_ones_f(int BN, int BNp, float* __restrict__ Feat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BNp * 8) return;
+  const int row = i >> 3, c4 = i & 7;
+  reinterpret_cast<float4*>(Feat)[i] = make_float4((c4 == 4 && row < BN) ? 1.f : 0.f, 0.f, 0.f, 0.f);
 }
 
 template <int HH>
@@ -901,7 +924,8 @@ FArgs make_fargs(const regt_args* a, const Layout& L) {
   k.M1t = L.M1t;
   k.Zp = L.Zp; k.Rp = L.Rp; k.Hcp = L.Hcp;
   k.out_hidden = a->out_hidden;
-  k.G = L.G; k.D = L.D; k.hpl = L.h; k.hRpl = L.hR; k.dpp = L.tc_dpp;
+  k.save = a->inference ? 0 : 1;
+  k.G = L.G; k.D = L.D; k.hpl = L.h; k.hRpl = L.hR; k.dpp = reinterpret_cast<double*>(L.tc_dpp);
   return k;
 }
 int num_sms_f() {
@@ -929,7 +953,9 @@ int run_fwd_kernel(const regt_args* a, const Layout& L, cudaStream_t st) {
   FArgs k = make_fargs<HH>(a, L);
   k.img = L.tc_img_f;
   REGT_CUDA(cudaFuncSetAttribute(k_cell_fwd_f<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  k_cell_fwd_f<HH><<<min(num_sms_f(), k.nqt), NTHR, C::SMEM, st>>>(k);
+  const int grid = min(num_sms_f(), k.nqt);
+  REGT_CHECK(grid <= TC_MAX_CTAS, "fused forward: grid %d exceeds the per-CTA scratch tiles", grid);
+  k_cell_fwd_f<HH><<<grid, NTHR, C::SMEM, st>>>(k);
   REGT_LAUNCHED("k_cell_fwd_f", st);
   return 0;
 }
@@ -963,10 +989,11 @@ int launch_cell_bwd_f(const regt_args* a, const Layout& L, cudaStream_t st, int*
   return a->H == 128 ? run_bwd_kernel<128>(a, L, st, grid) : run_bwd_kernel<64>(a, L, st, grid);
 }
 int launch_feat_f(const regt_args* a, const Layout& L, cudaStream_t st) {
-  const int BN = a->B * a->N, BNp = (BN + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
-  const long long n = (long long)a->T * BNp * 8;
-  k_feat_f<<<cdiv(n, 256), 256, 0, st>>>(L.Xt, L.S, BN, BNp, a->T, L.Feat);
-  REGT_LAUNCHED("k_feat_f", st);
+  const int BN = a->B * a->N, nqt = (BN + TC_ROWS - 1) / TC_ROWS, BNp = nqt * TC_ROWS;
+  k_featT_f<<<a->T * nqt, 128, 0, st>>>(L.Xt, L.S, BN, nqt, L.FeatT);
+  REGT_LAUNCHED("k_featT_f", st);
+  k_ones_f<<<cdiv((long long)BNp * 8, 256), 256, 0, st>>>(BN, BNp, L.Feat);
+  REGT_LAUNCHED("k_ones_f", st);
   return 0;
 }
 

@@ -60,7 +60,7 @@ struct GK {
   float* d_h_ext;
   float* Feat;        // [rows][32]: S_t (8) | X_t (8) | 1 | 0...   B operand of the F-wide weight-gradient GEMM
   float* out_hidden;  // [BN][H]
-  float* dp_part;     // [gridDim.x][T] attention-gradient partials
+  double* dp_part;    // [gridDim.x][T] attention-gradient partials (fp64: the softmax Jacobian differences them)
   long long BN;
 };
 
@@ -229,10 +229,10 @@ __global__ void __launch_bounds__(256) k_g_feat(GK a) {
 
 // Dz -> D[:, 0:H], Dh -> D[:, 2H:3H]; attention gradient partials d probs[t] = sum G * H'_t (H' recomputed)
 __global__ void __launch_bounds__(256) k_g_b1(GK a) {
-  __shared__ float red[8][64];
+  __shared__ double red[8][64];
   const int H = a.H, T = a.T, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long total = a.BN * (H >> 2);
-  for (int t = threadIdx.x; t < 8 * 64; t += 256) (&red[0][0])[t] = 0.f;
+  for (int t = threadIdx.x; t < 8 * 64; t += 256) (&red[0][0])[t] = 0.0;
   __syncthreads();
   // grid-stride over (q, 4 columns); trip counts are warp-uniform up to the tail (idle lanes add zeros)
   for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
@@ -259,14 +259,15 @@ __global__ void __launch_bounds__(256) k_g_b1(GK a) {
         st4(a.D + row * 4 * H + j, dz[0], dz[1], dz[2], dz[3]);
         st4(a.D + row * 4 * H + 2 * H + j, dh[0], dh[1], dh[2], dh[3]);
       }
+      double dpd = (double)dp;               // four terms in fp32, everything above in fp64
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
-      if (lane == 0) red[warp][t] += dp;     // only this warp's lane 0 touches red[warp][*]: fixed order
+      for (int d = 16; d > 0; d >>= 1) dpd += __shfl_xor_sync(0xffffffffu, dpd, d);
+      if (lane == 0) red[warp][t] += dpd;    // only this warp's lane 0 touches red[warp][*]: fixed order
     }
   }
   __syncthreads();
   if (threadIdx.x < T) {
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
     a.dp_part[(size_t)blockIdx.x * T + threadIdx.x] = s;
@@ -344,6 +345,15 @@ __global__ void __launch_bounds__(256) k_g_fw_scatter(const float* __restrict__ 
   }
 }
 
+// d probs[t] = sum over the CTAs of the fused backward's fp64 partials, in CTA order
+__global__ void k_f_sum_dpp(const double* __restrict__ part, int nparts, int T, float* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t >= T) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * T + t];
+  out[t] = (float)s;
+}
+
 GK make_gk(const regt_args* a, const Layout& L) {
   GK k{};
   k.rows = (long long)a->B * a->N * a->T;
@@ -404,15 +414,15 @@ int cell_backward_g(const regt_args* a, const Layout& L, cudaStream_t st) {
   float* part = L.part;
   float* BhT = part;                       // [H][H]   scratch until the weight-gradient partials take over
   float* BzrT = part + (size_t)H * H;      // [H][2H]
-  float* dpp = part + (size_t)3 * H * H;   // [nb1][T] attention-gradient partials
+  double* dpp = reinterpret_cast<double*>(part + (size_t)3 * H * H);   // [nb1][T] attention-gradient partials (fp64)
   k_g_pack_bt<<<cdiv(3ll * H * H, 256), 256, 0, st>>>(a->p.lin_w[0], a->p.lin_w[1], a->p.lin_w[2], H, BhT, BzrT);
   REGT_LAUNCHED("k_g_pack_bt", st);
   const int nb1 = (int)min(1024ll, (long long)cdiv(BN * (H / 4), 256));
   k.dp_part = dpp;
   k_g_b1<<<nb1, 256, 0, st>>>(k);
   REGT_LAUNCHED("k_g_b1", st);
-  k_g_sum_parts<<<cdiv(T, 32), dim3(32, 8), 0, st>>>(dpp, T, nb1, T, L.dprobs);
-  REGT_LAUNCHED("k_g_sum_parts", st);
+  k_f_sum_dpp<<<1, 64, 0, st>>>(dpp, nb1, T, L.dprobs);
+  REGT_LAUNCHED("k_f_sum_dpp", st);
   if (launch_gemm_nt_tma(L.D + 2 * H, 4 * H, BhT, H, L.Hn, H, rows, H, H, L.bsplit, st)) return -1;            // dHR = Dh . B_h
   G_LAUNCH(k_g_b2, "k_g_b2");
   if (launch_gemm_nt_tma(L.D, 4 * H, BzrT, 2 * H, L.D + 3 * H, 4 * H, rows, H, 2 * H, L.bsplit, st)) return -1;   // dhg
@@ -466,48 +476,59 @@ int cell_forward_f(const regt_args* a, const Layout& L, cudaStream_t st) {
   cudaStream_t side = fork_side(st);
   cudaStream_t fs = side ? side : st;
   if (launch_feat_tc(a->plan, a->x, a->B, a->x_rows > 0 ? a->x_rows : a->N, a->T, L.Xt, L.S, L.U, fs)) return -1;
-  if (launch_feat_f(a, L, fs)) return -1;     // feature plane of the weight-gradient contractions (cell and head backward)
+  if (!a->inference && launch_feat_f(a, L, fs)) return -1;   // feature plane of the weight-gradient contractions (cell and head backward)
   if (launch_prep(a, L, st)) return -1;
   if (launch_pack_f(a, L, st)) return -1;
   if (side && join_side(st)) return -1;
   return launch_cell_fwd_f(a, L, st);
 }
 
+int launch_gemm_kt(const float* AT, long long ntile, int Ktot, int nseg, const int* seg_k0, const int* seg_k1, const int* seg_b,
+                   float* const* seg_C, const float* const* BTs, int N, int splits, const float* FT, float* C2, long long c2_split,
+                   cudaStream_t st);
+int launch_wgrad_m1_kt(const regt_args* a, const Layout& L, cudaStream_t st);
+
 int cell_backward_f(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, T = a->T;
-  const long long BN = (long long)a->B * a->N, BNp = (BN + 127) / 128 * 128, rowsP = BNp * T;
+  const long long BN = (long long)a->B * a->N, nqt = (BN + 127) / 128, ntile = nqt * T;
   int grid = 0;
   if (launch_cell_bwd_f(a, L, st, &grid)) return -1;
-  k_g_sum_parts<<<cdiv(T, 32), dim3(32, 8), 0, st>>>(L.tc_dpp, T, grid, T, L.dprobs);
-  REGT_LAUNCHED("k_g_sum_parts", st);
-  // weight gradients: ONE row contraction over the four gate-gradient blocks of D (z | r against h, h~ against h*R,
-  // h_pre against the feature plane only; every block also against [S | X | 1]), rows in (t, q) order
+  k_f_sum_dpp<<<1, 64, 0, st>>>(reinterpret_cast<const double*>(L.tc_dpp), grid, T, L.dprobs);
+  REGT_LAUNCHED("k_f_sum_dpp", st);
+  // weight gradients: ONE row contraction over the transposed gate-gradient tiles D^T [tile][4H][128] (z | r against h,
+  // h~ against h*R, h_pre against the feature tile only; every block also against [S | X | 1]), rows = K
   float* part = L.part;
-  const bool merged = H % 128 == 0;
-  const int ctas_per_split = (4 * H / 128) * (H / 128);
-  const int splits = merged ? (int)max(1ll, min((long long)min(WGRAD_SPLITS, cdiv(148, ctas_per_split)), rowsP / 512))
-                            : (int)max(1ll, min((long long)WGRAD_SPLITS, rowsP / 512));
+  const int mtiles = 4 * H / 128;
+  const int splits = (int)max(1ll, min((long long)min(WGRAD_SPLITS, cdiv(148, mtiles)), ntile / 4));
   float* pB = part;                                          // [splits][2H][H]  dB_z | dB_r
   float* pBh = pB + (size_t)splits * 2 * H * H;              // [splits][H][H]   dB_h
   float* pF = pBh + (size_t)splits * H * H;                  // [splits][4H][32] D^T Feat
   const long long fsplit = 4ll * H * 32;
-  if (merged) {
-    const int k0[3] = {0, 2 * H, 3 * H}, sb[3] = {0, 1, -1};
-    float* cs[3] = {pB, pBh, nullptr};
+  {
+    // segments start at multiples of 128 columns.  H = 128: z|r (2 tiles), h~, h_pre.  H = 64: tile 0 = z|r, tile 1 = h~ | h_pre
+    // (its rows 64.. are contracted against h*R too and dropped: only the feature columns of h_pre are kept)
+    int k0[3], k1[3], sb[3];
+    float* cs[3];
+    int ns;
+    if (H == 128) {
+      ns = 3;
+      k0[0] = 0; k1[0] = 256; sb[0] = 0; cs[0] = pB;
+      k0[1] = 256; k1[1] = 384; sb[1] = 1; cs[1] = pBh;
+      k0[2] = 384; k1[2] = 512; sb[2] = -1; cs[2] = nullptr;
+    } else {
+      ns = 2;
+      k0[0] = 0; k1[0] = 128; sb[0] = 0; cs[0] = pB;
+      k0[1] = 128; k1[1] = 192; sb[1] = 1; cs[1] = pBh;
+    }
     const float* bs[2] = {L.h, L.hR};
-    const long long lds[2] = {H, H};
-    if (launch_gemm_tn_tma(L.D, 4 * H, rowsP, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, L.Feat, 32, pF, fsplit, st, 0)) return -1;
-  } else {
-    if (launch_gemm_tn_auto(L.D, 4 * H, L.h, H, pB, rowsP, 2 * H, H, splits, st, L.Feat, 32, pF, fsplit, 0)) return -1;
-    if (launch_gemm_tn_auto(L.D + 2 * H, 4 * H, L.hR, H, pBh, rowsP, H, H, splits, st, L.Feat, 32, pF + (size_t)2 * H * 32, fsplit, 0)) return -1;
-    if (launch_gemm_tn_auto(L.D + 3 * H, 4 * H, nullptr, 0, nullptr, rowsP, H, 0, splits, st, L.Feat, 32, pF + (size_t)3 * H * 32, fsplit, 0)) return -1;
+    if (launch_gemm_kt(L.D, ntile, 4 * H, ns, k0, k1, sb, cs, bs, H, splits, L.FeatT, pF, fsplit, st)) return -1;
   }
   if (launch_reduce_splits(pB, L.dB, 2ll * H * H, splits, 0, st)) return -1;
   if (launch_reduce_splits(pBh, L.dB + (size_t)2 * H * H, (long long)H * H, splits, 0, st)) return -1;
   k_g_fw_scatter<<<cdiv(4ll * H * 32, 32), dim3(32, 8), 0, st>>>(pF, splits, H, L.dP, L.dcg, L.dM0, L.dc0);
   REGT_LAUNCHED("k_g_fw_scatter", st);
   if (a->plan.nseg > 0) {   // dM1[r]: per-region sums over the (node, region) segments
-    if (launch_wgrad_m1_from(a, L, L.D + 3 * (size_t)H, 4ll * H, st, 1, BNp)) return -1;
+    if (launch_wgrad_m1_kt(a, L, st)) return -1;
   }
   return launch_chain(a, L, st);
 }

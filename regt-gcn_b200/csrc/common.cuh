@@ -99,6 +99,7 @@ struct Layout {
   // backward planes
   float* D;      // [rows][4H]  d_pre_z | d_pre_r | d_pre_h | d_hpre
   float* Feat;   // [rows][32]  S_t | X_t | 1 | 0  (tf32x3: B operand of the F-wide weight-gradient GEMM)
+  float* FeatT;  // fused tf32x3 cell: transposed feature tiles [T*nqt][32][128] (cell_f.cu)
   float* bsplit; // tf32x3: hi | lo images of the weight operand of the current gate GEMM (gemm_tma.cu)
   // collapsed-weight gradients
   float* dB;     // [3][H][H]   dB_z, dB_r, dB_h

@@ -565,6 +565,214 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn_tma(const __grid_cons
   if (warp == TN_W_MMA) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// gemm_kt: the same row contraction over TRANSPOSED tiles.  The fused cell backward (cell_f.cu) stores its gate gradients and
+// the h / h*R planes as [tile][column][128 rows] -- the layout its row-per-lane epilogue threads write as whole 128-byte
+// lines -- and a [column][row] tile is already the K-major operand of this contraction (K = rows).  A chunk (32 rows of one
+// tile) is three plain TMA boxes, [128 cols][32 k] of A^T, [N cols][32 k] of B^T and [32][32 k] of the feature plane; the
+// converters only split fp32 -> tf32 hi / lo at the SAME swizzled offset (one 128-bit load and two 128-bit stores per 16
+// bytes -- gemm_tn's transposing converters issue eight 4-byte stores for them and keep the LSU pipe 61 % busy).  MMA issue,
+// accumulator draining and the output format are gemm_tn's.
+//   A^T : [ntile * Ktot][128]   tile-major, Ktot = 4H columns per tile           (segments of 128 columns as in gemm_tn)
+//   B^T : [ntile * N][128]      N <= 128 columns per tile (h or h*R)
+//   F^T : [ntile * 32][128]
+// ------------------------------------------------------------------------------------------
+struct KtArgs {
+  CUtensorMap ta, tb[2], tf;
+  TnSeg seg[4];
+  int nseg;
+  float* C2;
+  long long c2_split;
+  long long ntile, tiles_per_split;
+  int Ktot, N, N2;
+};
+constexpr int KT_RAW = 2 * TILE + TN_BOX;        // raw stage: A^T box | B^T box | F^T box (fp32 as loaded)
+
+__global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_kt(const __grid_constant__ KtArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_raw[TN_NR], bar_rfree[TN_NR], bar_full[TN_NC], bar_empty[TN_NC], bar_done, bar_acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kg = blockIdx.x * 128;   // first column of A^T of this M tile
+  int si = 0;
+  for (int s = 1; s < a.nseg; ++s)
+    if (kg >= a.seg[s].k0) si = s;
+  const int sk0 = a.seg[si].k0, sk1 = a.seg[si].k1, sb = a.seg[si].b;
+  float* segC = a.seg[si].C;
+  const int kt = min(128, sk1 - kg);                          // output rows of this tile that belong to the segment's C
+  const int kt2 = min(128, a.Ktot - kg);                      // ... and to the feature outputs C2
+  const int nt = sb >= 0 ? a.N : 0;                           // columns from the B operand
+  const int n2 = a.N2;
+  const int ntot = nt + n2;
+  const long long t0 = (long long)blockIdx.z * a.tiles_per_split, t1 = min(a.ntile, t0 + a.tiles_per_split);
+  const int nchunks = ntot > 0 ? (int)max(0ll, (t1 - t0) * 4) : 0;
+  uint8_t* raw = sm;
+  uint8_t* cv = sm + TN_NR * KT_RAW;
+  if (tid == 0) {
+    for (int s = 0; s < TN_NR; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_rfree[s], TN_CONV);
+    }
+    for (int s = 0; s < TN_NC; ++s) {
+      mbar_init(&bar_full[s], TN_CONV);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    mbar_init(&bar_acc_free[0], TN_CONV);
+    mbar_init(&bar_acc_free[1], TN_CONV);
+    fence_barrier_init();
+  }
+  if (warp == TN_W_MMA) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < TN_W_MMA) {
+    // ---- converters: thread = (row of the A^T / B^T tile, four of its eight 16-byte pieces); feature tile: (row tid / 8, piece tid % 8)
+    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int frow = tid >> 3, fpc = tid & 7;
+    const bool b_ok = row < nt;
+    const int orow = row;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float acc[5][16];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+    int drained = 0;
+    auto drain = [&](int buf) {
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c0 = half * 16 + 32 * i;
+        if (c0 < ntot) {
+          float v[16];
+          tmem_ld16(tlane + buf * TN_ACC + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[i][j] += v[j];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acc_free[buf]);
+    };
+    uint32_t offs[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) offs[c] = (uint32_t)(row * 128 + (((half * 4 + c) ^ (row & 7)) << 4));
+    const uint32_t foff = (uint32_t)(frow * 128 + ((fpc ^ (frow & 7)) << 4));
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int rs = kc % TN_NR, cs = kc % TN_NC;
+      mbar_wait(&bar_raw[rs], (uint32_t)((kc / TN_NR) & 1));
+      const uint8_t* rw = raw + rs * KT_RAW;
+      float4 av[4], bv[4], fv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        av[c] = *reinterpret_cast<const float4*>(rw + offs[c]);
+        bv[c] = b_ok ? *reinterpret_cast<const float4*>(rw + TILE + offs[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (n2) fv = *reinterpret_cast<const float4*>(rw + 2 * TILE + foff);
+      {   // an mbarrier arrive does not wait for this thread's earlier shared-memory loads (see k_gemm_tn_tma)
+        const uint32_t dep = __float_as_uint(av[0].x) | __float_as_uint(av[1].x) | __float_as_uint(av[2].x) | __float_as_uint(av[3].x) |
+                             __float_as_uint(bv[0].x) | __float_as_uint(bv[1].x) | __float_as_uint(bv[2].x) | __float_as_uint(bv[3].x) |
+                             __float_as_uint(fv.x);
+        if (dep == 0x7FC0DEADu) __nanosleep(1);
+        mbar_arrive(&bar_rfree[rs]);
+      }
+      if (kc >= TN_NC) mbar_wait(&bar_empty[cs], (uint32_t)((kc / TN_NC - 1) & 1));
+      if (kc >= TN_GROUP + TN_NC - 1 && (kc - (TN_NC - 1)) % TN_GROUP == 0) {
+        drain(drained & 1);
+        ++drained;
+      }
+      uint8_t* st = cv + cs * TN_CV;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 hi, lo;
+        split4(av[c], hi, lo);
+        *reinterpret_cast<float4*>(st + offs[c]) = hi;
+        *reinterpret_cast<float4*>(st + TILE + offs[c]) = lo;
+        if (b_ok) {
+          split4(bv[c], hi, lo);
+          *reinterpret_cast<float4*>(st + 2 * TILE + offs[c]) = hi;
+          *reinterpret_cast<float4*>(st + 2 * TILE + TN_BT + offs[c]) = lo;
+        }
+      }
+      if (n2) {   // feature rows follow the nt rows of the B tile (nt is a multiple of 8: the swizzle phase carries over)
+        float4 hi, lo;
+        split4(fv, hi, lo);
+        *reinterpret_cast<float4*>(st + 2 * TILE + nt * 128 + foff) = hi;
+        *reinterpret_cast<float4*>(st + 2 * TILE + TN_BT + nt * 128 + foff) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&bar_full[cs]);
+    }
+    const int ngroups = (nchunks + TN_GROUP - 1) / TN_GROUP;
+    if (nchunks > 0) mbar_wait(&bar_done, 0);
+    for (; drained < ngroups; ++drained) drain(drained & 1);
+    const bool row_ok = orow < kt, row_ok2 = orow < kt2;
+    float* cp = nt > 0 ? segC + ((size_t)blockIdx.z * (sk1 - sk0) + (kg - sk0) + (row_ok ? orow : 0)) * a.N : nullptr;
+    float* cp2 = n2 ? a.C2 + (size_t)blockIdx.z * a.c2_split + (size_t)(kg + (row_ok2 ? orow : 0)) * 32 : nullptr;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int c0 = half * 16 + 32 * i;
+      if (c0 < ntot && (c0 < nt ? row_ok : row_ok2)) {
+        float* o = c0 < nt ? cp + c0 : cp2 + (c0 - nt);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      }
+    }
+  } else if (warp == TN_W_MMA) {
+    const uint32_t idesc = make_idesc(FMT_TF32, 128, max(ntot, 16), 0, 0);
+    const uint32_t base = smem_u32(cv);
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const int s = kc % TN_NC;
+      const int g = kc / TN_GROUP, buf = g & 1, kg0 = kc % TN_GROUP;
+      if (kg0 == 0 && g >= 2) {   // the converters have drained this accumulator's previous group (g - 2)
+        mbar_wait(&bar_acc_free[buf], (uint32_t)((g / 2 - 1) & 1));
+        tc_fence_after();
+      }
+      mbar_wait(&bar_full[s], (uint32_t)((kc / TN_NC) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + s * TN_CV;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t at = st + (p == 1 ? TILE : 0), bt = st + 2 * TILE + (p == 2 ? TN_BT : 0);
+#pragma unroll
+          for (int k = 0; k < KC / 8; ++k)
+            umma<FMT_TF32>(tmem + buf * TN_ACC, make_desc(at + k * 32, 16, 1024, LAYOUT_SW128), make_desc(bt + k * 32, 16, 1024, LAYOUT_SW128),
+                           idesc, (kg0 > 0 || p > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_empty[s]);
+        if (kc + 1 == nchunks) umma_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    // ---- producer ----
+    if (lane == 0 && nchunks > 0) {
+      tmap_prefetch(&a.ta);
+      if (sb >= 0) tmap_prefetch(&a.tb[sb]);
+      if (n2) tmap_prefetch(&a.tf);
+      const uint32_t bytes = (uint32_t)(TILE + (sb >= 0 ? a.N * 128 : 0) + (n2 ? TN_BOX : 0));
+      for (int kc = 0; kc < nchunks; ++kc) {
+        const int rs = kc % TN_NR;
+        if (kc >= TN_NR) mbar_wait(&bar_rfree[rs], (uint32_t)((kc / TN_NR - 1) & 1));
+        uint8_t* rw = raw + rs * KT_RAW;
+        const long long tile = t0 + kc / 4;
+        const int k0 = (kc & 3) * KC;
+        mbar_arrive_expect_tx(&bar_raw[rs], bytes);
+        tma_2d(rw, &a.ta, k0, (int)(tile * a.Ktot + kg), &bar_raw[rs]);
+        if (sb >= 0) tma_2d(rw + TILE, &a.tb[sb], k0, (int)(tile * a.N), &bar_raw[rs]);
+        if (n2) tma_2d(rw + 2 * TILE, &a.tf, k0, (int)(tile * 32), &bar_raw[rs]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == TN_W_MMA) tmem_dealloc(tmem, 512);
+}
+
 bool legacy_forced() {
   static int v = -1;
   if (v < 0) {
@@ -652,6 +860,43 @@ int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int
   return 0;
 }
 
+// the row contraction over transposed tiles (k_gemm_kt): AT [ntile * Ktot][128], BTs[b] [ntile * N][128], FT [ntile * 32][128];
+// segment boundaries are multiples of 128 columns except the end of the last segment with an operand (H = 64: [Dc | dhp])
+int launch_gemm_kt(const float* AT, long long ntile, int Ktot, int nseg, const int* seg_k0, const int* seg_k1, const int* seg_b,
+                   float* const* seg_C, const float* const* BTs, int N, int splits, const float* FT, float* C2, long long c2_split,
+                   cudaStream_t st) {
+  REGT_CHECK(AT && nseg >= 1 && nseg <= 4 && Ktot % 128 == 0 && N % 8 == 0 && N >= 16 && N <= 128 && splits > 0 && ntile > 0 && FT && C2,
+             "gemm_kt: bad shape (Ktot=%d N=%d)", Ktot, N);
+  REGT_CHECK(ntile * Ktot < (1ll << 31), "gemm_kt: tile count overflows the TMA coordinate");
+  KtArgs a{};
+  if (tmap_2d(&a.ta, AT, 128, ntile * Ktot, 128, 128, "gemm_kt(A^T)")) return -1;
+  for (int s = 0; s < nseg; ++s) {
+    a.seg[s].k0 = seg_k0[s];
+    a.seg[s].k1 = seg_k1[s];
+    a.seg[s].b = seg_b[s];
+    a.seg[s].C = seg_C[s];
+    REGT_CHECK(a.seg[s].k0 % 128 == 0, "gemm_kt: segment starts must be multiples of 128");
+    REGT_CHECK(seg_b[s] < 2 && (seg_b[s] < 0 || (seg_C[s] && BTs[seg_b[s]])), "gemm_kt: segment %d has no operand / output", s);
+  }
+  for (int b = 0; b < 2; ++b) {
+    bool used = false;
+    for (int s = 0; s < nseg; ++s) used |= seg_b[s] == b;
+    if (used && tmap_2d(&a.tb[b], BTs[b], 128, ntile * N, 128, N, "gemm_kt(B^T)")) return -1;
+  }
+  if (tmap_2d(&a.tf, FT, 128, ntile * 32, 128, 32, "gemm_kt(F^T)")) return -1;
+  a.nseg = nseg;
+  a.C2 = C2;
+  a.c2_split = c2_split > 0 ? c2_split : (long long)Ktot * 32;
+  a.ntile = ntile;
+  a.tiles_per_split = (ntile + splits - 1) / splits;
+  a.Ktot = Ktot; a.N = N; a.N2 = 32;
+  const size_t smem = (size_t)TN_NR * KT_RAW + (size_t)TN_NC * TN_CV + 1024;
+  REGT_CUDA(cudaFuncSetAttribute(k_gemm_kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gemm_kt<<<dim3(Ktot / 128, 1, splits), TN_THREADS, smem, st>>>(a);
+  REGT_LAUNCHED("k_gemm_kt", st);
+  return 0;
+}
+
 // drop-in for launch_gemm_tn_tf32x3 (single segment); falls back when the TMA preconditions do not hold
 int launch_gemm_tn_auto(const float* A, long long lda, const float* B, long long ldb, float* Cp, long long M, int K, int N, int splits,
                         cudaStream_t st, const float* B2, long long ldb2, float* Cp2, long long c2_split, int relu_b) {
@@ -684,4 +929,22 @@ extern "C" int regt_debug_gemm_tn_multi(const float* A, int64_t lda, int64_t M, 
   const float* bs[2] = {B0, B1};
   const long long lds[2] = {H, H};
   return regt::launch_gemm_tn_tma(A, lda, M, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, B2, 32, C2, 0, (cudaStream_t)stream, 0);
+}
+// the transposed-tile form used by the fused cell backward: AT [ntile][4H][128]; B0T, B1T [ntile][H][128]; FT [ntile][32][128]
+extern "C" int regt_debug_gemm_kt(const float* AT, int64_t ntile, int32_t H, const float* B0T, const float* B1T, const float* FT,
+                                  float* C0, float* C1, float* C2, int32_t splits, regt_stream_t stream) {
+  int k0[3], k1[3], sb[3], ns;
+  float* cs[3];
+  if (H == 128) {
+    ns = 3;
+    k0[0] = 0; k1[0] = 256; sb[0] = 0; cs[0] = C0;
+    k0[1] = 256; k1[1] = 384; sb[1] = 1; cs[1] = C1;
+    k0[2] = 384; k1[2] = 512; sb[2] = -1; cs[2] = nullptr;
+  } else {
+    ns = 2;
+    k0[0] = 0; k1[0] = 128; sb[0] = 0; cs[0] = C0;
+    k0[1] = 128; k1[1] = 192; sb[1] = 1; cs[1] = C1;
+  }
+  const float* bs[2] = {B0T, B1T};
+  return regt::launch_gemm_kt(AT, ntile, 4 * H, ns, k0, k1, sb, cs, bs, H, splits, FT, C2, 0, (cudaStream_t)stream);
 }

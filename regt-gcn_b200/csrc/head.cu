@@ -435,7 +435,7 @@ static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* 
   k.w1 = a->p.head_w1; k.w2 = a->p.head_w2; k.d_hidden = a->d_hidden;
   k.a1 = L.a1; k.out = a->out; k.d_out = a->d_out; k.loss_part = L.part; k.d_a1 = L.d_a1; k.G = L.G;
   k.hid_part = nullptr; k.ntc = 0; k.hid_out = a->out_hidden;
-  k.g_tiled = a->precision == REGT_PREC_BF16;   // the fused tcgen05 backward bulk-loads G tiles
+  k.g_tiled = a->precision == REGT_PREC_BF16 || cell_f_usable(a);   // the fused tcgen05 backward kernels read G tiles
   if (a->precision == REGT_PREC_BF16 && head_fusable(a)) {  // the cell left per-chunk partials (see cell_tc.cu)
     k.hid_part = L.hid_part;
     k.ntc = tc_num_chunks(a);
@@ -511,7 +511,7 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
     return launch_head_grad_reduce(a, L, st);
   }
   if (!a->d_out) {  // only out_hidden carries gradient
-    k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H, H, a->precision == REGT_PREC_BF16);
+    k_copy_or_zero<<<cdiv(BN * H, 256), 256, 0, st>>>(a->d_hidden, L.G, BN * H, H, a->precision == REGT_PREC_BF16 || cell_f_usable(a));
     REGT_LAUNCHED("k_copy_or_zero", st);
     return 0;
   }

@@ -67,14 +67,21 @@ __global__ void __launch_bounds__(256) k_spmm_rows(const int32_t* __restrict__ r
 // through L2 -- 7.1 x 384 B per output row at config 5 against 768 B of DRAM traffic -- and runs L2-gather-bound; here
 // the L2 side shrinks to the block load plus the out-of-block neighbours.  Same sequential CSR order and the same fmaf
 // chain as k_spmm_rows: bit-identical results.
-constexpr int SPMM_BLK_THREADS = 768;
-__global__ void __launch_bounds__(SPMM_BLK_THREADS, 1) k_spmm_blk(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+// v2 (this round): the block's CSR slice (rowptr, col, val -- contiguous, because the rows are) is staged too, so the
+// edge loop has no dependent global loads (v1 read col/val per edge through L2: 2.67 ms at config 5, latency-bound, 0.28
+// of the HBM peak), and two CTAs share an SM so that one's block load overlaps the other's gather.
+constexpr int SPMM_BLK_THREADS = 512;
+constexpr int SPMM_EMAX = 2304;          // staged edges per block (more: the tail is read from global memory)
+__global__ void __launch_bounds__(SPMM_BLK_THREADS, 2) k_spmm_blk(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                                   const float* __restrict__ val, const float4* __restrict__ x,
                                                                   float4* __restrict__ y, int B, int n_out, int n_in, int W4, int NB,
                                                                   int nblk) {
   extern __shared__ __align__(128) uint8_t spmm_smem[];
   __shared__ uint64_t bar;
   float4* xs = reinterpret_cast<float4*>(spmm_smem);
+  int32_t* s_ptr = reinterpret_cast<int32_t*>(spmm_smem + (size_t)NB * W4 * 16);   // [NB + 1]
+  int32_t* s_col = s_ptr + ((NB + 1 + 3) & ~3);                                     // [SPMM_EMAX]
+  float* s_val = reinterpret_cast<float*>(s_col + SPMM_EMAX);                       // [SPMM_EMAX]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x == 0) {
     tc::mbar_init(&bar, 1);
@@ -83,6 +90,9 @@ __global__ void __launch_bounds__(SPMM_BLK_THREADS, 1) k_spmm_blk(const int32_t*
   __syncthreads();
   uint32_t phase = 0;
   for (long long item = blockIdx.x; item < (long long)B * nblk; item += gridDim.x) {
+    // items are ordered snapshot-major: the CTAs running side by side work on neighbouring node blocks of ONE snapshot, so
+    // an out-of-block neighbour row is (still) in L2 because the CTA next door staged it.  (Block-major order -- every
+    // snapshot of a block before the next block -- turned those gathers into DRAM reads: 3.17 ms against 2.67 ms.)
     const int b = (int)(item / nblk), blk = (int)(item - (long long)b * nblk);
     const int r0 = blk * NB, r1 = min(n_out, r0 + NB);
     const int s1 = min(n_in, r0 + NB);                       // staged node range [r0, s1)
@@ -93,16 +103,24 @@ __global__ void __launch_bounds__(SPMM_BLK_THREADS, 1) k_spmm_blk(const int32_t*
       const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + (size_t)r0 * W4);
       for (uint32_t o = 0; o < bytes; o += 32768) tc::bulk_g2s(spmm_smem + o, src + o, min(32768u, bytes - o), &bar);
     }
+    const int eb = __ldg(rowptr + r0), ee = __ldg(rowptr + r1);
+    for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_ptr[i] = __ldg(rowptr + r0 + i);
+    for (int i = threadIdx.x; i < min(ee - eb, SPMM_EMAX); i += blockDim.x) {
+      s_col[i] = __ldg(col + eb + i);
+      s_val[i] = __ldg(val + eb + i);
+    }
+    __syncthreads();
     tc::mbar_wait(&bar, phase);
     phase ^= 1;
     for (int r = r0 + warp; r < r1; r += nwarp) {
-      const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
+      const int e0 = s_ptr[r - r0] - eb, e1 = s_ptr[r - r0 + 1] - eb;
       float4* yr = y + ((size_t)b * n_out + r) * W4;
       for (int c = lane; c < W4; c += 32) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int e = e0; e < e1; ++e) {
-          const int j = __ldg(col + e);
-          const float w = __ldg(val + e);
+          const bool staged = e < SPMM_EMAX;
+          const int j = staged ? s_col[e] : __ldg(col + eb + e);
+          const float w = staged ? s_val[e] : __ldg(val + eb + e);
           const float4 v = (j >= r0 && j < s1) ? xs[(size_t)(j - r0) * W4 + c] : __ldg(xb + (size_t)j * W4 + c);
           acc.x = fmaf(w, v.x, acc.x);
           acc.y = fmaf(w, v.y, acc.y);
@@ -208,13 +226,15 @@ int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val
   // NB nodes = up to 192 KB of shared memory; small problems keep the plain warp-per-row kernel (less than one wave)
   static const bool no_blk = getenv("REGT_SPMM_PLAIN") && getenv("REGT_SPMM_PLAIN")[0] == '1';
   const int row_bytes = width * 4;
-  int NB = (192 * 1024) / row_bytes / 8 * 8;
+  const int meta_bytes = 2 * SPMM_EMAX * 4 + 64;
+  // two CTAs per SM: each gets half of the 227 KB, minus the staged CSR slice
+  int NB = ((227 * 1024) / 2 - 2048 - meta_bytes) / (row_bytes + 4) / 8 * 8;
   if (!no_blk && n_out <= n_in && NB >= 64 && (long long)B * n_out >= 4096 && ((uintptr_t)x % 16) == 0) {
     NB = min(NB, (n_out + 7) / 8 * 8);
     // balance the blocks of a snapshot (a short last block would idle an SM for most of a wave)
     const int nblk = cdiv(n_out, NB);
     NB = (cdiv(n_out, nblk) + 7) / 8 * 8;
-    const size_t smem = (size_t)NB * row_bytes;
+    const size_t smem = (size_t)NB * row_bytes + (size_t)((NB + 1 + 3) & ~3) * 4 + 2 * SPMM_EMAX * 4;
     static int sms = 0;
     if (sms == 0) {
       int dev = 0;
@@ -222,8 +242,8 @@ int launch_spmm_rows(const int32_t* rowptr, const int32_t* col, const float* val
     }
     REGT_CUDA(cudaFuncSetAttribute(k_spmm_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long items = (long long)B * nblk;
-    k_spmm_blk<<<(int)min(items, (long long)sms), SPMM_BLK_THREADS, smem, st>>>(rowptr, col, val, (const float4*)x, (float4*)y, B, n_out,
-                                                                              n_in, width / 4, NB, nblk);
+    k_spmm_blk<<<(int)min(items, 2ll * sms), SPMM_BLK_THREADS, smem, st>>>(rowptr, col, val, (const float4*)x, (float4*)y, B, n_out,
+                                                                         n_in, width / 4, NB, nblk);
     REGT_LAUNCHED("k_spmm_blk", st);
     return 0;
   }

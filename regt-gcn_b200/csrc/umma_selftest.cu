@@ -11,7 +11,9 @@ using namespace tc;
 // variant 1: K-major chunk   A[128][K], B[N][K]          (K = one MMA k-step: 8 tf32 / 16 bf16)
 // variant 2: MN-major SW128  A[K][128], B[K][N]          (contraction over the tile rows)
 // variant 3: MN-major: A SW128 [K][128], B chunk tile [K][N]
-// variant 4: MN-major SW128 with 32-byte swizzle atoms (descriptor layout 1)  A[K][128], B[K][N]   (32-bit elements)
+// variant 4: MN-major SW128 with 32-byte swizzle atoms (descriptor layout 1)  A[K][128], B[K][N]   (32-bit elements), SBO = 1024
+// variant 5: the same with SBO = 512: the 32-byte-atom swizzle repeats every FOUR 128-byte rows (CuTe's
+//            Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (1024 bits, 4 rows)), so consecutive K groups are 512 bytes apart
 template <int FMT>
 __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ D, int variant, int N, int K) {
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
   const int a_rows = mn ? K : 128, a_cols = mn ? 128 : K;   // tile rows / extent along the 128-byte direction
   const int b_rows = mn ? K : N, b_cols = mn ? N : K;
   const bool a_chunk = (variant == 1), b_chunk = (variant == 1 || variant == 3);
-  const bool b32 = (variant == 4);
+  const bool b32 = (variant == 4 || variant == 5);
   uint8_t* As = smem;
   uint8_t* Bs = smem + 64 * 1024;
 
@@ -63,9 +65,10 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
                      : make_desc(b0 + (kb >> 7) * b_rows * 128 + (kb & 127), 16, 1024, LAYOUT_SW128);
       } else {
         const uint32_t lay = b32 ? LAYOUT_SW128_B32 : LAYOUT_SW128;
-        da = make_desc(a0 + s * UK * 128, a_rows * 128, 1024, lay);
+        const uint32_t sbo = (variant == 5) ? 512 : 1024;
+        da = make_desc(a0 + s * UK * 128, a_rows * 128, sbo, lay);
         db = b_chunk ? make_desc(b0 + s * UK * 16, 128, b_rows * 16, LAYOUT_NONE)
-                     : make_desc(b0 + s * UK * 128, b_rows * 128, 1024, lay);
+                     : make_desc(b0 + s * UK * 128, b_rows * 128, sbo, lay);
       }
       umma<FMT>(tmem, da, db, idesc, s > 0 ? 1u : 0u);
     }
@@ -91,7 +94,7 @@ extern "C" int regt_debug_umma_selftest(int fmt, int variant, const float* A, co
   using namespace regt;
   cudaStream_t st = (cudaStream_t)stream;
   REGT_CHECK(fmt == 1 || fmt == 2, "selftest: fmt must be 1 (bf16) or 2 (tf32)");
-  REGT_CHECK(variant >= 0 && variant <= 4 && N % 32 == 0 && N >= 32 && N <= 128, "selftest: bad variant/N");
+  REGT_CHECK(variant >= 0 && variant <= 5 && N % 32 == 0 && N >= 32 && N <= 128, "selftest: bad variant/N");
   const size_t smem = 129 * 1024;
   if (fmt == 2) {
     REGT_CUDA(cudaFuncSetAttribute(k_umma_selftest<tc::FMT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

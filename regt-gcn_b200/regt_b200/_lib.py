@@ -35,7 +35,7 @@ class Params(C.Structure):
 class Args(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("O", C.c_int32),
                 ("mode", C.c_int32), ("precision", C.c_int32), ("accumulate", C.c_int32),
-                ("fuse_head", C.c_int32), ("x_rows", C.c_int32), ("loss_nodes", C.c_int32), ("_reserved", C.c_int32),
+                ("fuse_head", C.c_int32), ("x_rows", C.c_int32), ("loss_nodes", C.c_int32), ("inference", C.c_int32),
                 ("plan", GraphPlan),
                 ("x", vp), ("y", vp), ("h_ext", vp),
                 ("p", Params), ("g", Params),
@@ -145,6 +145,8 @@ def load() -> C.CDLL:
                                            vp, C.c_int64, vp, vp]
     lib.regt_debug_gemm_tn_multi.restype = C.c_int
     lib.regt_debug_gemm_tn_multi.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp]
+    lib.regt_debug_gemm_kt.restype = C.c_int
+    lib.regt_debug_gemm_kt.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp]
     lib.regt_debug_umma_selftest.restype = C.c_int
     lib.regt_debug_umma_selftest.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = lib

@@ -76,7 +76,7 @@ def build_state(mode: int, precision: int, plan: GraphPlanTensors, x: torch.Tens
                 params: Dict[str, torch.Tensor], y: Optional[torch.Tensor] = None,
                 h_ext: Optional[torch.Tensor] = None, head: bool = True,
                 workspace: Optional[torch.Tensor] = None, fuse_head: bool = False,
-                loss_nodes: Optional[int] = None) -> StepState:
+                loss_nodes: Optional[int] = None, inference: bool = False) -> StepState:
     """x [B,N,F,T] float32 CUDA.  Allocates outputs + workspace and fills ``regt_args``.
     Region shards (shard.py): x is [B,x_rows,F,T] with x_rows >= plan.N -- the plan's N owned rows
     followed by halo rows that only the plan's column indices address -- and ``loss_nodes`` is the
@@ -95,6 +95,7 @@ def build_state(mode: int, precision: int, plan: GraphPlanTensors, x: torch.Tens
     a.B, a.N, a.T, a.H, a.O = B, N, T, H, O
     a.mode, a.precision, a.accumulate = mode, precision, 0
     a.fuse_head = 1 if (fuse_head and head and y is not None) else 0
+    a.inference = 1 if inference else 0
     a.x_rows = x_rows
     a.loss_nodes = int(loss_nodes) if loss_nodes else 0
     a.plan = plan.c_struct()
@@ -221,4 +222,11 @@ class _ModelFn(torch.autograd.Function):
 def model_apply(mode: int, precision: int, plan: GraphPlanTensors, H: int, O: int, x: torch.Tensor,
                 params: Dict[str, torch.Tensor], h_ext: Optional[torch.Tensor] = None, head: bool = True):
     keys = keys_for(mode, head)
+    needs_grad = torch.is_grad_enabled() and (any(params[k].requires_grad for k in keys) or
+                                              (h_ext is not None and h_ext.requires_grad))
+    if not needs_grad:
+        # run.py:208-216 / predict.py:151-172 (torch.no_grad()): forward only -- the fused kernels keep no activations
+        st = build_state(mode, precision, plan, x, H, O, params, None, h_ext, head, inference=True)
+        run_forward(st, head)
+        return (st.out, st.out_hidden) if head else st.out_hidden
     return _ModelFn.apply(mode, precision, plan, H, O, keys, x, h_ext, *[params[k] for k in keys])

@@ -114,3 +114,22 @@ def test_reference_state_dict_keys():
     ref = "/root/reference/pretrained/occrate/RegionalTemporalGCN/model_in6_out1_epoch50.pt"
     if os.path.exists(ref):
         m.load_state_dict(torch.load(ref, map_location="cpu"), strict=True)
+
+
+def test_run_py_keeps_the_reference_flags():
+    """run.py:24-44 / SURVEY section 5: every flag of the reference's parser exists with the reference's default."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("regt_run", os.path.join(ROOT, "run.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ns = mod.build_parser().parse_args([])
+    ref_defaults = dict(seed=42, epochs=30, lr=1e-3, decay=1e-4, momentum=0.9, bs=32, tr=0.8, tf="available", edge_cut=None,
+                        dataset_path="./dataset", checkpoint_path="../checkpoints/", dataloading_type=2, decomp_type=None,
+                        num_timesteps_in=8, num_timesteps_out=4, model="TemporalGCN", is_preprocessed=False,
+                        is_pretrained=False, pretrained_model="", pretrained_model_epoch="0", logs=False)
+    for k, v in ref_defaults.items():
+        assert getattr(ns, k) == v, k
+    # the scripts' flag line parses (scripts/RegionalTemporalGCN.sh:1)
+    ns = mod.build_parser().parse_args("--num_timesteps_in 6 --num_timesteps_out 1 --tr 0.2 --tf occrate --dataloading_type 2 "
+                                       "--epochs 50 --decomp_type regional --model RegionalTemporalGCN".split())
+    assert (ns.num_timesteps_in, ns.num_timesteps_out, ns.tr, ns.tf, ns.epochs, ns.decomp_type) == (6, 1, 0.2, "occrate", 50, "regional")

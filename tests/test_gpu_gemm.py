@@ -146,3 +146,30 @@ def test_gemm_tn_tma_stage_reuse_stress(M, K, N, splits):
         _lib.check(rc, "regt_debug_gemm_tn_tma")
         assert float((Cp.double().sum(0) - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
         assert float((Cp2.double().sum(0) - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max())
+
+
+@pytest.mark.parametrize("H,ntile,splits", [(128, 5, 1), (128, 37, 4), (64, 9, 2), (128, 300, 37)])
+def test_gemm_kt_transposed_tiles(H, ntile, splits):
+    """the row contraction of the fused cell backward over transposed tiles (csrc/gemm_tma.cu k_gemm_kt): D^T [tile][4H][128],
+    h^T / (h*R)^T [tile][H][128], F^T [tile][32][128] -> dB_z|dB_r = [Dz|Dr]^T h, dB_h = Dc^T hR, D^T F for all four blocks."""
+    from regt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(H + ntile)
+    AT = (torch.rand(ntile, 4 * H, 128, generator=g) - 0.5).cuda()
+    B0T = (torch.rand(ntile, H, 128, generator=g) - 0.5).cuda()
+    B1T = (torch.rand(ntile, H, 128, generator=g) - 0.5).cuda()
+    FT = (torch.rand(ntile, 32, 128, generator=g) - 0.5).cuda()
+    C0 = torch.full((splits, 2 * H, H), float("nan"), device="cuda")
+    C1 = torch.full((splits, H, H), float("nan"), device="cuda")
+    C2 = torch.full((splits, 4 * H, 32), float("nan"), device="cuda")
+    rc = lib.regt_debug_gemm_kt(AT.data_ptr(), ntile, H, B0T.data_ptr(), B1T.data_ptr(), FT.data_ptr(), C0.data_ptr(), C1.data_ptr(),
+                                C2.data_ptr(), splits, _st())
+    _lib.check(rc, "regt_debug_gemm_kt")
+    torch.cuda.synchronize()
+    A, B0, B1, Fm = AT.double(), B0T.double(), B1T.double(), FT.double()
+    ref0 = torch.einsum("tkr,tnr->kn", A[:, :2 * H], B0)
+    ref1 = torch.einsum("tkr,tnr->kn", A[:, 2 * H:3 * H], B1)
+    ref2 = torch.einsum("tkr,tnr->kn", A, Fm)
+    assert relerr(C0.double().sum(0), ref0) <= 1e-5
+    assert relerr(C1.double().sum(0), ref1) <= 1e-5
+    assert relerr(C2.double().sum(0), ref2) <= 1e-5

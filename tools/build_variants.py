@@ -18,6 +18,10 @@ VARIANTS = {
     "bwd_early_only": ["REGT_FWD_PIPE=0", "REGT_BWD_H_UNDER_M2=0"],
     "cw16": ["REGT_CW=16"],
     "cw16_nopipe": ["REGT_CW=16"] + NOPIPE,
+    # round 2, fused 3xTF32 cell (cell_f.cu)
+    "fpre": ["REGT_F_PRE=1"],
+    "tn2": ["REGT_TN_GROUP=2"],      # row contraction: drain the TMEM accumulator every 2 chunks (24 MMAs) instead of 8
+    "tn4": ["REGT_TN_GROUP=4"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
