@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(128) k_wgrad_m1_pm(const float* __restrict__ d
     }
   }
 }
-// transposed variant (planes of cell_f.cu v2): dhp lives in D^T tiles [tp][4H][128 rows] (tp = t * nqt + qt), Ut is period
+// transposed variant (planes of cell_f.cu): dhp lives in D^T tiles [tp][4 row quarters][4H][32 rows] (tp = t * nqt + qt), Ut is period
 // major.  Lanes run along the SEGMENTS of a region (= consecutive nodes = consecutive rows of a tile: 128-byte lines of every
 // D^T column), a warp owns NPW gate columns, a thread keeps NPW x F running sums over all its rows and the 32 row lanes
 // are summed once per chunk (butterfly, fixed order).  Chunk = (region, group of bper snapshots): part[chunk][H][F].
@@ -549,17 +549,17 @@ __global__ void __launch_bounds__(512) k_wgrad_m1_kt(const float* __restrict__ D
         const int s = __ldg(rseg_list + si);
         const long long q = (long long)b * N + __ldg(seg_node + s);
         const int qt = (int)(q >> 7), rr = (int)(q & 127);
-        const float* dcol = DT + ((size_t)qt * Ktot + col0 + n0) * 128 + rr;
+        const float* dcol = DT + (((size_t)qt * 4 + (rr >> 5)) * Ktot + col0 + n0) * 32 + (rr & 31);   // [tp][row quarter][col][32 rows]
         const float* urow = Ut + ((size_t)b * nseg + s) * F;
 #pragma unroll 2
         for (int t = 0; t < T; ++t) {
           const float4 ua = __ldg(reinterpret_cast<const float4*>(urow + (size_t)t * B * nseg * F));
           const float4 ub = __ldg(reinterpret_cast<const float4*>(urow + (size_t)t * B * nseg * F) + 1);
           const float u[F] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
-          const float* dp = dcol + (size_t)t * nqt * Ktot * 128;
+          const float* dp = dcol + (size_t)t * nqt * 4 * Ktot * 32;
           float d[NPW];
 #pragma unroll
-          for (int k = 0; k < NPW; ++k) d[k] = __ldg(dp + (size_t)k * 128);
+          for (int k = 0; k < NPW; ++k) d[k] = __ldg(dp + (size_t)k * 32);
 #pragma unroll
           for (int k = 0; k < NPW; ++k)
 #pragma unroll

@@ -32,11 +32,26 @@
 // build-time switch (tools/build_variants.py, A/B on B200): 1 = h of the next step is computed under the candidate MMAs and
 // waits in registers (32 more live registers per epilogue thread), 0 = computed after them
 #ifndef REGT_F_PRE
-#define REGT_F_PRE 0
+#define REGT_F_PRE 1
+#endif
+// timing experiments only (results are wrong with either): what the recompute of h and the E0 stores cost
+#ifndef REGT_F_BULKSTORE
+#define REGT_F_BULKSTORE 0     // 1: backward planes leave through shared-memory slots + cp.async.bulk (measured slower, see WarpStore)
+#endif
+#ifndef REGT_XP_SKIP_H16
+#define REGT_XP_SKIP_H16 0
+#endif
+#ifndef REGT_XP_SKIP_E0_STORES
+#define REGT_XP_SKIP_E0_STORES 0
 #endif
 
 namespace regt {
 using namespace tc;
+
+// phase timestamps of CTA 0 / epilogue thread 0 (REGT_F_DEBUG=1; read back with regt_debug_f_timestamps): 16 steps x 12 marks
+__device__ long long g_f_dbg[2][16 * 12];
+#define F_TS(which, i)                                                                        \
+  if (a.dbg && blockIdx.x == 0 && tid == 0 && s >= a.dbg && s < a.dbg + 16) g_f_dbg[which][(s - a.dbg) * 12 + (i)] = clock64();
 
 namespace {
 constexpr int F = REGT_F;
@@ -87,10 +102,11 @@ struct FArgs {
   const uint8_t* img;
   float *Zp, *Rp, *Hcp;            // saved planes, tile layout [T][nqt][H/4][128][4]
   float* out_hidden;               // [BN][H]
+  int dbg;                         // 0: off; k > 0: record the phase timestamps of steps [k, k + 16) of CTA 0
   int save;                        // 0: forward only -- Z goes to a per-CTA scratch tile (Zp = [grid][128][H]), R and H~ nowhere
   // backward
   const float* G;                  // gradient wrt out_hidden, tile layout [nqt][H/4][128][4] (the head writes it that way)
-  float *D, *hpl, *hRpl;           // transposed tiles [T*nqt][4H][128], [T*nqt][H][128], [T*nqt][H][128]
+  float *D, *hpl, *hRpl;           // transposed tiles [T*nqt][4 row quarters][4H | H | H][32 rows]
   double* dpp;                     // [grid][T] attention-gradient partials
 };
 
@@ -129,17 +145,6 @@ __device__ __forceinline__ void st_f32x16(uint32_t taddr, const float (&v)[16]) 
   tmem_st16(taddr, u);
 }
 
-__device__ __forceinline__ float ld_own1(const float* p) {
-  float v;
-  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-// re-read of a 16-byte piece this thread stored earlier in the kernel (plain coherent load, never the read-only path)
-__device__ __forceinline__ float4 ld_own4(const void* p) {
-  float4 v;
-  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
 // byte offset of the 16-byte piece holding columns [c, c+4) of row r inside a saved-plane tile [H/4][128][4]
 __device__ __forceinline__ size_t piece(int r, int c) { return ((size_t)(c >> 2) * TC_ROWS + r) * 16; }
 
@@ -299,6 +304,17 @@ __device__ __forceinline__ void mma_spart(uint32_t tmem, uint32_t acc_col, uint3
   __syncwarp();
 }
 
+// F-wide features of one (tile, period) -> L2: 128 rows x 32 bytes of X_t (and S_t, and U_t where every node has exactly one
+// regional segment in node order, as in the regional decomposition) are contiguous runs of the period-major arrays
+__device__ __forceinline__ void prefetch_feats(const FArgs& a, int t, int qt) {
+  const long long q0 = (long long)qt * TC_ROWS;
+  const int rows = (int)min((long long)TC_ROWS, (long long)a.BN - q0);
+  if (rows <= 0) return;
+  const uint32_t bytes = (uint32_t)rows * F * 4;
+  bulk_prefetch_l2(a.Xt + ((size_t)t * a.BN + q0) * F, bytes);
+  bulk_prefetch_l2(a.St + ((size_t)t * a.BN + q0) * F, bytes);
+  if (a.nseg == a.N) bulk_prefetch_l2(a.Ut + ((size_t)t * a.BN + q0) * F, bytes);   // segment of node n = n: same row order as X
+}
 // weight-stage producer: cycles the NSTEP stages of the image for every (tile, period) of this CTA
 template <int HH>
 __device__ __forceinline__ void produce(const uint8_t* img, uint8_t* ring, uint64_t* bar_full, uint64_t* bar_empty, long long total) {
@@ -434,8 +450,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
       uint8_t* rt = reinterpret_cast<uint8_t*>(a.Rp) + toff;
       uint8_t* ct = reinterpret_cast<uint8_t*>(a.Hcp) + toff;
       // ---- E1z: update gate (runs while the r-gate MMAs are in flight) ----
+      F_TS(0, 0)
       mbar_wait(&bar_z, ph);
       tc_fence_after();
+      F_TS(0, 1)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16], h[16];
@@ -450,8 +468,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
         for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(zt + piece(r, c0 + j + i)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
       // ---- E1r: reset gate, h*R -> A operand of the candidate GEMM ----
+      F_TS(0, 2)
       mbar_wait(&bar_r, ph);
       tc_fence_after();
+      F_TS(0, 3)
 #pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
         float v[16], h[16];
@@ -471,24 +491,32 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_a2);
+      F_TS(0, 4)
 #if REGT_F_PRE
       if (s + 1 < S) Pcompute(s + 1);      // under the candidate MMAs (h of the next step waits in registers)
 #endif
       // ---- candidate GEMM done: A is free -> h of the next step goes in first (its z-gate MMAs start), then E2 under them ----
+      F_TS(0, 5)
       mbar_wait(&bar_c, ph);
       tc_fence_after();
+      F_TS(0, 6)
 #if !REGT_F_PRE
       if (s + 1 < S) Pcompute(s + 1);
 #endif
       if (s + 1 < S) Pstore();
+      F_TS(0, 7)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
+        float4 zq[4];
+        // Z of this chunk: this thread's own stores of E1z, re-read with ordinary (coherent) loads -- all four issued before
+        // any is used (one asm-volatile load per use serialised four L2 round trips per chunk: 2.4 us per step)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) zq[i] = *reinterpret_cast<const float4*>(zt + piece(r, c0 + j + 4 * i));
         tmem_ld16(tR + c0 + j, v);
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 z = ld_own4(zt + piece(r, c0 + j + i));   // this thread's own store above
-          const float zz[4] = {z.x, z.y, z.z, z.w};
+          const float zz[4] = {zq[i >> 2].x, zq[i >> 2].y, zq[i >> 2].z, zq[i >> 2].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float hc = tanh_(v[i + e] + consts[C::C_CC + c0 + j + i + e]);
@@ -500,6 +528,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
       }
       tc_fence_before();
       mbar_arrive(&bar_cfree);
+      F_TS(0, 8)
       if (t + 1 == a.T) {   // item done: out_hidden = sum_t probs[t] H'_t
         if (q_cur < a.BN) {
           float* o = a.out_hidden + (size_t)q_cur * HH + c0;
@@ -540,7 +569,25 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     }
     tc_fence_before();
   } else if (warp == W_PROD && lane == 0) {
-    produce<HH>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
+    // weight stages, and two steps ahead of them the F-wide features of the coming (tile, period) into L2
+    auto pf = [&](int s) {
+      const int k = s / a.T, t = s - k * a.T;
+      prefetch_feats(a, t, (int)blockIdx.x + k * (int)gridDim.x);
+    };
+    if (S > 0) pf(0);
+    if (S > 1) pf(1);
+    long long gs = 0;
+    for (int s = 0; s < S; ++s) {
+      if (s + 2 < S) pf(s + 2);
+      for (int i = 0; i < C::NSTEP; ++i, ++gs) {
+        const int st = (int)(gs % C::NS);
+        if (gs >= C::NS) mbar_wait(&bar_empty[st], (uint32_t)((gs / C::NS - 1) & 1));
+        mbar_arrive_expect_tx(&bar_full[st], C::STAGE);
+        const uint8_t* src = a.img + (size_t)i * C::STAGE;
+#pragma unroll
+        for (int o = 0; o < C::STAGE; o += 16384) bulk_g2s(ring + (size_t)st * C::STAGE + o, src + o, 16384, &bar_full[st]);
+      }
+    }
   }
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, C::TCOLS);
@@ -553,18 +600,59 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 // plane touches 32 different 128-byte lines.  v0 did exactly that (65 us per (tile, period): 32 LSU wavefronts and 32
 // half-written sectors per store instruction), v1 transposed through per-warp shared-memory staging tiles (40 us, LSU pipe
 // 61 % busy).  v2 (this one) stores what the weight-gradient contraction reads TRANSPOSED, per (tile, period):
-//     DT [tp][4H][128]   hT, hRT [tp][H][128]        (tp = t * nqt + qt; 128 = the rows of the tile)
-// Lane = row makes every store of one column a contiguous 128-byte line, no staging at all -- and a [column][row] tile is
-// exactly the K-major operand the row contraction wants (K = rows): gemm_tma.cu reads these tiles with plain TMA boxes and
-// no transposing converters.
+//     DT [tp][4 row quarters][4H][32]   hT, hRT [tp][4][H][32]        (tp = t * nqt + qt; quarter = 32 rows = one warp's lanes)
+// Lane = row makes every store of one column a contiguous 128-byte line -- and a [column][row] tile is exactly the K-major
+// operand the row contraction wants (K = rows): gemm_tma.cu reads these tiles with plain TMA boxes and no transposing
+// converters.  v2 issued those lines as 192 scalar st.global per thread and step: 8.5 of the 17.7 us of phase E0 were spent
+// stalled on the store path (timing experiment REGT_XP_SKIP_E0_STORES, tools/f_phases.py).  v3: the 16 columns x 32 rows a
+// warp produces per chunk are one contiguous 2 KB run of this layout; the lanes put them into a per-warp shared-memory
+// slot (conflict-free 4-byte stores) and one lane hands the slot to the bulk-copy engine (cp.async.bulk shared -> global),
+// which drains it while the warp computes on.
 template <int HH>
 struct BCfg {   // shared-memory plan of the backward: ring | resident tail | M1 cache
   using C = FCfg<HH>;
-  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C;
+  static constexpr int SLOT = 16 * 32 * 4;                        // one staged chunk: 16 columns x 32 rows
+  static constexpr int NSLOT = 2;                                 // per warp (the copy engine reads one while the lanes fill the other)
+  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C + (REGT_F_BULKSTORE ? NEPI_W * NSLOT * SLOT : 0);
   static constexpr int NS_FIT = (SMEM_MAX - 12288 - FIXED) / C::STAGE;
   static constexpr int NS = NS_FIT < 2 * C::NSTEP ? NS_FIT : 2 * C::NSTEP;
   static constexpr int SMEM = 1024 + NS * C::STAGE + FIXED;
   static_assert(NS >= 3, "backward ring too shallow");
+};
+
+// one warp's chunk (16 columns x its 32 rows) -> global through the bulk-copy engine.  v[i] = this lane's value of column i.
+struct WarpStore {
+  float* slot0;      // this warp's NSLOT staging slots
+  int n;             // stores issued so far
+  __device__ __forceinline__ void put(int lane, float* dst, const float (&v)[16]) {
+#if !REGT_F_BULKSTORE
+    // plain stores: one 128-byte line per column.  Measured against the staged bulk stores below (tools/f_phases.py, config 4):
+    // 29.8 us per backward step vs 33.3 us -- with two slots per warp a put waits ~0.7 us for the copy engine to have read the
+    // slot used two puts ago, and shared memory has no room for more slots
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dst[i * 32 + lane] = v[i];
+    return;
+#endif
+    float* sl = slot0 + (n & 1) * (16 * 32);
+    if (lane == 0) bulk_wait_read<1>();       // the store that used this slot two puts ago has read it
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sl[i * 32 + lane] = v[i];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(dst, sl, 16 * 32 * 4);
+      bulk_commit();
+    }
+    ++n;
+  }
+  // all stores of this warp have landed (and are visible to its lanes): before re-reading them, and before the kernel ends
+  __device__ __forceinline__ void drain(int lane) {
+#if REGT_F_BULKSTORE
+    if (lane == 0) bulk_wait<0>();
+#endif
+    __syncwarp();
+  }
 };
 
 template <int HH, int NS>
@@ -616,6 +704,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   uint8_t* ring = sm;
   uint8_t* tail = ring + NS * C::STAGE;
   float* m1data = reinterpret_cast<float*>(tail + ((C::TAIL + 1023) & ~1023));
+  float* slots = m1data + C::M1C / 4;
   __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
   __shared__ uint32_t tmem_base_s;
   __shared__ int m1tag[4];
@@ -658,6 +747,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
     const uint32_t t1c = tl + 2 * HH, t2c = tl + 3 * HH;   // acc1 = dHR (then dHR * R), acc2 = p G Z + dhg
     Row ri;
     const M1Cache mc{m1data, m1tag};
+    WarpStore ws{slots + warp * (BC::NSLOT * BC::SLOT / 4), 0};
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       const int k = s / a.T, t = s - k * a.T;
@@ -673,11 +763,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       const uint8_t* rt = reinterpret_cast<const uint8_t*>(a.Rp) + toff;
       const uint8_t* ct = reinterpret_cast<const uint8_t*>(a.Hcp) + toff;
       const uint8_t* gt = reinterpret_cast<const uint8_t*>(a.G) + (size_t)qt * (size_t)(TC_ROWS * HH * 4);   // G tile of this item
-      // transposed outputs of this (tile, period): element (column c, row r) at c * 128 + r
-      float* DT = a.D + tp * (size_t)(4 * HH * TC_ROWS) + r;
-      float* hT = a.hpl + tp * (size_t)(HH * TC_ROWS) + r;
-      float* hRT = a.hRpl + tp * (size_t)(HH * TC_ROWS) + r;
+      // transposed outputs of this (tile, period), this warp's row quarter: column c at c * 32 (+ lane)
+      float* DT = a.D + (tp * 4 + qd) * (size_t)(4 * HH * 32);
+      float* hT = a.hpl + (tp * 4 + qd) * (size_t)(HH * 32);
+      float* hRT = a.hRpl + (tp * 4 + qd) * (size_t)(HH * 32);
       // ---- E0: recompute h; gate gradients from the saved planes ----
+      F_TS(1, 0)
       Feats f;
       load_feats(a, ri, t, f);
       float dz[CWF];
@@ -685,8 +776,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       unsigned int neg = 0u;                     // h <= 0 per column (leaky_relu slope of the regional combine)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
-        float h[16], dc[16], gz[16];
+        float h[16], dc[16], gz[16], hr[16];
+#if REGT_XP_SKIP_H16
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = consts[C::C_C0 + c0 + j + i] + f.x[i & 7];
+#else
         h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
+#endif
+        if (j == 0) { F_TS(1, 9) }
         float dpc = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
@@ -706,20 +803,31 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
             dz[j + i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
             dc[i + e] = gg * (1.0f - z[e]) * (1.0f - hc[e] * hc[e]);
             gz[i + e] = gg * z[e];
-            hT[(size_t)(c + e) * TC_ROWS] = hh;
-            hRT[(size_t)(c + e) * TC_ROWS] = hh * rg[e];
-            DT[(size_t)(c + e) * TC_ROWS] = dz[j + i + e];
-            DT[(size_t)(2 * HH + c + e) * TC_ROWS] = dc[i + e];
+            hr[i + e] = hh * rg[e];
             if (!(hh > 0.f)) neg |= 1u << (j + i + e);
           }
         }
         dp += (double)dpc;
+        if (j == 0) { F_TS(1, 10) }
         put_a16<HH>(tl, c0 + j, dc);
         st_f32x16(t2c + c0 + j, gz);              // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
+#if !REGT_XP_SKIP_E0_STORES
+        ws.put(lane, hT + (size_t)(c0 + j) * 32, h);
+        ws.put(lane, hRT + (size_t)(c0 + j) * 32, hr);
+        ws.put(lane, DT + (size_t)(2 * HH + c0 + j) * 32, dc);
+        {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+          ws.put(lane, DT + (size_t)(c0 + j) * 32, v);
+        }
+#endif
+        if (j == 0) { F_TS(1, 11) }
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_a);
+      F_TS(1, 1)
       // attention gradient d probs[t] += sum G * H'_t.  The softmax Jacobian takes differences of these nearly equal sums
       // (models/RegionalTemporalGCN.py:134), so everything above 16 terms is summed in fp64: fixed-order warp sum, one
       // shared-memory slot per (warp, period)
@@ -729,6 +837,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       // ---- M1 done (dHR in acc1): Dz -> A, M2z starts ----
       mbar_wait(&bar_1, ph);
       tc_fence_after();
+      F_TS(1, 2)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
@@ -739,31 +848,38 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_az);
+      F_TS(1, 3)
       // ---- E1 (under M2z): Dr = dHR h R (1-R) (registers, reusing dz), t1 = dHR R -> acc1 in place ----
+      ws.drain(lane);     // the h tiles of E0 have landed: they are re-read below with ordinary loads
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
-        float v[16];
+        float v[16], hh[16], dr[16];
+        float4 rq[4];
+        // h (this warp's own bulk stores of E0) and R of the chunk, all in flight before the first use
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hh[i] = hT[(size_t)(c0 + j + i) * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rq[i] = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c0 + j + 4 * i)));
         tmem_ld16(t1c + c0 + j, v);
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const int c = c0 + j + i;
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
-          const float rg[4] = {r4.x, r4.y, r4.z, r4.w};
+          const float rg[4] = {rq[i >> 2].x, rq[i >> 2].y, rq[i >> 2].z, rq[i >> 2].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float hh = ld_own1(hT + (size_t)(c + e) * TC_ROWS);        // this thread's own store in E0
-            const float dr = v[i + e] * hh * rg[e] * (1.0f - rg[e]);
-            dz[j + i + e] = dr;
-            DT[(size_t)(HH + c + e) * TC_ROWS] = dr;
+            dr[i + e] = v[i + e] * hh[i + e] * rg[e] * (1.0f - rg[e]);
+            dz[j + i + e] = dr[i + e];
             v[i + e] *= rg[e];
           }
         }
         st_f32x16(t1c + c0 + j, v);
+        ws.put(lane, DT + (size_t)(HH + c0 + j) * 32, dr);
       }
       tmem_st_wait();
+      F_TS(1, 4)
       // ---- M2z done (A free): Dr -> A, M2r ----
       mbar_wait(&bar_2z, ph);
       tc_fence_after();
+      F_TS(1, 5)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
@@ -774,9 +890,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_ar);
+      F_TS(1, 6)
       // ---- E2: d h_pre = act'(h) (p G Z + dhg + dHR R) ----
       mbar_wait(&bar_2r, ph);
       tc_fence_after();
+      F_TS(1, 7)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16], u[16];
@@ -786,11 +904,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
         for (int i = 0; i < 16; ++i) {
           float d = v[i] + u[i];
           if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i)) & 1u)) d *= 0.01f;
-          DT[(size_t)(3 * HH + c0 + j + i) * TC_ROWS] = d;
+          v[i] = d;
         }
+        ws.put(lane, DT + (size_t)(3 * HH + c0 + j) * 32, v);
       }
       tc_fence_before();
+      F_TS(1, 8)
     }
+    ws.drain(lane);
   } else if (warp == W_MMA) {
     const uint32_t ring0 = smem_u32(ring);
     long long gs = 0;
@@ -814,7 +935,32 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
     }
     tc_fence_before();
   } else if (warp == W_PROD && lane == 0) {
-    produce_n<HH, NS>(a.img, ring, bar_full, bar_empty, (long long)S * C::NSTEP);
+    // weight stages, and one step ahead of them the saved-plane tiles of the NEXT step into L2: the epilogue threads read
+    // Z, R, H~ (and G once per item) with ordinary loads, which would otherwise wait out a DRAM round trip per 16-column chunk
+    constexpr uint32_t TB = TC_ROWS * HH * 4;
+    auto prefetch_step = [&](int s) {
+      const int k = s / a.T, t = s - k * a.T;
+      const int qt = (int)blockIdx.x + k * (int)gridDim.x;
+      const size_t toff = ((size_t)t * a.nqt + qt) * (size_t)TB;
+      bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.Zp) + toff, TB);
+      bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.Rp) + toff, TB);
+      bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.Hcp) + toff, TB);
+      if (t == 0) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.G) + (size_t)qt * TB, TB);
+      prefetch_feats(a, t, qt);
+    };
+    if (S > 0) prefetch_step(0);
+    long long gs = 0;
+    for (int s = 0; s < S; ++s) {
+      if (s + 1 < S) prefetch_step(s + 1);
+      for (int i = 0; i < C::NSTEP; ++i, ++gs) {
+        const int st = (int)(gs % NS);
+        if (gs >= NS) mbar_wait(&bar_empty[st], (uint32_t)((gs / NS - 1) & 1));
+        mbar_arrive_expect_tx(&bar_full[st], C::STAGE);
+        const uint8_t* src = a.img + (size_t)i * C::STAGE;
+#pragma unroll
+        for (int o = 0; o < C::STAGE; o += 16384) bulk_g2s(ring + (size_t)st * C::STAGE + o, src + o, 16384, &bar_full[st]);
+      }
+    }
   }
   __syncthreads();
   if (tid < a.T) {
@@ -883,7 +1029,7 @@ __global__ void k_pack_f(const float* __restrict__ Wzr, const float* __restrict_
   }
 }
 
-// F^T tiles of the weight-gradient contraction, [tp][32][128]: rows 0..7 = S_t, 8..15 = X_t, 16 = 1, 17..31 = 0 of the 128 rows
+// F^T tiles of the weight-gradient contraction, [tp][4 row quarters][32][32 rows]: rows 0..7 = S_t, 8..15 = X_t, 16 = 1, 17..31 = 0 of the 128 rows
 // of tile tp = t * nqt + qt (padded rows q >= BN: all zero).  One thread per (tile, row): its 32-byte S and X rows are
 // contiguous across the warp, every store of one feature is a 128-byte line.
 __global__ void __launch_bounds__(128) k_featT_f(const float* __restrict__ Xt, const float* __restrict__ St, int BN, int nqt,
@@ -895,15 +1041,15 @@ __global__ void __launch_bounds__(128) k_featT_f(const float* __restrict__ Xt, c
   float s[8], x[8];
   load8(St + ((size_t)t * BN + (ok ? q : 0)) * F, s, ok ? 1.f : 0.f);
   load8(Xt + ((size_t)t * BN + (ok ? q : 0)) * F, x, ok ? 1.f : 0.f);
-  float* o = FT + (size_t)tp * 32 * TC_ROWS + r;
+  float* o = FT + ((size_t)tp * 4 + (r >> 5)) * (32 * 32) + (r & 31);      // [tp][row quarter][32 features][32 rows]
 #pragma unroll
   for (int f = 0; f < 8; ++f) {
-    o[(size_t)f * TC_ROWS] = s[f];
-    o[(size_t)(8 + f) * TC_ROWS] = x[f];
+    o[(size_t)f * 32] = s[f];
+    o[(size_t)(8 + f) * 32] = x[f];
   }
-  o[(size_t)16 * TC_ROWS] = ok ? 1.f : 0.f;
+  o[(size_t)16 * 32] = ok ? 1.f : 0.f;
 #pragma unroll
-  for (int f = 17; f < 32; ++f) o[(size_t)f * TC_ROWS] = 0.f;
+  for (int f = 17; f < 32; ++f) o[(size_t)f * 32] = 0.f;
 }
 // the head's weight-gradient contraction (head.cu) takes its bias column sums from a ones column: Feat [BNp][32], column 16
 __global__ void __launch_bounds__(256) k_ones_f(int BN, int BNp, float* __restrict__ Feat) {
@@ -925,6 +1071,10 @@ FArgs make_fargs(const regt_args* a, const Layout& L) {
   k.Zp = L.Zp; k.Rp = L.Rp; k.Hcp = L.Hcp;
   k.out_hidden = a->out_hidden;
   k.save = a->inference ? 0 : 1;
+  {
+    const char* e = getenv("REGT_F_DEBUG");
+    k.dbg = e ? atoi(e) : 0;
+  }
   k.G = L.G; k.D = L.D; k.hpl = L.h; k.hRpl = L.hR; k.dpp = reinterpret_cast<double*>(L.tc_dpp);
   return k;
 }
@@ -998,3 +1148,10 @@ int launch_feat_f(const regt_args* a, const Layout& L, cudaStream_t st) {
 }
 
 }  // namespace regt
+
+// TEST HOOK: phase timestamps (clock64) of the fused kernels, recorded when REGT_F_DEBUG=<first step> is set:
+// out[which][step][mark], which 0 = forward, 1 = backward, 16 steps x 12 marks each
+extern "C" int regt_debug_f_timestamps(long long* out) {
+  REGT_CUDA(cudaMemcpyFromSymbol(out, regt::g_f_dbg, sizeof(long long) * 2 * 16 * 12));
+  return 0;
+}

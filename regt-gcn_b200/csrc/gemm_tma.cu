@@ -573,9 +573,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn_tma(const __grid_cons
 // converters only split fp32 -> tf32 hi / lo at the SAME swizzled offset (one 128-bit load and two 128-bit stores per 16
 // bytes -- gemm_tn's transposing converters issue eight 4-byte stores for them and keep the LSU pipe 61 % busy).  MMA issue,
 // accumulator draining and the output format are gemm_tn's.
-//   A^T : [ntile * Ktot][128]   tile-major, Ktot = 4H columns per tile           (segments of 128 columns as in gemm_tn)
-//   B^T : [ntile * N][128]      N <= 128 columns per tile (h or h*R)
-//   F^T : [ntile * 32][128]
+//   A^T : [ntile][4 row quarters][Ktot][32 rows]   Ktot = 4H columns per tile    (segments of 128 columns as in gemm_tn)
+//   B^T : [ntile][4][N][32]                        N <= 128 columns per tile (h or h*R)
+//   F^T : [ntile][4][32][32]
+// (a chunk = one row quarter of a tile: the 32 rows a warp of the producing kernel owns)
 // ------------------------------------------------------------------------------------------
 struct KtArgs {
   CUtensorMap ta, tb[2], tf;
@@ -763,9 +764,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_kt(const __grid_constant
         const long long tile = t0 + kc / 4;
         const int k0 = (kc & 3) * KC;
         mbar_arrive_expect_tx(&bar_raw[rs], bytes);
-        tma_2d(rw, &a.ta, k0, (int)(tile * a.Ktot + kg), &bar_raw[rs]);
-        if (sb >= 0) tma_2d(rw + TILE, &a.tb[sb], k0, (int)(tile * a.N), &bar_raw[rs]);
-        if (n2) tma_2d(rw + 2 * TILE, &a.tf, k0, (int)(tile * 32), &bar_raw[rs]);
+        const long long tq = tile * 4 + (k0 >> 5);      // (tile, row quarter)
+        tma_2d(rw, &a.ta, 0, (int)(tq * a.Ktot + kg), &bar_raw[rs]);
+        if (sb >= 0) tma_2d(rw + TILE, &a.tb[sb], 0, (int)(tq * a.N), &bar_raw[rs]);
+        if (n2) tma_2d(rw + 2 * TILE, &a.tf, 0, (int)(tq * 32), &bar_raw[rs]);
       }
     }
   }
@@ -860,16 +862,16 @@ int launch_gemm_tn_tma(const float* A, long long lda, long long M, int Ktot, int
   return 0;
 }
 
-// the row contraction over transposed tiles (k_gemm_kt): AT [ntile * Ktot][128], BTs[b] [ntile * N][128], FT [ntile * 32][128];
+// the row contraction over transposed tiles (k_gemm_kt): AT [ntile][4][Ktot][32], BTs[b] [ntile][4][N][32], FT [ntile][4][32][32];
 // segment boundaries are multiples of 128 columns except the end of the last segment with an operand (H = 64: [Dc | dhp])
 int launch_gemm_kt(const float* AT, long long ntile, int Ktot, int nseg, const int* seg_k0, const int* seg_k1, const int* seg_b,
                    float* const* seg_C, const float* const* BTs, int N, int splits, const float* FT, float* C2, long long c2_split,
                    cudaStream_t st) {
   REGT_CHECK(AT && nseg >= 1 && nseg <= 4 && Ktot % 128 == 0 && N % 8 == 0 && N >= 16 && N <= 128 && splits > 0 && ntile > 0 && FT && C2,
              "gemm_kt: bad shape (Ktot=%d N=%d)", Ktot, N);
-  REGT_CHECK(ntile * Ktot < (1ll << 31), "gemm_kt: tile count overflows the TMA coordinate");
+  REGT_CHECK(ntile * 4 * Ktot < (1ll << 31), "gemm_kt: tile count overflows the TMA coordinate");
   KtArgs a{};
-  if (tmap_2d(&a.ta, AT, 128, ntile * Ktot, 128, 128, "gemm_kt(A^T)")) return -1;
+  if (tmap_2d(&a.ta, AT, 32, ntile * 4 * Ktot, 32, 128, "gemm_kt(A^T)")) return -1;
   for (int s = 0; s < nseg; ++s) {
     a.seg[s].k0 = seg_k0[s];
     a.seg[s].k1 = seg_k1[s];
@@ -881,9 +883,9 @@ int launch_gemm_kt(const float* AT, long long ntile, int Ktot, int nseg, const i
   for (int b = 0; b < 2; ++b) {
     bool used = false;
     for (int s = 0; s < nseg; ++s) used |= seg_b[s] == b;
-    if (used && tmap_2d(&a.tb[b], BTs[b], 128, ntile * N, 128, N, "gemm_kt(B^T)")) return -1;
+    if (used && tmap_2d(&a.tb[b], BTs[b], 32, ntile * 4 * N, 32, N, "gemm_kt(B^T)")) return -1;
   }
-  if (tmap_2d(&a.tf, FT, 128, ntile * 32, 128, 32, "gemm_kt(F^T)")) return -1;
+  if (tmap_2d(&a.tf, FT, 32, ntile * 4 * 32, 32, 32, "gemm_kt(F^T)")) return -1;
   a.nseg = nseg;
   a.C2 = C2;
   a.c2_split = c2_split > 0 ? c2_split : (long long)Ktot * 32;
@@ -930,7 +932,7 @@ extern "C" int regt_debug_gemm_tn_multi(const float* A, int64_t lda, int64_t M, 
   const long long lds[2] = {H, H};
   return regt::launch_gemm_tn_tma(A, lda, M, 4 * H, 3, k0, sb, cs, bs, lds, H, splits, B2, 32, C2, 0, (cudaStream_t)stream, 0);
 }
-// the transposed-tile form used by the fused cell backward: AT [ntile][4H][128]; B0T, B1T [ntile][H][128]; FT [ntile][32][128]
+// the transposed-tile form used by the fused cell backward: AT [ntile][4][4H][32]; B0T, B1T [ntile][4][H][32]; FT [ntile][4][32][32]
 extern "C" int regt_debug_gemm_kt(const float* AT, int64_t ntile, int32_t H, const float* B0T, const float* B1T, const float* FT,
                                   float* C0, float* C1, float* C2, int32_t splits, regt_stream_t stream) {
   int k0[3], k1[3], sb[3], ns;

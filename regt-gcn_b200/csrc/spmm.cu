@@ -117,15 +117,29 @@ __global__ void __launch_bounds__(SPMM_BLK_THREADS, 2) k_spmm_blk(const int32_t*
       float4* yr = y + ((size_t)b * n_out + r) * W4;
       for (int c = lane; c < W4; c += 32) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = e0; e < e1; ++e) {
-          const bool staged = e < SPMM_EMAX;
-          const int j = staged ? s_col[e] : __ldg(col + eb + e);
-          const float w = staged ? s_val[e] : __ldg(val + eb + e);
-          const float4 v = (j >= r0 && j < s1) ? xs[(size_t)(j - r0) * W4 + c] : __ldg(xb + (size_t)j * W4 + c);
-          acc.x = fmaf(w, v.x, acc.x);
-          acc.y = fmaf(w, v.y, acc.y);
-          acc.z = fmaf(w, v.z, acc.z);
-          acc.w = fmaf(w, v.w, acc.w);
+        // four neighbour rows in flight (an out-of-block neighbour is an L2 round trip: one at a time made the row loop a chain
+        // of ~600-cycle waits), accumulated in CSR order
+        for (int e = e0; e < e1; e += 4) {
+          float4 v[4];
+          float w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ee = e + u;
+            const bool live = ee < e1;
+            const bool staged = ee < SPMM_EMAX;
+            const int j = live ? (staged ? s_col[ee] : __ldg(col + eb + ee)) : r0;
+            w[u] = live ? (staged ? s_val[ee] : __ldg(val + eb + ee)) : 0.f;
+            v[u] = (j >= r0 && j < s1) ? xs[(size_t)(j - r0) * W4 + c] : __ldg(xb + (size_t)j * W4 + c);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (e + u < e1) {
+              acc.x = fmaf(w[u], v[u].x, acc.x);
+              acc.y = fmaf(w[u], v[u].y, acc.y);
+              acc.z = fmaf(w[u], v[u].z, acc.z);
+              acc.w = fmaf(w[u], v[u].w, acc.w);
+            }
+          }
         }
         yr[c] = acc;
       }

@@ -191,6 +191,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                : "memory");
 }
 
+// a contiguous run of global memory -> L2 (no destination, no completion tracking): used to hide the DRAM latency of
+// tiles the epilogue threads will read with ordinary loads one step later
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// shared -> global bulk store (asynchronous proxy, tracked in the issuing thread's bulk async-groups)
+__device__ __forceinline__ void bulk_s2g(void* dst_global, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// at most N of this thread's bulk groups may still be in flight (writes of the others are complete and visible to this thread)
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- operand tile addressing ----------------------------------------------------------------
 // byte offset of (row, byte position `kb` along the 128-byte direction) inside a SW128 tile
 __device__ __forceinline__ uint32_t sw128_off(int row, int kb, int rows) {

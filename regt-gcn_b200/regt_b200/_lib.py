@@ -147,6 +147,8 @@ def load() -> C.CDLL:
     lib.regt_debug_gemm_tn_multi.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp]
     lib.regt_debug_gemm_kt.restype = C.c_int
     lib.regt_debug_gemm_kt.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp]
+    lib.regt_debug_f_timestamps.restype = C.c_int
+    lib.regt_debug_f_timestamps.argtypes = [vp]
     lib.regt_debug_umma_selftest.restype = C.c_int
     lib.regt_debug_umma_selftest.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp]
     _lib = lib

@@ -150,15 +150,15 @@ def test_gemm_tn_tma_stage_reuse_stress(M, K, N, splits):
 
 @pytest.mark.parametrize("H,ntile,splits", [(128, 5, 1), (128, 37, 4), (64, 9, 2), (128, 300, 37)])
 def test_gemm_kt_transposed_tiles(H, ntile, splits):
-    """the row contraction of the fused cell backward over transposed tiles (csrc/gemm_tma.cu k_gemm_kt): D^T [tile][4H][128],
-    h^T / (h*R)^T [tile][H][128], F^T [tile][32][128] -> dB_z|dB_r = [Dz|Dr]^T h, dB_h = Dc^T hR, D^T F for all four blocks."""
+    """the row contraction of the fused cell backward over transposed tiles (csrc/gemm_tma.cu k_gemm_kt): D^T [tile][4 row
+    quarters][4H][32], h^T / (h*R)^T [tile][4][H][32], F^T [tile][4][32][32] -> dB_z|dB_r = [Dz|Dr]^T h, dB_h = Dc^T hR, D^T F."""
     from regt_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(H + ntile)
-    AT = (torch.rand(ntile, 4 * H, 128, generator=g) - 0.5).cuda()
-    B0T = (torch.rand(ntile, H, 128, generator=g) - 0.5).cuda()
-    B1T = (torch.rand(ntile, H, 128, generator=g) - 0.5).cuda()
-    FT = (torch.rand(ntile, 32, 128, generator=g) - 0.5).cuda()
+    AT = (torch.rand(ntile * 4, 4 * H, 32, generator=g) - 0.5).cuda()
+    B0T = (torch.rand(ntile * 4, H, 32, generator=g) - 0.5).cuda()
+    B1T = (torch.rand(ntile * 4, H, 32, generator=g) - 0.5).cuda()
+    FT = (torch.rand(ntile * 4, 32, 32, generator=g) - 0.5).cuda()
     C0 = torch.full((splits, 2 * H, H), float("nan"), device="cuda")
     C1 = torch.full((splits, H, H), float("nan"), device="cuda")
     C2 = torch.full((splits, 4 * H, 32), float("nan"), device="cuda")

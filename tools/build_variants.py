@@ -19,7 +19,9 @@ VARIANTS = {
     "cw16": ["REGT_CW=16"],
     "cw16_nopipe": ["REGT_CW=16"] + NOPIPE,
     # round 2, fused 3xTF32 cell (cell_f.cu)
-    "fpre": ["REGT_F_PRE=1"],
+    "fpre0": ["REGT_F_PRE=0"],     # h of the next step computed after the candidate MMAs (default: under them)
+    "xp_noh16": ["REGT_XP_SKIP_H16=1"],              # timing experiments (wrong results)
+    "xp_nostore": ["REGT_XP_SKIP_E0_STORES=1"],
     "tn2": ["REGT_TN_GROUP=2"],      # row contraction: drain the TMEM accumulator every 2 chunks (24 MMAs) instead of 8
     "tn4": ["REGT_TN_GROUP=4"],
 }
