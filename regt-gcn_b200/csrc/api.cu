@@ -74,6 +74,13 @@ Layout make_layout(const regt_args* a, void* base) {
     L.tc_wpart = c.take<float>((size_t)TC_MAX_CTAS * 128 * 192);
     L.tc_dpp = c.take<float>(T * TC_MAX_CTAS + 64);   // one attention-gradient partial per (CTA, period)
   }
+  if (a->precision == REGT_PREC_TF32X3) {   // tensor-core head (head_f.cu)
+    L.hf_rh = c.take<float>(BN * H);
+    L.hf_do32 = c.take<float>(BN * 32);
+    L.hf_split = c.take<float>(max(gemm_nt_scratch_floats(HEAD_HID, (int)H), gemm_nt_scratch_floats((int)H, HEAD_HID)));
+    L.hf_loss_floats = BN / 8 + 2;
+    L.hf_loss = c.take<float>(L.hf_loss_floats);
+  }
   L.a1 = c.take<float>(BN * HEAD_HID);
   L.G = c.take<float>(((BN + 127) / 128) * 128 * H);   // padded: the tensor-core backward reads whole 128-row tiles
   L.d_a1 = c.take<float>(BN * HEAD_HID);

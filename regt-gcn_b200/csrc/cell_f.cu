@@ -138,6 +138,20 @@ __device__ __forceinline__ void get_a16(uint32_t tlane, int col, float (&v)[16])
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] += lo[i];
 }
+// accumulator chunk + the A operand chunk (hi + lo) of the same 16 columns: three TMEM reads in flight, one wait
+template <int HH>
+__device__ __forceinline__ void get_acc_a16(uint32_t tacc, uint32_t tlane, int col, float (&v)[16], float (&h)[16]) {
+  uint32_t rv[16], rh[16], rl[16];
+  tmem_ld16_nw(tacc, rv);
+  tmem_ld16_nw(tlane + col, rh);
+  tmem_ld16_nw(tlane + HH + col, rl);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = __uint_as_float(rv[i]);
+    h[i] = __uint_as_float(rh[i]) + __uint_as_float(rl[i]);
+  }
+}
 __device__ __forceinline__ void st_f32x16(uint32_t taddr, const float (&v)[16]) {
   uint32_t u[16];
 #pragma unroll
@@ -209,16 +223,16 @@ __device__ __forceinline__ void m1_cache_fill(const FArgs& a, const Row& ri, flo
   }
   named_bar(1, NEPI);
 }
-template <int HH>
-__device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M1Cache& mc, const Row& ri, const Feats& f, int t, int c,
-                                    float (&h)[16]) {
+template <int HH, int NC>
+__device__ __forceinline__ void hcols(const FArgs& a, const float* consts, const M1Cache& mc, const Row& ri, const Feats& f, int t, int c,
+                                      float (&h)[NC]) {
   using C = FCfg<HH>;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) h[i] = consts[C::C_C0 + c + i];
+  for (int i = 0; i < NC; ++i) h[i] = consts[C::C_C0 + c + i];
 #pragma unroll
   for (int k = 0; k < F; ++k) {
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {
+    for (int i = 0; i < NC; i += 4) {
       const float4 w = *reinterpret_cast<const float4*>(consts + C::C_M0 + k * HH + c + i);
       h[i] = fmaf(f.x[k], w.x, h[i]); h[i + 1] = fmaf(f.x[k], w.y, h[i + 1]);
       h[i + 2] = fmaf(f.x[k], w.z, h[i + 2]); h[i + 3] = fmaf(f.x[k], w.w, h[i + 3]);
@@ -238,7 +252,7 @@ __device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M
 #pragma unroll
       for (int k = 0; k < F; ++k) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
+        for (int i = 0; i < NC; i += 4) {
           const float4 w = *reinterpret_cast<const float4*>(m + k * HH + i);
           h[i] = fmaf(uv[k], w.x, h[i]); h[i + 1] = fmaf(uv[k], w.y, h[i + 1]);
           h[i + 2] = fmaf(uv[k], w.z, h[i + 2]); h[i + 3] = fmaf(uv[k], w.w, h[i + 3]);
@@ -249,7 +263,7 @@ __device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M
 #pragma unroll
       for (int k = 0; k < F; ++k) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
+        for (int i = 0; i < NC; i += 4) {
           const float4 w = __ldg(reinterpret_cast<const float4*>(m + k * HH + i));
           h[i] = fmaf(uv[k], w.x, h[i]); h[i + 1] = fmaf(uv[k], w.y, h[i + 1]);
           h[i + 2] = fmaf(uv[k], w.z, h[i + 2]); h[i + 3] = fmaf(uv[k], w.w, h[i + 3]);
@@ -259,8 +273,13 @@ __device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M
   }
   if (a.mode == REGT_MODE_REGIONAL) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) h[i] = h[i] > 0.f ? h[i] : 0.01f * h[i];   // F.leaky_relu
+    for (int i = 0; i < NC; ++i) h[i] = h[i] > 0.f ? h[i] : 0.01f * h[i];   // F.leaky_relu
   }
+}
+template <int HH>
+__device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M1Cache& mc, const Row& ri, const Feats& f, int t, int c,
+                                    float (&h)[16]) {
+  hcols<HH, 16>(a, consts, mc, ri, f, t, c, h);
 }
 
 // one H x H block: acc (+)= A(TMEM, hi|lo) . W_g^T over the NCH ring stages of gate block g, three tf32 products
@@ -457,8 +476,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float v[16], h[16];
-        tmem_ld16(tZ + c0 + j, v);
-        get_a16<HH>(tl, c0 + j, h);
+        get_acc_a16<HH>(tZ + c0 + j, tl, c0 + j, v, h);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           v[i] = sigm(v[i] + consts[C::C_CZR + c0 + j + i]);
@@ -475,8 +493,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 #pragma unroll 1
       for (int j = 0; j < CWF; j += 16) {
         float v[16], h[16];
-        tmem_ld16(tR + c0 + j, v);
-        get_a16<HH>(tl, c0 + j, h);
+        get_acc_a16<HH>(tR + c0 + j, tl, c0 + j, v, h);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           v[i] = sigm(v[i] + consts[C::C_CZR + HH + c0 + j + i]);
@@ -776,6 +793,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       unsigned int neg = 0u;                     // h <= 0 per column (leaky_relu slope of the regional combine)
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
+        // (Interleaving the stores with a per-4-column recompute of h -- so that they drain under compute instead of in
+        // bursts of 64 -- was measured slower: 35.9 vs 29.8 us per step, the unrolled code spills.)
         float h[16], dc[16], gz[16], hr[16];
 #if REGT_XP_SKIP_H16
 #pragma unroll

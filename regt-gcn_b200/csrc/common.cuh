@@ -99,6 +99,12 @@ struct Layout {
   // backward planes
   float* D;      // [rows][4H]  d_pre_z | d_pre_r | d_pre_h | d_hpre
   float* Feat;   // [rows][32]  S_t | X_t | 1 | 0  (tf32x3: B operand of the F-wide weight-gradient GEMM)
+  // tensor-core head (head_f.cu, precision tf32x3)
+  float* hf_rh;      // [BN][H]   relu(out_hidden) forward, then the unmasked gradient wrt out_hidden backward
+  float* hf_do32;    // [BN][32]  d_out | 1 (column 16): feature-plane operand of the head's weight-gradient contractions
+  float* hf_split;   // hi | lo images of the weight operand of the head GEMMs
+  float* hf_loss;    // per-block loss partials
+  size_t hf_loss_floats;
   float* FeatT;  // fused tf32x3 cell: transposed feature tiles [T*nqt][32][128] (cell_f.cu)
   float* bsplit; // tf32x3: hi | lo images of the weight operand of the current gate GEMM (gemm_tma.cu)
   // collapsed-weight gradients
@@ -126,7 +132,8 @@ struct Layout {
 constexpr int TC_MAX_CTAS = 160;
 constexpr int TC_IMG_BYTES = 160 * 1024;
 constexpr int F_IMG_BYTES = 432 * 1024;   // fused 3xTF32 cell (cell_f.cu): 12 ring stages of 32 KB + F-wide weights + constants at H = 128
-bool cell_f_usable(const regt_args* a);   // precision tf32x3, hidden 128 / 64, not the bare TGCN cell
+bool cell_f_usable(const regt_args* a);
+bool head_f_usable(const regt_args* a);   // precision tf32x3, hidden % 32 == 0, output_dim <= 16, >= 128 rows   // precision tf32x3, hidden 128 / 64, not the bare TGCN cell
 
 Layout make_layout(const regt_args* a, void* base);
 size_t gemm_nt_scratch_floats(int N, int K);

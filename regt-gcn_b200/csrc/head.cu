@@ -444,9 +444,13 @@ static HeadK make_headk(const regt_args* a, const Layout& L, float* W1t, float* 
   return k;
 }
 
+int head_forward_f(const regt_args* a, const Layout& L, cudaStream_t st);
+int head_backward_f(const regt_args* a, const Layout& L, cudaStream_t st, int g_tiled);
+
 int head_forward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, O = a->O;
   if (head_tc_usable(a)) return head_forward_tc(a, L, st, true);
+  if (head_f_usable(a)) return head_forward_f(a, L, st);      // tf32x3: the 128-wide GEMMs on the tensor cores (head_f.cu)
   if (head_fusable(a)) {
     HeadK k = make_headk(a, L, nullptr, nullptr);
     const int grid = head_fused_grid(a), ntiles = cdiv(k.BN, TMH), OP = (O + 3) & ~3;
@@ -505,7 +509,7 @@ int launch_head_grad_reduce(const regt_args* a, const Layout& L, cudaStream_t st
 int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
   const int H = a->H, O = a->O;
   const long long BN = (long long)a->B * a->N;
-  if (head_fusable(a)) {  // everything but the cross-CTA sum already happened in head_forward
+  if (!head_f_usable(a) && head_fusable(a)) {  // everything but the cross-CTA sum already happened in head_forward
     // tensor-core step: the sum runs beside the cell backward (launch_head_grad_reduce from cell_backward_tc)
     if (head_tc_usable(a)) return 0;
     return launch_head_grad_reduce(a, L, st);
@@ -515,6 +519,7 @@ int head_backward_fp32(const regt_args* a, const Layout& L, cudaStream_t st) {
     REGT_LAUNCHED("k_copy_or_zero", st);
     return 0;
   }
+  if (head_f_usable(a)) return head_backward_f(a, L, st, a->precision == REGT_PREC_BF16 || cell_f_usable(a));
   HeadK k = make_headk(a, L, nullptr, nullptr);
   const int nblk = cdiv(BN, TMH);
   const size_t smem = ((size_t)TMH * (O + 1) + TMH * (HEAD_HID + 1) + KT * TN + 4) * sizeof(float);

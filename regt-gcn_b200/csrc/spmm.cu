@@ -72,6 +72,10 @@ __global__ void __launch_bounds__(256) k_spmm_rows(const int32_t* __restrict__ r
 // of the HBM peak), and two CTAs share an SM so that one's block load overlaps the other's gather.
 constexpr int SPMM_BLK_THREADS = 512;
 constexpr int SPMM_EMAX = 2304;          // staged edges per block (more: the tail is read from global memory)
+// v3: the kernel was ISSUE-bound (ncu: 70 % issue-active, integer compares and address arithmetic around four FMAs per
+// edge and lane).  The staging threads now resolve every edge ONCE per block into (float4 index of the neighbour row inside
+// the staged block, or -1 - its global row) + weight, one 8-byte word; the gather loop is a broadcast LDS.64, a warp-uniform
+// branch, one 128-bit load and four FMAs.
 __global__ void __launch_bounds__(SPMM_BLK_THREADS, 2) k_spmm_blk(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                                   const float* __restrict__ val, const float4* __restrict__ x,
                                                                   float4* __restrict__ y, int B, int n_out, int n_in, int W4, int NB,
@@ -79,9 +83,8 @@ __global__ void __launch_bounds__(SPMM_BLK_THREADS, 2) k_spmm_blk(const int32_t*
   extern __shared__ __align__(128) uint8_t spmm_smem[];
   __shared__ uint64_t bar;
   float4* xs = reinterpret_cast<float4*>(spmm_smem);
-  int32_t* s_ptr = reinterpret_cast<int32_t*>(spmm_smem + (size_t)NB * W4 * 16);   // [NB + 1]
-  int32_t* s_col = s_ptr + ((NB + 1 + 3) & ~3);                                     // [SPMM_EMAX]
-  float* s_val = reinterpret_cast<float*>(s_col + SPMM_EMAX);                       // [SPMM_EMAX]
+  int32_t* s_ptr = reinterpret_cast<int32_t*>(spmm_smem + (size_t)NB * W4 * 16);   // [NB + 1] edge offsets relative to the block's first edge
+  int2* s_edge = reinterpret_cast<int2*>(s_ptr + ((NB + 1 + 3) & ~3));              // [SPMM_EMAX] (resolved neighbour, weight bits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x == 0) {
     tc::mbar_init(&bar, 1);
@@ -91,8 +94,7 @@ __global__ void __launch_bounds__(SPMM_BLK_THREADS, 2) k_spmm_blk(const int32_t*
   uint32_t phase = 0;
   for (long long item = blockIdx.x; item < (long long)B * nblk; item += gridDim.x) {
     // items are ordered snapshot-major: the CTAs running side by side work on neighbouring node blocks of ONE snapshot, so
-    // an out-of-block neighbour row is (still) in L2 because the CTA next door staged it.  (Block-major order -- every
-    // snapshot of a block before the next block -- turned those gathers into DRAM reads: 3.17 ms against 2.67 ms.)
+    // an out-of-block neighbour row is (still) in L2 because the CTA next door staged it
     const int b = (int)(item / nblk), blk = (int)(item - (long long)b * nblk);
     const int r0 = blk * NB, r1 = min(n_out, r0 + NB);
     const int s1 = min(n_in, r0 + NB);                       // staged node range [r0, s1)
@@ -104,42 +106,42 @@ __global__ void __launch_bounds__(SPMM_BLK_THREADS, 2) k_spmm_blk(const int32_t*
       for (uint32_t o = 0; o < bytes; o += 32768) tc::bulk_g2s(spmm_smem + o, src + o, min(32768u, bytes - o), &bar);
     }
     const int eb = __ldg(rowptr + r0), ee = __ldg(rowptr + r1);
-    for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_ptr[i] = __ldg(rowptr + r0 + i);
+    for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_ptr[i] = __ldg(rowptr + r0 + i) - eb;
     for (int i = threadIdx.x; i < min(ee - eb, SPMM_EMAX); i += blockDim.x) {
-      s_col[i] = __ldg(col + eb + i);
-      s_val[i] = __ldg(val + eb + i);
+      const int j = __ldg(col + eb + i);
+      s_edge[i] = make_int2((j >= r0 && j < s1) ? (j - r0) * W4 : -1 - j * W4, __float_as_int(__ldg(val + eb + i)));
     }
     __syncthreads();
     tc::mbar_wait(&bar, phase);
     phase ^= 1;
     for (int r = r0 + warp; r < r1; r += nwarp) {
-      const int e0 = s_ptr[r - r0] - eb, e1 = s_ptr[r - r0 + 1] - eb;
+      const int e0 = s_ptr[r - r0], e1 = s_ptr[r - r0 + 1];
       float4* yr = y + ((size_t)b * n_out + r) * W4;
+      const int e1s = min(e1, SPMM_EMAX);
       for (int c = lane; c < W4; c += 32) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // four neighbour rows in flight (an out-of-block neighbour is an L2 round trip: one at a time made the row loop a chain
-        // of ~600-cycle waits), accumulated in CSR order
-        for (int e = e0; e < e1; e += 4) {
-          float4 v[4];
-          float w[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int ee = e + u;
-            const bool live = ee < e1;
-            const bool staged = ee < SPMM_EMAX;
-            const int j = live ? (staged ? s_col[ee] : __ldg(col + eb + ee)) : r0;
-            w[u] = live ? (staged ? s_val[ee] : __ldg(val + eb + ee)) : 0.f;
-            v[u] = (j >= r0 && j < s1) ? xs[(size_t)(j - r0) * W4 + c] : __ldg(xb + (size_t)j * W4 + c);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (e + u < e1) {
-              acc.x = fmaf(w[u], v[u].x, acc.x);
-              acc.y = fmaf(w[u], v[u].y, acc.y);
-              acc.z = fmaf(w[u], v[u].z, acc.z);
-              acc.w = fmaf(w[u], v[u].w, acc.w);
-            }
-          }
+        const float4* xc = xs + c;
+        const float4* gc = xb + c;
+#pragma unroll 2
+        for (int e = e0; e < e1s; ++e) {      // sequential CSR order: deterministic sums
+          const int2 ed = s_edge[e];          // one broadcast 8-byte load: resolved neighbour + weight
+          const float w = __int_as_float(ed.y);
+          float4 v;
+          if (ed.x >= 0) v = xc[ed.x];        // warp-uniform: the neighbour row is staged
+          else v = __ldg(gc + (-1 - ed.x));   // ... or lives in another block (L2)
+          acc.x = fmaf(w, v.x, acc.x);
+          acc.y = fmaf(w, v.y, acc.y);
+          acc.z = fmaf(w, v.z, acc.z);
+          acc.w = fmaf(w, v.w, acc.w);
+        }
+        for (int e = max(e0, SPMM_EMAX); e < e1; ++e) {   // edges beyond the staged slice (blocks with very many edges)
+          const int j = __ldg(col + eb + e);
+          const float w = __ldg(val + eb + e);
+          const float4 v = (j >= r0 && j < s1) ? xc[(j - r0) * W4] : __ldg(gc + (size_t)j * W4);
+          acc.x = fmaf(w, v.x, acc.x);
+          acc.y = fmaf(w, v.y, acc.y);
+          acc.z = fmaf(w, v.z, acc.z);
+          acc.w = fmaf(w, v.w, acc.w);
         }
         yr[c] = acc;
       }

@@ -47,7 +47,7 @@ def test_fused_cell_matches_oracle(w, B, unfused, monkeypatch):
     x, y = w.inputs(B)
     (loss, out, hid), names = _kernels_of_one_step(m, x.cuda(), y.cuda(), to_dev(w.graph_args(), "cuda"))
     assert ("k_cell_fwd_f" in names and "k_cell_bwd_f" in names) == (not unfused), names
-    assert ("k_gemm_nt_tma_ts" in names or "k_gemm_nt_tf32x3" in names) == unfused, names
+    assert ("k_g_zr" in names and "k_g_b1" in names) == unfused, names
     assert relerr(hid, ref["hid"]) <= 1e-5 and relerr(out, ref["out"]) <= 1e-5
     assert abs(float(loss) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
     lim, twin = twin_limits(w, B, ref)
