@@ -94,6 +94,19 @@ int regt_cheb_plan_build(const int64_t* edge_index, const float* edge_weight, co
  * Replaces GCNConv.propagate's index_select/mul/scatter_add (models/utils.py:169).      */
 int regt_spmm_f8(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
                  int32_t B, int32_t N, int32_t width, regt_stream_t stream);
+/* Plan-time row partition for the staged SpMM kernel (once per static graph, like gcn_norm's plan: the reference
+ * re-derives the same index structure on every GCNConv call, models/utils.py:169).  The kernel stages a block of
+ * consecutive node rows in shared memory and gathers from there; regt_spmm_partition cuts the rows into blocks that
+ * fit, at the positions the fewest edges cross (region borders when node ids are ordered by region), so that nearly
+ * all neighbour reads stay on chip.  blk_ptr: device int32[regt_spmm_partition_capacity(N, width)] (0: rows too wide
+ * for the staged kernel), receives nblk+1 row offsets; nblk_out: host.  Synchronises the stream (copies the CSR back).
+ * regt_spmm_f8_blocked computes exactly what regt_spmm_f8 does (same order of additions: bit-identical).           */
+int32_t regt_spmm_partition_capacity(int32_t N, int32_t width);
+int regt_spmm_partition(const int32_t* rowptr, const int32_t* col, int32_t N, int32_t width, int32_t* blk_ptr,
+                        int32_t* nblk_out /*host*/, regt_stream_t stream);
+int regt_spmm_f8_blocked(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
+                         int32_t B, int32_t N, int32_t width, const int32_t* blk_ptr, int32_t nblk,
+                         regt_stream_t stream);
 
 /* ---- K4: regional gather / scatter of node rows -------------------------------------- */
 /* The reference has no node subsets (a region is an edge list over global ids,

@@ -48,7 +48,8 @@ PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
 
 EXPORTS = ["regt_version", "regt_last_error", "regt_launch_count", "regt_plan_workspace_bytes",
-           "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_gather_rows", "regt_scatter_rows", "regt_workspace_bytes",
+           "regt_gcn_plan_build", "regt_cheb_plan_build", "regt_spmm_f8", "regt_spmm_partition_capacity", "regt_spmm_partition",
+           "regt_spmm_f8_blocked", "regt_gather_rows", "regt_scatter_rows", "regt_workspace_bytes",
            "regt_cell_forward", "regt_head_forward", "regt_head_backward", "regt_cell_backward",
            "regt_profile", "regt_profile_begin", "regt_profile_read",
            "regt_comm_region_bytes", "regt_comm_data_offset", "regt_comm_alloc", "regt_comm_free", "regt_comm_export",
@@ -91,6 +92,12 @@ def load() -> C.CDLL:
                                         [c_i32p, vp, C.c_size_t, vp]
     lib.regt_spmm_f8.restype = C.c_int
     lib.regt_spmm_f8.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.regt_spmm_partition_capacity.restype = C.c_int32
+    lib.regt_spmm_partition_capacity.argtypes = [C.c_int32, C.c_int32]
+    lib.regt_spmm_partition.restype = C.c_int
+    lib.regt_spmm_partition.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, c_i32p, vp]
+    lib.regt_spmm_f8_blocked.restype = C.c_int
+    lib.regt_spmm_f8_blocked.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]
     for name in ("regt_gather_rows", "regt_scatter_rows"):
         fn = getattr(lib, name)
         fn.restype = C.c_int

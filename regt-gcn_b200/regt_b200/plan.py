@@ -171,15 +171,51 @@ def get_plan(N: int, device: torch.device, edge_index: torch.Tensor, edge_weight
     return plan
 
 
-def spmm_f8(rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """y[b,n,:] = sum_e val[e] x[b,col[e],:] over rows of F*T floats (x [B,N,F,T] or [B,N,W])."""
+_PARTS: dict = {}     # (rowptr ptr, col ptr, versions, N, width) -> (rowptr, col, blk_ptr, nblk): the staged SpMM's row partition
+
+
+def spmm_partition(rowptr: torch.Tensor, col: torch.Tensor, N: int, width: int):
+    """(blk_ptr, nblk) of regt_spmm_partition for this CSR, built once per static graph (None, 0 when the rows are too
+    wide for the staged kernel)."""
+    lib = _lib.load()
+    key = (rowptr.data_ptr(), col.data_ptr(), rowptr._version, col._version, int(N), int(width))
+    hit = _PARTS.get(key)
+    if hit is not None:
+        return hit[2], hit[3]
+    cap = lib.regt_spmm_partition_capacity(int(N), int(width))
+    blk, nblk = None, 0
+    if cap > 0:
+        import ctypes as C
+        blk = torch.empty(cap, dtype=torch.int32, device=rowptr.device)
+        n = C.c_int32(0)
+        with torch.cuda.device(rowptr.device):
+            rc = lib.regt_spmm_partition(rowptr.data_ptr(), col.data_ptr(), int(N), int(width), blk.data_ptr(), C.byref(n), _stream_ptr())
+        _lib.check(rc, "regt_spmm_partition")
+        nblk = int(n.value)
+        blk = blk[: nblk + 1]
+    if len(_PARTS) > 16:
+        _PARTS.clear()
+    _PARTS[key] = (rowptr, col, blk, nblk)      # the key tensors stay alive: their data_ptr() cannot be recycled
+    return blk, nblk
+
+
+def spmm_f8(rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, x: torch.Tensor, partition: bool = True) -> torch.Tensor:
+    """y[b,n,:] = sum_e val[e] x[b,col[e],:] over rows of F*T floats (x [B,N,F,T] or [B,N,W]).  With ``partition`` the row
+    blocks of the staged kernel come from regt_spmm_partition (cached per CSR); the sums are bit-identical either way."""
     lib = _lib.load()
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
     B, N = x.shape[0], x.shape[1]
     width = x[0, 0].numel()
     y = torch.empty_like(x)
+    blk, nblk = (None, 0)
+    if partition and width % 4 == 0 and B * N >= 4096 and x.data_ptr() % 16 == 0:
+        blk, nblk = spmm_partition(rowptr, col, N, width)
     with torch.cuda.device(x.device):
-        rc = lib.regt_spmm_f8(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(), y.data_ptr(), B, N, width,
-                              _stream_ptr())
+        if nblk > 0:
+            rc = lib.regt_spmm_f8_blocked(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(), y.data_ptr(), B, N, width,
+                                          blk.data_ptr(), nblk, _stream_ptr())
+        else:
+            rc = lib.regt_spmm_f8(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), x.data_ptr(), y.data_ptr(), B, N, width,
+                                  _stream_ptr())
     _lib.check(rc, "regt_spmm_f8")
     return y

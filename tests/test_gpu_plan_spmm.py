@@ -115,3 +115,72 @@ def test_spmm_linearity_and_empty_rows_full_size():
     lhs = spmm_f8(*args, (2.0 * x1 + x2).contiguous())
     rhs = 2.0 * spmm_f8(*args, x1) + spmm_f8(*args, x2)
     assert relerr(lhs, rhs) <= 1e-6
+
+
+def _csr_ref(rowptr, col, val, x):
+    """fp64 reference of the CSR product on the GPU (index_add over the edges)."""
+    N = rowptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(N, device=x.device), (rowptr[1:] - rowptr[:-1]).long())
+    xd = x.double().reshape(x.shape[0], N, -1)
+    out = torch.zeros_like(xd)
+    out.index_add_(1, rows, xd[:, col.long()] * val.double()[None, :, None])
+    return out.reshape(x.shape)
+
+
+@pytest.mark.parametrize("cfg,B", [(4, 3), (5, 2)])
+def test_spmm_staged_partition_bit_identical_full_graphs(cfg, B):
+    """the staged kernel on the 10 k / 100 k-node graphs: the plan's row partition (regt_spmm_partition) and the uniform
+    blocks give bit-identical sums (same CSR order of additions), both within fp32 rounding of the fp64 product; the
+    partition covers the rows, respects the kernel's block capacity and cuts the region-ordered graph at region borders."""
+    from regt_b200 import _lib
+    from regt_b200.plan import GraphPlanTensors, build_gcn, spmm_f8, spmm_partition
+    w = W.make_workload(cfg)
+    dev = torch.device("cuda:0")
+    plan = GraphPlanTensors(dev, w.N)
+    build_gcn(plan, w.edge_index.to(dev), None if w.edge_attr is None else w.edge_attr.to(dev))
+    rp, cj, va = plan.t["g_rowptr"], plan.t["g_col"], plan.t["g_val"]
+    x, _ = w.inputs(B)
+    x = x.to(dev)
+    y_part = spmm_f8(rp, cj, va, x, partition=True)
+    y_unif = spmm_f8(rp, cj, va, x, partition=False)
+    assert torch.equal(y_part, y_unif)
+    assert relerr(y_part, _csr_ref(rp, cj, va, x)) <= 2e-6
+    blk, nblk = spmm_partition(rp, cj, w.N, x[0, 0].numel())
+    assert nblk > 0 and blk.numel() == nblk + 1
+    b = blk.cpu().numpy()
+    assert b[0] == 0 and b[-1] == w.N and (np.diff(b) > 0).all()
+    cap = (227 * 1024 - 2048 - 3584 * 16 - 64) // (x[0, 0].numel() * 4 + 4) // 8 * 8     # spmm_geometry, one CTA per SM
+    assert np.diff(b).max() <= cap
+    # edges leaving their block: far fewer than with uniform blocks of the same count
+    rows = torch.repeat_interleave(torch.arange(w.N, device=dev), (rp[1:] - rp[:-1]).long()).cpu().numpy()
+    cols = cj.cpu().numpy()[: len(rows)]
+    def crossing(bounds):
+        return int((np.searchsorted(bounds, rows, side="right") != np.searchsorted(bounds, cols, side="right")).sum())
+    uniform = np.minimum(np.arange(nblk + 1) * -(-w.N // nblk), w.N)
+    assert crossing(b) <= crossing(uniform)
+    assert crossing(b) <= 0.2 * len(rows)      # the synthetic graphs keep > 95 % of their edges inside a region
+
+
+def test_spmm_staged_hub_row_and_tail_edges():
+    """a hub row with more edges than one block stages (the tail of its edge list is read from global memory), rows
+    without any edge, and a partition forced down to single-row blocks around the hub."""
+    from regt_b200.plan import spmm_f8
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    N, Wd, B = 6000, 96, 2
+    deg = torch.randint(0, 6, (N,), generator=g)
+    deg[17] = 5000                       # hub
+    deg[100:140] = 0                     # empty rows
+    rowptr = torch.zeros(N + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).int()
+    E = int(rowptr[-1])
+    col = torch.randint(0, N, (E,), generator=g).int()
+    val = torch.rand(E, generator=g) - 0.5
+    x = torch.rand(B, N, Wd, generator=g)
+    rowptr, col, val, x = rowptr.to(dev), col.to(dev), val.to(dev), x.to(dev)
+    ref = _csr_ref(rowptr, col, val, x)
+    for part in (True, False):
+        y = spmm_f8(rowptr, col, val, x, partition=part)
+        assert relerr(y, ref) <= 5e-6, part
+        assert (y[:, 100:140] == 0).all()
+    assert torch.equal(spmm_f8(rowptr, col, val, x, partition=True), spmm_f8(rowptr, col, val, x, partition=False))
