@@ -131,6 +131,23 @@ __device__ __forceinline__ void put_a16(uint32_t tlane, int col, const float (&v
   tmem_st16(tlane + HH + col, lo);
 }
 template <int HH>
+__device__ __forceinline__ void put_a8(uint32_t tlane, int col, const float (&v)[8]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = tf32_rn_bits(v[i]);
+    lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
+  }
+  tmem_st8(tlane + col, hi);
+  tmem_st8(tlane + HH + col, lo);
+}
+__device__ __forceinline__ void st_f32x8(uint32_t taddr, const float (&v)[8]) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(v[i]);
+  tmem_st8(taddr, u);
+}
+template <int HH>
 __device__ __forceinline__ void get_a16(uint32_t tlane, int col, float (&v)[16]) {
   float lo[16];
   tmem_ld16(tlane + col, v);
@@ -625,12 +642,27 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 // warp produces per chunk are one contiguous 2 KB run of this layout; the lanes put them into a per-warp shared-memory
 // slot (conflict-free 4-byte stores) and one lane hands the slot to the bulk-copy engine (cp.async.bulk shared -> global),
 // which drains it while the warp computes on.
+#ifndef REGT_F_PREFETCH
+#define REGT_F_PREFETCH 0      // 1: the producer lane prefetches the next step's planes into L2 (see the note in k_cell_bwd_f)
+#endif
+#ifndef REGT_F_LDCS
+#define REGT_F_LDCS 1          // backward: Z and H~ (read once) with the streaming load operator
+#endif
+#ifndef REGT_F_STCS
+#define REGT_F_STCS 1          // backward plane stores with the streaming (evict-first) cache operator
+#endif
 template <int HH>
 struct BCfg {   // shared-memory plan of the backward: ring | resident tail | M1 cache
   using C = FCfg<HH>;
   static constexpr int SLOT = 16 * 32 * 4;                        // one staged chunk: 16 columns x 32 rows
   static constexpr int NSLOT = 2;                                 // per warp (the copy engine reads one while the lanes fill the other)
-  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C + (REGT_F_BULKSTORE ? NEPI_W * NSLOT * SLOT : 0);
+  // Dz (then Dr) of the step: HH/4 values per epilogue thread that live from E0 to the Dr -> A conversion.  In registers, next
+  // to E0's unrolled 16-column chunks, they pushed the epilogue warps far over their 112 registers (ncu: 62 STL + 94 LDL per
+  // thread and step, 5 GB of spill traffic per launch through a 28 KB L1 into L2 -- a quarter of the kernel's L2 traffic, and
+  // E0 is L2-bound: with a quarter of the CTAs it takes 11.6 us instead of 18.5).  The backward does not need a deep weight
+  // ring (its MMAs wait for the epilogue, not for the weights): two of its stages pay for a [HH/4][512] plane in shared memory.
+  static constexpr int DZS = NEPI_W * 32 * (HH / 4) * 4;
+  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C + (REGT_F_BULKSTORE ? NEPI_W * NSLOT * SLOT : 0) + DZS;
   static constexpr int NS_FIT = (SMEM_MAX - 12288 - FIXED) / C::STAGE;
   static constexpr int NS = NS_FIT < 2 * C::NSTEP ? NS_FIT : 2 * C::NSTEP;
   static constexpr int SMEM = 1024 + NS * C::STAGE + FIXED;
@@ -641,13 +673,19 @@ struct BCfg {   // shared-memory plan of the backward: ring | resident tail | M1
 struct WarpStore {
   float* slot0;      // this warp's NSLOT staging slots
   int n;             // stores issued so far
-  __device__ __forceinline__ void put(int lane, float* dst, const float (&v)[16]) {
+  __device__ __forceinline__ void put(int lane, float* dst, const float (&v)[16], bool stream = true) {
 #if !REGT_F_BULKSTORE
     // plain stores: one 128-byte line per column.  Measured against the staged bulk stores below (tools/f_phases.py, config 4):
     // 29.8 us per backward step vs 33.3 us -- with two slots per warp a put waits ~0.7 us for the copy engine to have read the
     // slot used two puts ago, and shared memory has no room for more slots
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dst[i * 32 + lane] = v[i];
+    for (int i = 0; i < 16; ++i) {
+#if REGT_F_STCS
+      if (stream) __stcs(dst + i * 32 + lane, v[i]);
+      else
+#endif
+        dst[i * 32 + lane] = v[i];
+    }
     return;
 #endif
     float* sl = slot0 + (n & 1) * (16 * 32);
@@ -722,6 +760,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   uint8_t* tail = ring + NS * C::STAGE;
   float* m1data = reinterpret_cast<float*>(tail + ((C::TAIL + 1023) & ~1023));
   float* slots = m1data + C::M1C / 4;
+  float* dzp = slots + (REGT_F_BULKSTORE ? NEPI_W * BC::NSLOT * BC::SLOT / 4 : 0) + (threadIdx.x & (NEPI_W * 32 - 1));   // [HH/4][512]: this thread's column
+#define DZ(i) dzp[(i) * (NEPI_W * 32)]
   __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
   __shared__ uint32_t tmem_base_s;
   __shared__ int m1tag[4];
@@ -788,29 +828,46 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       F_TS(1, 0)
       Feats f;
       load_feats(a, ri, t, f);
-      float dz[CWF];
       double dp = 0.0;
       unsigned int neg = 0u;                     // h <= 0 per column (leaky_relu slope of the regional combine)
+      // Eight columns per trip of a ROLLED loop: the plane loads of the trip go first, h of the eight columns is recomputed under
+      // them, every result leaves before the next trip (Dz -> shared memory, Dc -> A, p G Z -> acc2, h / hR / Dc / Dz -> their
+      // transposed tiles).  Unrolled over 16-column chunks the compiler kept up to 16 float4 loads and five 16-column arrays
+      // alive at once and spilled (see BCfg).
+#pragma unroll 1
+      for (int j = 0; j < CWF; j += 8) {
+        const int c = c0 + j;
+        float4 zq[2], rq[2], cq[2], gq[2];
 #pragma unroll
-      for (int j = 0; j < CWF; j += 16) {
-        // (Interleaving the stores with a per-4-column recompute of h -- so that they drain under compute instead of in
-        // bursts of 64 -- was measured slower: 35.9 vs 29.8 us per step, the unrolled code spills.)
-        float h[16], dc[16], gz[16], hr[16];
+        for (int i = 0; i < 2; ++i) {
+#if REGT_F_LDCS
+          zq[i] = __ldcs(reinterpret_cast<const float4*>(zt + piece(r, c + 4 * i)));
+          cq[i] = __ldcs(reinterpret_cast<const float4*>(ct + piece(r, c + 4 * i)));
+#else
+          zq[i] = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c + 4 * i)));
+          cq[i] = __ldg(reinterpret_cast<const float4*>(ct + piece(r, c + 4 * i)));
+#endif
+          rq[i] = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c + 4 * i)));
+          gq[i] = __ldg(reinterpret_cast<const float4*>(gt + piece(r, c + 4 * i)));
+        }
+        float h[8];
 #if REGT_XP_SKIP_H16
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = consts[C::C_C0 + c0 + j + i] + f.x[i & 7];
+        for (int i = 0; i < 8; ++i) h[i] = consts[C::C_C0 + c + i] + f.x[i & 7];
 #else
-        h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
+        hcols<HH, 8>(a, consts, mc, ri, f, t, c, h);
 #endif
         if (j == 0) { F_TS(1, 9) }
+        float dc[8], gz[8];
         float dpc = 0.f;
+        unsigned int ng = 0u;
+        float* o_h = hT + (size_t)c * 32 + lane;
+        float* o_hr = hRT + (size_t)c * 32 + lane;
+        float* o_dz = DT + (size_t)c * 32 + lane;
+        float* o_dc = DT + (size_t)(2 * HH + c) * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const int c = c0 + j + i;
-          const float4 z4 = __ldg(reinterpret_cast<const float4*>(zt + piece(r, c)));
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c)));
-          const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + piece(r, c)));
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gt + piece(r, c)));
+        for (int i = 0; i < 8; i += 4) {
+          const float4 z4 = zq[i >> 2], r4 = rq[i >> 2], c4 = cq[i >> 2], g4 = gq[i >> 2];
           const float z[4] = {z4.x, z4.y, z4.z, z4.w}, rg[4] = {r4.x, r4.y, r4.z, r4.w}, hc[4] = {c4.x, c4.y, c4.z, c4.w};
           const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -819,28 +876,30 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
             const float gv = ri.valid ? g[e] : 0.f;                           // padded rows of the last tile: zero gradient
             const float gg = p * gv;                                          // dH' = probs[t] * d out_hidden
             dpc = fmaf(gv, z[e] * hh + (1.0f - z[e]) * hc[e], dpc);
-            dz[j + i + e] = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
+            const float dzv = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
             dc[i + e] = gg * (1.0f - z[e]) * (1.0f - hc[e] * hc[e]);
             gz[i + e] = gg * z[e];
-            hr[i + e] = hh * rg[e];
-            if (!(hh > 0.f)) neg |= 1u << (j + i + e);
+            DZ(j + i + e) = dzv;
+            if (!(hh > 0.f)) ng |= 1u << (i + e);
+#if !REGT_XP_SKIP_E0_STORES
+            o_h[(i + e) * 32] = hh;                                           // re-read in E1: not streamed
+#if REGT_F_STCS
+            __stcs(o_hr + (i + e) * 32, hh * rg[e]);
+            __stcs(o_dz + (i + e) * 32, dzv);
+            __stcs(o_dc + (i + e) * 32, dc[i + e]);
+#else
+            o_hr[(i + e) * 32] = hh * rg[e];
+            o_dz[(i + e) * 32] = dzv;
+            o_dc[(i + e) * 32] = dc[i + e];
+#endif
+#endif
           }
         }
+        neg |= ng << j;
         dp += (double)dpc;
         if (j == 0) { F_TS(1, 10) }
-        put_a16<HH>(tl, c0 + j, dc);
-        st_f32x16(t2c + c0 + j, gz);              // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
-#if !REGT_XP_SKIP_E0_STORES
-        ws.put(lane, hT + (size_t)(c0 + j) * 32, h);
-        ws.put(lane, hRT + (size_t)(c0 + j) * 32, hr);
-        ws.put(lane, DT + (size_t)(2 * HH + c0 + j) * 32, dc);
-        {
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
-          ws.put(lane, DT + (size_t)(c0 + j) * 32, v);
-        }
-#endif
+        put_a8<HH>(tl, c, dc);
+        st_f32x8(t2c + c, gz);                    // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
         if (j == 0) { F_TS(1, 11) }
       }
       tmem_st_wait();
@@ -861,7 +920,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+        for (int i = 0; i < 16; ++i) v[i] = DZ(j + i);
         put_a16<HH>(tl, c0 + j, v);
       }
       tmem_st_wait();
@@ -886,7 +945,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             dr[i + e] = v[i + e] * hh[i + e] * rg[e] * (1.0f - rg[e]);
-            dz[j + i + e] = dr[i + e];
+            DZ(j + i + e) = dr[i + e];
             v[i + e] *= rg[e];
           }
         }
@@ -903,7 +962,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       for (int j = 0; j < CWF; j += 16) {
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = dz[j + i];
+        for (int i = 0; i < 16; ++i) v[i] = DZ(j + i);
         put_a16<HH>(tl, c0 + j, v);
       }
       tmem_st_wait();
@@ -967,10 +1026,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       if (t == 0) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.G) + (size_t)qt * TB, TB);
       prefetch_feats(a, t, qt);
     };
+#if REGT_F_PREFETCH
     if (S > 0) prefetch_step(0);
+#endif
     long long gs = 0;
     for (int s = 0; s < S; ++s) {
+#if REGT_F_PREFETCH
       if (s + 1 < S) prefetch_step(s + 1);
+#endif
       for (int i = 0; i < C::NSTEP; ++i, ++gs) {
         const int st = (int)(gs % NS);
         if (gs >= NS) mbar_wait(&bar_empty[st], (uint32_t)((gs / NS - 1) & 1));

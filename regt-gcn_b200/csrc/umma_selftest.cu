@@ -14,6 +14,10 @@ using namespace tc;
 // variant 4: MN-major SW128 with 32-byte swizzle atoms (descriptor layout 1)  A[K][128], B[K][N]   (32-bit elements), SBO = 1024
 // variant 5: the same with SBO = 512: the 32-byte-atom swizzle repeats every FOUR 128-byte rows (CuTe's
 //            Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (1024 bits, 4 rows)), so consecutive K groups are 512 bytes apart
+// variant 6 / 7: MN-major without swizzle ("interleaved"): tile [MN/16 B][K rows][16 B], i.e. the 16 bytes of four fp32
+//            (eight bf16) consecutive MN indices of one K row are contiguous and the K rows of such a group are 16 bytes
+//            apart -- one 8 x 16 B core matrix per k-step; the groups along MN are K*16 bytes apart.
+//            6: LBO = K*16 (MN), SBO = 128 (K);  7: LBO = 128, SBO = K*16
 template <int FMT>
 __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ D, int variant, int N, int K) {
@@ -29,12 +33,14 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
   const int b_rows = mn ? K : N, b_cols = mn ? N : K;
   const bool a_chunk = (variant == 1), b_chunk = (variant == 1 || variant == 3);
   const bool b32 = (variant == 4 || variant == 5);
+  const bool inter = (variant == 6 || variant == 7);
   uint8_t* As = smem;
   uint8_t* Bs = smem + 64 * 1024;
 
   auto put = [&](uint8_t* base, bool chunk, int rows, int r, int c, float v) {
     uint32_t off = chunk ? chunk_off(r, (c * ES) >> 4, rows) + ((c * ES) & 15)
                          : (b32 ? sw128b32_off(r, c * ES, rows) : sw128_off(r, c * ES, rows));
+    if (inter) off = (uint32_t)(((c * ES) >> 4) * rows * 16 + r * 16 + ((c * ES) & 15));
     if constexpr (FMT == FMT_TF32) *reinterpret_cast<float*>(base + off) = v;
     else *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(v);
   };
@@ -63,6 +69,11 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
                      : make_desc(a0 + (kb >> 7) * a_rows * 128 + (kb & 127), 16, 1024, LAYOUT_SW128);
         db = b_chunk ? make_desc(b0 + s * 2 * b_rows * 16, b_rows * 16, 128, LAYOUT_NONE)
                      : make_desc(b0 + (kb >> 7) * b_rows * 128 + (kb & 127), 16, 1024, LAYOUT_SW128);
+      } else if (inter) {
+        const uint32_t mn_stride = (uint32_t)K * 16u, k_stride = 128u;
+        const uint32_t lbo = variant == 6 ? mn_stride : k_stride, sbo = variant == 6 ? k_stride : mn_stride;
+        da = make_desc(a0 + s * UK * 16, lbo, sbo, LAYOUT_NONE);
+        db = make_desc(b0 + s * UK * 16, lbo, sbo, LAYOUT_NONE);
       } else {
         const uint32_t lay = b32 ? LAYOUT_SW128_B32 : LAYOUT_SW128;
         const uint32_t sbo = (variant == 5) ? 512 : 1024;
@@ -94,7 +105,7 @@ extern "C" int regt_debug_umma_selftest(int fmt, int variant, const float* A, co
   using namespace regt;
   cudaStream_t st = (cudaStream_t)stream;
   REGT_CHECK(fmt == 1 || fmt == 2, "selftest: fmt must be 1 (bf16) or 2 (tf32)");
-  REGT_CHECK(variant >= 0 && variant <= 5 && N % 32 == 0 && N >= 32 && N <= 128, "selftest: bad variant/N");
+  REGT_CHECK(variant >= 0 && variant <= 7 && N % 32 == 0 && N >= 32 && N <= 128, "selftest: bad variant/N");
   const size_t smem = 129 * 1024;
   if (fmt == 2) {
     REGT_CUDA(cudaFuncSetAttribute(k_umma_selftest<tc::FMT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
