@@ -424,7 +424,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     const M1Cache mc{m1data, m1tag};
     // P(s) in two halves: Pcompute (h of step s on the CUDA cores, into registers; runs under the candidate MMAs of step
     // s - 1) and Pstore (registers -> TMEM A, S_t tile -> smem, bar_a; as soon as those MMAs have released A)
-    float hn[CWF], svn[8];
+    // h of the next step waits in the (free) z-gate accumulator columns of TMEM, not in registers: next to acc[] it pushed the
+    // epilogue warps over their 112 registers (ncu: 34 STL + 43 LDL per thread and step, through a 28 KB L1 into L2)
+    float svn[8];
     auto Pcompute = [&](int s) {
       const int k = s / a.T, t = s - k * a.T;
       const int qt = (int)blockIdx.x + k * (int)gridDim.x;
@@ -440,9 +442,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
       for (int j = 0; j < CWF; j += 16) {
         float h[16];
         h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hn[j + i] = h[i];
+        st_f32x16(tZ + c0 + j, h);     // acc_z is free here: E1z of this step has read it, the next z-gate MMAs wait for bar_a
       }
+      tmem_st_wait();
     };
     auto Pstore = [&]() {
       if (ch == 0) {   // the F-wide gate operand S_t of this row: two 16-byte chunks, hi | lo
@@ -462,8 +464,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float h[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = hn[j + i];
+        tmem_ld16(tZ + c0 + j, h);
         put_a16<HH>(tl, c0 + j, h);
       }
       tmem_st_wait();
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 // slot (conflict-free 4-byte stores) and one lane hands the slot to the bulk-copy engine (cp.async.bulk shared -> global),
 // which drains it while the warp computes on.
 #ifndef REGT_F_PREFETCH
-#define REGT_F_PREFETCH 0      // 1: the producer lane prefetches the next step's planes into L2 (see the note in k_cell_bwd_f)
+#define REGT_F_PREFETCH 2      // L2 prefetch of the next step's planes by the producer lane: 0 off, 1 a step ahead, 2 late (see k_cell_bwd_f)
 #endif
 #ifndef REGT_F_LDCS
 #define REGT_F_LDCS 1          // backward: Z and H~ (read once) with the streaming load operator
@@ -1026,21 +1027,37 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       if (t == 0) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.G) + (size_t)qt * TB, TB);
       prefetch_feats(a, t, qt);
     };
-#if REGT_F_PREFETCH
+    // REGT_F_PREFETCH 1: a whole step ahead (as the weight stages are issued) -- measured harmful: at 148 x 576 KB of plane
+    // traffic per step the lines are evicted again before their step comes and DRAM reads double (ncu: 7.6 GB against 3.3 GB
+    // per launch).  2 (default): when the dHR MMAs of step s complete (bar_1), i.e. 6-8 us before E0 of step s + 1 reads them.
+#if REGT_F_PREFETCH == 1
     if (S > 0) prefetch_step(0);
 #endif
     long long gs = 0;
     for (int s = 0; s < S; ++s) {
-#if REGT_F_PREFETCH
+#if REGT_F_PREFETCH == 1
       if (s + 1 < S) prefetch_step(s + 1);
 #endif
+      bool pf_pending = (REGT_F_PREFETCH == 2) && (s + 1 < S);
       for (int i = 0; i < C::NSTEP; ++i, ++gs) {
         const int st = (int)(gs % NS);
-        if (gs >= NS) mbar_wait(&bar_empty[st], (uint32_t)((gs / NS - 1) & 1));
+        if (gs >= NS) {
+          const uint32_t par = (uint32_t)((gs / NS - 1) & 1);
+          while (!mbar_try_wait(&bar_empty[st], par)) {
+            if (pf_pending && mbar_try_wait(&bar_1, (uint32_t)(s & 1))) {
+              prefetch_step(s + 1);
+              pf_pending = false;
+            }
+          }
+        }
         mbar_arrive_expect_tx(&bar_full[st], C::STAGE);
         const uint8_t* src = a.img + (size_t)i * C::STAGE;
 #pragma unroll
         for (int o = 0; o < C::STAGE; o += 16384) bulk_g2s(ring + (size_t)st * C::STAGE + o, src + o, 16384, &bar_full[st]);
+      }
+      if (pf_pending) {      // all stages of the step were issued before its dHR MMAs finished
+        mbar_wait(&bar_1, (uint32_t)(s & 1));
+        prefetch_step(s + 1);
       }
     }
   }

@@ -24,7 +24,8 @@ VARIANTS = {
     "xp_nostore": ["REGT_XP_SKIP_E0_STORES=1"],
     "tn2": ["REGT_TN_GROUP=2"],      # row contraction: drain the TMEM accumulator every 2 chunks (24 MMAs) instead of 8
     "tn4": ["REGT_TN_GROUP=4"],
-    "prefetch1": ["REGT_F_PREFETCH=1"],    # backward: L2 prefetch of the next step's planes (round-2 default until call X)
+    "prefetch1": ["REGT_F_PREFETCH=1"],    # backward: L2 prefetch of the next step's planes a whole step ahead (round-2 default until call X)
+    "prefetch0": ["REGT_F_PREFETCH=0"],    # backward: no L2 prefetch
     "stcs0": ["REGT_F_STCS=0"],            # backward: plain plane stores
     "ldcs0": ["REGT_F_LDCS=0"],            # backward: Z / H~ with ld.global.nc instead of the streaming operator
     "cache_plain": ["REGT_F_STCS=0", "REGT_F_LDCS=0"],
