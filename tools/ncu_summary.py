@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` report (read here, on the CPU box) into the tracked files under profiles/:
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_v7_bf16_ncu_full
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_v7_bf16_ncu_full [key-prefix]
 writes <out>.md (per-kernel table) and <out>.json, and refreshes profiles/ncu_traffic.json
-(kernel name -> DRAM bytes per launch at the default bench workload; bench.py's roofline.traffic)."""
+(kernel name -> DRAM bytes per launch at the default bench workload; bench.py's roofline.traffic).
+key-prefix "5/tf32x3/" files the entries under "<workload>/<precision>/<kernel>" (what bench.py looks up first)."""
 import csv
 import io
 import json
@@ -44,7 +45,7 @@ def to_float(v, unit):
     return x
 
 
-def main(rep, out):
+def main(rep, out, prefix=""):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -52,6 +53,7 @@ def main(rep, out):
     res = []
     for r in rows[2:]:
         name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").strip()
+        name = re.sub(r"<unnamed>::|unnamed>::|regt::|\(anonymous namespace\)::", "", name)
         d = {"kernel": name}
         for m, k in METRICS:
             if m in idx:
@@ -72,10 +74,10 @@ def main(rep, out):
     for d in res:
         if d.get("dram_read_MB") is not None:
             key = re.sub(r"<.*", "", d["kernel"])
-            traffic[key] = {"bytes_per_launch": int((d["dram_read_MB"] + d["dram_write_MB"]) * 1e6), "source": os.path.basename(out)}
+            traffic[prefix + key] = {"bytes_per_launch": int((d["dram_read_MB"] + d["dram_write_MB"]) * 1e6), "source": os.path.basename(out)}
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print(open(out + ".md").read())
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
