@@ -84,9 +84,18 @@ struct FCfg {
   static constexpr int TAIL = SW_IMG + C_FLOATS * 4;  // resident part of the image (copied once per CTA)
   static constexpr int IMG = RING_IMG + TAIL;
   static constexpr int S_TILE = 2 * TC_ROWS * 16;     // A operand of the F-wide part: S_t (8 tf32) per row, chunk tile
-  static constexpr int FIXED = ((TAIL + 1023) & ~1023) + 2 * S_TILE + 4 * 8 * HH * 4;   // + M1 cache (M1C, declared below)
+  // h_pre on the tensor cores (forward, regional mode): A = [X | U.1(r = ra) | U.1(r = rb)] per row, three K = 8 chunk tiles
+  // (hi | lo), B = [M0 ; M1[ra] ; M1[rb]]^T of the item, three chunk tiles (hi | lo)
+  static constexpr int XU_TILE = 3 * 2 * S_TILE;
+  static constexpr int WP_TILE = 3 * 2 * SW_TILE;
+  static constexpr int FIXED = ((TAIL + 1023) & ~1023) + 2 * S_TILE + 4 * 8 * HH * 4 + XU_TILE + WP_TILE;   // + M1 cache (M1C, declared below)
   static constexpr int NS_FIT = (SMEM_MAX - 2048 - FIXED) / STAGE;
+#ifdef REGT_F_NS_CAP
+  static constexpr int NS0 = NS_FIT < 2 * NSTEP ? NS_FIT : 2 * NSTEP;
+  static constexpr int NS = NS0 < REGT_F_NS_CAP ? NS0 : REGT_F_NS_CAP;   // TEST HOOK: shallower ring
+#else
   static constexpr int NS = NS_FIT < 2 * NSTEP ? NS_FIT : 2 * NSTEP;   // ring depth
+#endif
   static constexpr int SMEM = 1024 + NS * STAGE + FIXED;
   static constexpr int CWF = HH / 4;                  // columns per epilogue thread
   static constexpr int M1C = 4 * REGT_F * HH * 4;     // bytes of the 4-slot cache of per-region M1 blocks
@@ -378,9 +387,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
   uint8_t* tail = ring + C::NS * C::STAGE;                    // S-part weights | constants
   uint8_t* stile = tail + ((C::TAIL + 1023) & ~1023);         // S_t operand tile (hi | lo)
   float* m1data = reinterpret_cast<float*>(stile + 2 * C::S_TILE);
-  __shared__ uint64_t bar_full[C::NS], bar_empty[C::NS], bar_tail, bar_a, bar_z, bar_r, bar_a2, bar_c, bar_cfree;
+  uint8_t* xu = reinterpret_cast<uint8_t*>(m1data) + C::M1C;   // [3 k-steps][hi | lo] chunk tiles of [X | U(ra) | U(rb)]
+  uint8_t* wp = xu + C::XU_TILE;                               // [3 k-steps][hi | lo] chunk tiles of [M0 ; M1[ra] ; M1[rb]]^T
+  __shared__ uint64_t bar_full[C::NS], bar_empty[C::NS], bar_tail, bar_a, bar_z, bar_r, bar_a2, bar_c, bar_cfree, bar_x, bar_p;
   __shared__ uint32_t tmem_base_s;
   __shared__ int m1tag[4];
+  __shared__ int pregs[2], pover, puse;    // the (at most two) regions of the item's rows, "does not fit" flag, path of the item
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = (a.nqt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int S = n_items * a.T;
@@ -397,7 +409,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     mbar_init(&bar_a2, NEPI_W * 32);
     mbar_init(&bar_c, 1);
     mbar_init(&bar_cfree, NEPI_W * 32);
+    mbar_init(&bar_x, NEPI_W * 32);
+    mbar_init(&bar_p, 1);
     m1tag[0] = m1tag[1] = m1tag[2] = m1tag[3] = -1;
+    puse = 0;
     fence_barrier_init();
     mbar_arrive_expect_tx(&bar_tail, C::TAIL);
     for (int o = 0; o < C::TAIL; o += 16384) bulk_g2s(tail + o, a.img + C::RING_IMG + o, min(16384, C::TAIL - o), &bar_tail);
@@ -427,25 +442,113 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     // h of the next step waits in the (free) z-gate accumulator columns of TMEM, not in registers: next to acc[] it pushed the
     // epilogue warps over their 112 registers (ncu: 34 STL + 43 LDL per thread and step, through a 28 KB L1 into L2)
     float svn[8];
+    // h_pre = X M0 + U M1[region] (+ c0, leaky_relu) of the NEXT step.  Regional mode, items whose rows lie in at most two
+    // regions with one regional segment each (always, for the reference's contiguous regions of more than 64 nodes): ONE K = 24
+    // MMA group  [X | U.1(r = ra) | U.1(r = rb)] . [M0 ; M1[ra] ; M1[rb]]  into the free z-accumulator columns -- the epilogue
+    // threads only stage the 16 features of a row (ch 1: X, ch 2: U) instead of 512 FMAs per thread (4.2 of the 11.4 us of
+    // epilogue work per step).  Other items: the CUDA-core sum, parked in the same columns.
+    bool use_mma = false;
+    int slot = -1;                            // this row's region slot (0 = ra, 1 = rb), -1: no regional segment
+    constexpr int NEPI = NEPI_W * 32;
     auto Pcompute = [&](int s) {
       const int k = s / a.T, t = s - k * a.T;
       const int qt = (int)blockIdx.x + k * (int)gridDim.x;
       if (t == 0) {
         ri.set(a, qt, r);
-        // every epilogue thread has finished the previous item's last Pcompute before any of them gets here (bar_a2 chain)
-        m1_cache_fill<HH>(a, ri, m1data, m1tag, tid);
+        // every epilogue thread has finished the previous item's last Pcompute before any of them gets here (bar_a2 chain),
+        // and the previous item's last h_pre MMAs have completed (bar_p was waited on in Pstore)
+        const int nsg = ri.s1 - ri.s0;
+        const int reg = nsg > 0 ? a.seg_reg[ri.s0] : -1;
+        if (a.mode == REGT_MODE_REGIONAL) {
+          if (tid == 0) { pregs[0] = pregs[1] = -1; pover = 0; }
+          named_bar(1, NEPI);
+          if (ch == 0) {
+            if (nsg > 1) pover = 1;
+            else if (nsg == 1) {
+              const int o0 = atomicCAS(&pregs[0], -1, reg);
+              if (o0 != -1 && o0 != reg) {
+                const int o1 = atomicCAS(&pregs[1], -1, reg);
+                if (o1 != -1 && o1 != reg) pover = 1;
+              }
+            }
+          }
+          named_bar(1, NEPI);
+          use_mma = pover == 0;
+        } else {
+          use_mma = false;
+        }
+        if (use_mma) {
+          slot = nsg == 1 ? (pregs[0] == reg ? 0 : 1) : -1;
+          // B operand of the item: element (k-step j, output n, kk) at chunk (kk >> 2) of row n, hi | lo
+          for (int i = tid; i < 3 * F * HH; i += NEPI) {
+            const int j = i / (F * HH), rem = i - j * (F * HH), kk = rem / HH, n = rem - kk * HH;
+            float v;
+            if (j == 0) v = consts[C::C_M0 + kk * HH + n];
+            else {
+              const int rg = pregs[j - 1];
+              v = rg >= 0 ? __ldg(a.M1t + ((size_t)rg * F + kk) * HH + n) : 0.f;
+            }
+            const float hi = __uint_as_float(tf32_rn_bits(v));
+            uint8_t* w0 = wp + j * 2 * C::SW_TILE + chunk_off(n, kk >> 2, HH) + (kk & 3) * 4;
+            *reinterpret_cast<float*>(w0) = hi;
+            *reinterpret_cast<float*>(w0 + C::SW_TILE) = v - hi;
+          }
+          if (tid == 0) puse = 1;
+        } else {
+          if (tid == 0) puse = 0;
+          m1_cache_fill<HH>(a, ri, m1data, m1tag, tid);
+        }
       }
-      Feats f;
-      load_feats(a, ri, t, f);
       if (ch == 0) load8(a.St + ((size_t)t * a.BN + (ri.valid ? ri.q : 0)) * F, svn, ri.valid ? 1.f : 0.f);
+      if (use_mma) {
+        if (ch == 1 || ch == 2) {
+          float v[8];
+          const float m = ri.valid ? 1.f : 0.f;
+          if (ch == 1) load8(a.Xt + ((size_t)t * a.BN + (ri.valid ? ri.q : 0)) * F, v, m);
+          else if (slot >= 0) load8(a.Ut + (((size_t)t * a.Bsz + ri.b) * a.nseg + ri.s0) * F, v, m);
+          else {
 #pragma unroll
-      for (int j = 0; j < CWF; j += 16) {
-        float h[16];
-        h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
-        st_f32x16(tZ + c0 + j, h);     // acc_z is free here: E1z of this step has read it, the next z-gate MMAs wait for bar_a
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          }
+          float hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            hi[i] = __uint_as_float(tf32_rn_bits(v[i]));
+            lo[i] = v[i] - hi[i];
+          }
+          const int j = ch == 1 ? 0 : (slot == 1 ? 2 : 1);      // k-step that receives this row's values
+          uint8_t* t0 = xu + j * 2 * C::S_TILE;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            *reinterpret_cast<float4*>(t0 + chunk_off(r, c, TC_ROWS)) = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            *reinterpret_cast<float4*>(t0 + C::S_TILE + chunk_off(r, c, TC_ROWS)) = make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+          if (ch == 2) {    // the other region slot of this row is zero
+            uint8_t* z0 = xu + (j == 1 ? 2 : 1) * 2 * C::S_TILE;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              *reinterpret_cast<float4*>(z0 + chunk_off(r, c, TC_ROWS)) = zero;
+              *reinterpret_cast<float4*>(z0 + C::S_TILE + chunk_off(r, c, TC_ROWS)) = zero;
+            }
+          }
+        }
+        fence_proxy_async();
+      } else {
+        Feats f;
+        load_feats(a, ri, t, f);
+#pragma unroll
+        for (int j = 0; j < CWF; j += 16) {
+          float h[16];
+          h16<HH>(a, consts, mc, ri, f, t, c0 + j, h);
+          st_f32x16(tZ + c0 + j, h);     // acc_z is free here: E1z of this step has read it, the next z-gate MMAs wait for bar_a
+        }
+        tmem_st_wait();
       }
-      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_x);               // operands staged (or h parked): the MMA warp issues the h_pre MMAs / passes on
     };
+    int n_p = 0;                         // completed bar_p phases consumed
     auto Pstore = [&]() {
       if (ch == 0) {   // the F-wide gate operand S_t of this row: two 16-byte chunks, hi | lo
         float hi[8], lo[8];
@@ -461,10 +564,20 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
         }
         fence_proxy_async();
       }
+      mbar_wait(&bar_p, (uint32_t)(n_p & 1));
+      ++n_p;
+      tc_fence_after();
 #pragma unroll
       for (int j = 0; j < CWF; j += 16) {
         float h[16];
         tmem_ld16(tZ + c0 + j, h);
+        if (use_mma) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v = h[i] + consts[C::C_C0 + c0 + j + i];
+            h[i] = v > 0.f ? v : 0.01f * v;          // F.leaky_relu of the regional combine
+          }
+        }
         put_a16<HH>(tl, c0 + j, h);
       }
       tmem_st_wait();
@@ -578,7 +691,30 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
   } else if (warp == W_MMA) {
     mbar_wait(&bar_tail, 0);
     const uint32_t ring0 = smem_u32(ring), sw0 = smem_u32(tail), st0 = smem_u32(stile);
+    const uint32_t xu0 = smem_u32(xu), wp0 = smem_u32(wp);
+    const volatile int* puse_v = &puse;
+    // h_pre of step s: [X | U(ra) | U(rb)] . [M0 ; M1[ra] ; M1[rb]] -> the z-accumulator columns (free between E1z of step s - 1
+    // and the z-gate MMAs of step s), K = 3 x 8, three tf32 products each; items on the CUDA-core path only pass the barrier on
+    auto pmma = [&](int s) {
+      mbar_wait(&bar_x, (uint32_t)(s & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        if (*puse_v) {
+          const uint32_t idesc = make_idesc(FMT_TF32, 128, HH, 0, 0);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+              umma<FMT_TF32>(tmem + 2 * HH, make_desc(xu0 + j * 2 * C::S_TILE + (p == 1 ? C::S_TILE : 0), TC_ROWS * 16, 128, LAYOUT_NONE),
+                             make_desc(wp0 + j * 2 * C::SW_TILE + (p == 2 ? C::SW_TILE : 0), HH * 16, 128, LAYOUT_NONE), idesc,
+                             (j > 0 || p > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_p);
+      }
+      __syncwarp();
+    };
     long long gs = 0;
+    if (S > 0) pmma(0);
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       mbar_wait(&bar_a, ph);
@@ -601,6 +737,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
       mma_spart<HH>(tmem, 3 * HH, st0, sw0 + 4 * C::SW_TILE, lane);
       if (lane == 0) umma_commit(&bar_c);
       __syncwarp();
+      if (s + 1 < S) pmma(s + 1);
     }
     tc_fence_before();
   } else if (warp == W_PROD && lane == 0) {

@@ -26,6 +26,8 @@ VARIANTS = {
     "tn4": ["REGT_TN_GROUP=4"],
     "prefetch1": ["REGT_F_PREFETCH=1"],    # backward: L2 prefetch of the next step's planes a whole step ahead (round-2 default until call X)
     "prefetch0": ["REGT_F_PREFETCH=0"],    # backward: no L2 prefetch
+    "fns3": ["REGT_F_NS_CAP=3"],           # forward: weight ring of 3 stages instead of 5 (what an extra 48 KB of operands would leave)
+    "fns4": ["REGT_F_NS_CAP=4"],
     "stcs0": ["REGT_F_STCS=0"],            # backward: plain plane stores
     "ldcs0": ["REGT_F_LDCS=0"],            # backward: Z / H~ with ld.global.nc instead of the streaming operator
     "cache_plain": ["REGT_F_STCS=0", "REGT_F_LDCS=0"],
