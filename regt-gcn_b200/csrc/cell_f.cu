@@ -49,7 +49,9 @@ namespace regt {
 using namespace tc;
 
 // phase timestamps of CTA 0 / epilogue thread 0 (REGT_F_DEBUG=1; read back with regt_debug_f_timestamps): 16 steps x 12 marks
-__device__ long long g_f_dbg[2][16 * 12];
+__device__ long long g_f_dbg[3][16 * 12];      // [2]: marks of the forward's MMA warp (lane 0)
+#define F_TSM(i)                                                                              \
+  if (a.dbg && blockIdx.x == 0 && lane == 0 && s >= a.dbg && s < a.dbg + 16) g_f_dbg[2][(s - a.dbg) * 12 + (i)] = clock64();
 #define F_TS(which, i)                                                                        \
   if (a.dbg && blockIdx.x == 0 && tid == 0 && s >= a.dbg && s < a.dbg + 16) g_f_dbg[which][(s - a.dbg) * 12 + (i)] = clock64();
 
@@ -117,6 +119,7 @@ struct FArgs {
   const float* G;                  // gradient wrt out_hidden, tile layout [nqt][H/4][128][4] (the head writes it that way)
   float *D, *hpl, *hRpl;           // transposed tiles [T*nqt][4 row quarters][4H | H | H][32 rows]
   double* dpp;                     // [grid][T] attention-gradient partials
+  int hpre_mma;                    // forward: h_pre on the tensor cores where the item allows it (TEST HOOK REGT_F_HPRE_MMA=0: CUDA cores)
 };
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(float a) {
@@ -312,13 +315,15 @@ __device__ __forceinline__ void h16(const FArgs& a, const float* consts, const M
 // (hi*hi + lo*hi + hi*lo).  Called by the whole MMA warp; lane 0 issues.
 template <int HH>
 __device__ __forceinline__ void mma_block(uint32_t tmem, uint32_t acc_col, uint32_t ring0, uint64_t* bar_full, uint64_t* bar_empty,
-                                          long long& gs, int lane, bool accumulate) {
+                                          long long& gs, int lane, bool accumulate, long long* wait_clk = nullptr) {
   using C = FCfg<HH>;
   const uint32_t idesc = make_idesc(FMT_TF32, 128, HH, 0, 0);
 #pragma unroll 1
   for (int kc = 0; kc < C::NCH; ++kc, ++gs) {
     const int st = (int)(gs % C::NS);
+    const long long w0 = wait_clk ? clock64() : 0;
     mbar_wait(&bar_full[st], (uint32_t)((gs / C::NS) & 1));
+    if (wait_clk) *wait_clk += clock64() - w0;
     tc_fence_after();
     if (lane == 0) {
       const uint32_t bt = ring0 + st * C::STAGE;
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
         // and the previous item's last h_pre MMAs have completed (bar_p was waited on in Pstore)
         const int nsg = ri.s1 - ri.s0;
         const int reg = nsg > 0 ? a.seg_reg[ri.s0] : -1;
-        if (a.mode == REGT_MODE_REGIONAL) {
+        if (a.mode == REGT_MODE_REGIONAL && a.hpre_mma) {
           if (tid == 0) { pregs[0] = pregs[1] = -1; pover = 0; }
           named_bar(1, NEPI);
           if (ch == 0) {
@@ -717,27 +722,38 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
     if (S > 0) pmma(0);
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
+      long long wclk = 0;
+      long long* wp_clk = a.dbg ? &wclk : nullptr;
+      F_TSM(0)
       mbar_wait(&bar_a, ph);
       tc_fence_after();
-      mma_block<HH>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false);
+      F_TSM(1)
+      mma_block<HH>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false, wp_clk);
       mma_spart<HH>(tmem, 2 * HH, st0, sw0, lane);
       if (lane == 0) umma_commit(&bar_z);
       __syncwarp();
+      F_TSM(2)
       if (s > 0) {   // acc_c of the previous step (same columns as acc_r) has been read
         mbar_wait(&bar_cfree, (uint32_t)((s - 1) & 1));
         tc_fence_after();
       }
-      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false);
+      F_TSM(3)
+      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false, wp_clk);
       mma_spart<HH>(tmem, 3 * HH, st0, sw0 + 2 * C::SW_TILE, lane);
       if (lane == 0) umma_commit(&bar_r);
       __syncwarp();
+      F_TSM(4)
       mbar_wait(&bar_a2, ph);
       tc_fence_after();
-      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false);
+      F_TSM(5)
+      mma_block<HH>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, false, wp_clk);
       mma_spart<HH>(tmem, 3 * HH, st0, sw0 + 4 * C::SW_TILE, lane);
       if (lane == 0) umma_commit(&bar_c);
       __syncwarp();
+      F_TSM(6)
       if (s + 1 < S) pmma(s + 1);
+      F_TSM(7)
+      if (a.dbg && blockIdx.x == 0 && lane == 0 && s >= a.dbg && s < a.dbg + 16) g_f_dbg[2][(s - a.dbg) * 12 + 8] = wclk;
     }
     tc_fence_before();
   } else if (warp == W_PROD && lane == 0) {
@@ -1310,6 +1326,8 @@ FArgs make_fargs(const regt_args* a, const Layout& L) {
   {
     const char* e = getenv("REGT_F_DEBUG");
     k.dbg = e ? atoi(e) : 0;
+    const char* hm = getenv("REGT_F_HPRE_MMA");     // read per launch: the test toggles it inside one process
+    k.hpre_mma = !(hm && hm[0] == '0');
   }
   k.G = L.G; k.D = L.D; k.hpl = L.h; k.hRpl = L.hR; k.dpp = reinterpret_cast<double*>(L.tc_dpp);
   return k;
@@ -1388,6 +1406,6 @@ int launch_feat_f(const regt_args* a, const Layout& L, cudaStream_t st) {
 // TEST HOOK: phase timestamps (clock64) of the fused kernels, recorded when REGT_F_DEBUG=<first step> is set:
 // out[which][step][mark], which 0 = forward, 1 = backward, 16 steps x 12 marks each
 extern "C" int regt_debug_f_timestamps(long long* out) {
-  REGT_CUDA(cudaMemcpyFromSymbol(out, regt::g_f_dbg, sizeof(long long) * 2 * 16 * 12));
+  REGT_CUDA(cudaMemcpyFromSymbol(out, regt::g_f_dbg, sizeof(long long) * 3 * 16 * 12));
   return 0;
 }

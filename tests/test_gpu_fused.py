@@ -63,6 +63,29 @@ def test_fused_cell_matches_oracle(w, B, unfused, monkeypatch):
             assert e <= bound, f"grad {k}: {e:.3e} (fp32 twin {twin[k]:.3e})"
 
 
+def test_forward_hpre_tensor_core_path_against_cuda_core_path(monkeypatch):
+    """the forward computes h_pre of the regional combine as a K = 24 MMA group where a 128-row item lies in at most two regions
+    (cell_f.cu: Pcompute), and on the CUDA cores otherwise; REGT_F_HPRE_MMA=0 forces the CUDA-core sum for every item.  Both must
+    agree to 3xTF32 accuracy on a case whose items take the MMA path, and must not be bit-identical (the MMA path did run)."""
+    w = W.tiny_workload("RegionalTemporalGCN", N=700, T=4, H=128, O=4, R=5, B=6, seed=9)
+    ref = oracle_step(w, 6)
+    x, y = w.inputs(6)
+    g = to_dev(w.graph_args(), "cuda")
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("REGT_F_HPRE_MMA", flag)
+        m = build_cuda(w, ref["state"], precision="tf32x3")
+        loss, out, hid = m.fused_step(x.cuda(), y.cuda(), *g)
+        torch.cuda.synchronize()
+        outs[flag] = (hid.clone(), out.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+        assert relerr(hid, ref["hid"]) <= 1e-5 and relerr(out, ref["out"]) <= 1e-5
+    assert relerr(outs["1"][0], outs["0"][0]) <= 3e-6 and relerr(outs["1"][1], outs["0"][1]) <= 3e-6
+    assert not torch.equal(outs["1"][0], outs["0"][0])
+    for k in outs["0"][2]:
+        if not is_dead(w.model, k) and not k.endswith("_attention"):
+            assert relerr(outs["1"][2][k], outs["0"][2][k]) <= 2e-5, k
+
+
 def test_fused_cell_autograd_surface():
     """the reference's call sites use model(...) + loss.backward(): same kernels behind the autograd Function."""
     w = W.tiny_workload("RegionalTemporalGCN", N=300, T=6, H=128, O=12, R=7, B=2, seed=25, k_intra=4)

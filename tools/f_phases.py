@@ -20,7 +20,7 @@ x, y = x.to(dev), y.to(dev)
 for _ in range(2):
     m.fused_step(x, y, *g)
 torch.cuda.synchronize()
-buf = (C.c_longlong * (2 * 16 * 12))()
+buf = (C.c_longlong * (3 * 16 * 12))()
 _lib.check(_lib.load().regt_debug_f_timestamps(buf), "timestamps")
 names = {0: ["wait z-gate MMAs", "E1z (sigmoid, save Z, acc)", "wait r-gate MMAs", "E1r (sigmoid, save R, h*R -> A)", "Pcompute(next) [REGT_F_PRE]",
              "wait candidate MMAs", "Pstore(next) (+Pcompute if not PRE)", "E2 (tanh, save H~, acc)"],
@@ -43,3 +43,13 @@ for which, title in ((0, "forward k_cell_fwd_f"), (1, "backward k_cell_bwd_f")):
             print(f"      {nm:52s} {sum(r[i1] - r[i0] for r in rows) / len(rows) / 1.9e3:7.2f} us")
     step = sum(rows[i + 1][0] - rows[i][0] for i in range(len(rows) - 1)) / max(1, len(rows) - 1) / 1.9e3
     print(f"   {'sum of phases':55s} {tot:7.2f} us      step to step {step:7.2f} us")
+
+# forward, MMA warp (lane 0 of CTA 0): when the gate blocks are ISSUED (the tensor pipe runs behind the issue by its queue)
+rows = [[buf[(2 * 16 + s) * 12 + i] for i in range(12)] for s in range(16)]
+rows = [r for r in rows if r[0] > 0 and r[7] > 0]
+if rows:
+    print(f"== forward, MMA warp: {len(rows)} steps")
+    for nm, (i0, i1) in (("wait bar_a (h staged)", (0, 1)), ("issue z block (incl. waits for weight stages)", (1, 2)), ("wait acc_c free", (2, 3)),
+                         ("issue r block", (3, 4)), ("wait bar_a2 (h*R staged)", (4, 5)), ("issue c block", (5, 6)), ("wait bar_x + issue h_pre MMAs", (6, 7))):
+        print(f"   {nm:55s} {sum(r[i1] - r[i0] for r in rows) / len(rows) / 1.9e3:7.2f} us")
+    print(f"   {'of which: waiting for weight stages (bar_full)':55s} {sum(r[8] for r in rows) / len(rows) / 1.9e3:7.2f} us")
