@@ -35,9 +35,6 @@
 #define REGT_F_PRE 1
 #endif
 // timing experiments only (results are wrong with either): what the recompute of h and the E0 stores cost
-#ifndef REGT_F_BULKSTORE
-#define REGT_F_BULKSTORE 0     // 1: backward planes leave through shared-memory slots + cp.async.bulk (measured slower, see WarpStore)
-#endif
 #ifndef REGT_XP_SKIP_H16
 #define REGT_XP_SKIP_H16 0
 #endif
@@ -792,10 +789,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 // Lane = row makes every store of one column a contiguous 128-byte line -- and a [column][row] tile is exactly the K-major
 // operand the row contraction wants (K = rows): gemm_tma.cu reads these tiles with plain TMA boxes and no transposing
 // converters.  v2 issued those lines as 192 scalar st.global per thread and step: 8.5 of the 17.7 us of phase E0 were spent
-// stalled on the store path (timing experiment REGT_XP_SKIP_E0_STORES, tools/f_phases.py).  v3: the 16 columns x 32 rows a
-// warp produces per chunk are one contiguous 2 KB run of this layout; the lanes put them into a per-warp shared-memory
-// slot (conflict-free 4-byte stores) and one lane hands the slot to the bulk-copy engine (cp.async.bulk shared -> global),
-// which drains it while the warp computes on.
+// stalled on the store path (timing experiment REGT_XP_SKIP_E0_STORES, tools/f_phases.py).  Staging the lines in per-warp
+// shared-memory slots for the bulk-copy engine (cp.async.bulk shared -> global) measured slower (33.3 vs 29.8 us per step: a put
+// waits for the engine to have read the slot used two puts ago); what did help is in profiles/r02_fused_phases.md.
 #ifndef REGT_F_PREFETCH
 #define REGT_F_PREFETCH 2      // L2 prefetch of the next step's planes by the producer lane: 0 off, 1 a step ahead, 2 late (see k_cell_bwd_f)
 #endif
@@ -808,60 +804,17 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_fwd_f(FArgs a) {
 template <int HH>
 struct BCfg {   // shared-memory plan of the backward: ring | resident tail | M1 cache
   using C = FCfg<HH>;
-  static constexpr int SLOT = 16 * 32 * 4;                        // one staged chunk: 16 columns x 32 rows
-  static constexpr int NSLOT = 2;                                 // per warp (the copy engine reads one while the lanes fill the other)
   // Dz (then Dr) of the step: HH/4 values per epilogue thread that live from E0 to the Dr -> A conversion.  In registers, next
   // to E0's unrolled 16-column chunks, they pushed the epilogue warps far over their 112 registers (ncu: 62 STL + 94 LDL per
   // thread and step, 5 GB of spill traffic per launch through a 28 KB L1 into L2 -- a quarter of the kernel's L2 traffic, and
   // E0 is L2-bound: with a quarter of the CTAs it takes 11.6 us instead of 18.5).  The backward does not need a deep weight
   // ring (its MMAs wait for the epilogue, not for the weights): two of its stages pay for a [HH/4][512] plane in shared memory.
   static constexpr int DZS = NEPI_W * 32 * (HH / 4) * 4;
-  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C + (REGT_F_BULKSTORE ? NEPI_W * NSLOT * SLOT : 0) + DZS;
+  static constexpr int FIXED = ((C::TAIL + 1023) & ~1023) + C::M1C + DZS;
   static constexpr int NS_FIT = (SMEM_MAX - 12288 - FIXED) / C::STAGE;
   static constexpr int NS = NS_FIT < 2 * C::NSTEP ? NS_FIT : 2 * C::NSTEP;
   static constexpr int SMEM = 1024 + NS * C::STAGE + FIXED;
   static_assert(NS >= 3, "backward ring too shallow");
-};
-
-// one warp's chunk (16 columns x its 32 rows) -> global through the bulk-copy engine.  v[i] = this lane's value of column i.
-struct WarpStore {
-  float* slot0;      // this warp's NSLOT staging slots
-  int n;             // stores issued so far
-  __device__ __forceinline__ void put(int lane, float* dst, const float (&v)[16], bool stream = true) {
-#if !REGT_F_BULKSTORE
-    // plain stores: one 128-byte line per column.  Measured against the staged bulk stores below (tools/f_phases.py, config 4):
-    // 29.8 us per backward step vs 33.3 us -- with two slots per warp a put waits ~0.7 us for the copy engine to have read the
-    // slot used two puts ago, and shared memory has no room for more slots
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-#if REGT_F_STCS
-      if (stream) __stcs(dst + i * 32 + lane, v[i]);
-      else
-#endif
-        dst[i * 32 + lane] = v[i];
-    }
-    return;
-#endif
-    float* sl = slot0 + (n & 1) * (16 * 32);
-    if (lane == 0) bulk_wait_read<1>();       // the store that used this slot two puts ago has read it
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sl[i * 32 + lane] = v[i];
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      bulk_s2g(dst, sl, 16 * 32 * 4);
-      bulk_commit();
-    }
-    ++n;
-  }
-  // all stores of this warp have landed (and are visible to its lanes): before re-reading them, and before the kernel ends
-  __device__ __forceinline__ void drain(int lane) {
-#if REGT_F_BULKSTORE
-    if (lane == 0) bulk_wait<0>();
-#endif
-    __syncwarp();
-  }
 };
 
 template <int HH, int NS>
@@ -889,6 +842,34 @@ __device__ __forceinline__ void mma_block_n(uint32_t tmem, uint32_t acc_col, uin
     __syncwarp();
   }
 }
+// ONE K chunk (32 A columns) of an H x H block, gated on `ready` (the epilogue threads have staged exactly these A columns);
+// `done`, if given, gets an arrive when the chunk's MMAs (and everything before them) have completed
+template <int HH, int NS>
+__device__ __forceinline__ void mma_chunk_n(uint32_t tmem, uint32_t acc_col, uint32_t ring0, uint64_t* bar_full, uint64_t* bar_empty,
+                                            long long& gs, int lane, int kc, bool accumulate, uint64_t* ready, uint32_t parity,
+                                            uint64_t* done) {
+  using C = FCfg<HH>;
+  const uint32_t idesc = make_idesc(FMT_TF32, 128, HH, 0, 0);
+  mbar_wait(ready, parity);
+  const int st = (int)(gs % NS);
+  mbar_wait(&bar_full[st], (uint32_t)((gs / NS) & 1));
+  tc_fence_after();
+  if (lane == 0) {
+    const uint32_t bt = ring0 + st * C::STAGE;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const uint32_t ap = tmem + (p == 1 ? HH : 0) + kc * 32, bp = bt + (p == 2 ? C::TILE : 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ts_tf32(tmem + acc_col, ap + 8 * k, make_desc(bp + k * 32, 16, 1024, LAYOUT_SW128), idesc,
+                     (accumulate || kc > 0 || p > 0 || k > 0) ? 1u : 0u);
+    }
+    umma_commit(&bar_empty[st]);
+    if (done) umma_commit(done);
+  }
+  __syncwarp();
+  ++gs;
+}
 template <int HH, int NS>
 __device__ __forceinline__ void produce_n(const uint8_t* img, uint8_t* ring, uint64_t* bar_full, uint64_t* bar_empty, long long total) {
   using C = FCfg<HH>;
@@ -906,17 +887,16 @@ template <int HH>
 __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   using C = FCfg<HH>;
   using BC = BCfg<HH>;
-  constexpr int CWF = C::CWF;
   constexpr int NS = BC::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = sm;
   uint8_t* tail = ring + NS * C::STAGE;
   float* m1data = reinterpret_cast<float*>(tail + ((C::TAIL + 1023) & ~1023));
-  float* slots = m1data + C::M1C / 4;
-  float* dzp = slots + (REGT_F_BULKSTORE ? NEPI_W * BC::NSLOT * BC::SLOT / 4 : 0) + (threadIdx.x & (NEPI_W * 32 - 1));   // [HH/4][512]: this thread's column
+  float* dzp = m1data + C::M1C / 4 + (threadIdx.x & (NEPI_W * 32 - 1));   // Dz plane [HH/4][512]: this thread's column
 #define DZ(i) dzp[(i) * (NEPI_W * 32)]
-  __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tail, bar_a, bar_1, bar_az, bar_2z, bar_ar, bar_2r;
+  // per K chunk: A columns of the chunk staged (bar_a / bar_az / bar_ar, all epilogue threads), M2z MMAs of the chunk done (bar_2z)
+  __shared__ uint64_t bar_full[NS], bar_empty[NS], bar_tail, bar_a[4], bar_1, bar_az[4], bar_2z[4], bar_ar[4], bar_2r;
   __shared__ uint32_t tmem_base_s;
   __shared__ int m1tag[4];
   __shared__ double red[NEPI_W][64];      // attention-gradient partials: fp64 sums (see below)
@@ -930,11 +910,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_tail, 1);
-    mbar_init(&bar_a, NEPI_W * 32);
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(&bar_a[c], NEPI_W * 32);
+      mbar_init(&bar_az[c], NEPI_W * 32);
+      mbar_init(&bar_ar[c], NEPI_W * 32);
+      mbar_init(&bar_2z[c], 1);
+    }
     mbar_init(&bar_1, 1);
-    mbar_init(&bar_az, NEPI_W * 32);
-    mbar_init(&bar_2z, 1);
-    mbar_init(&bar_ar, NEPI_W * 32);
     mbar_init(&bar_2r, 1);
     m1tag[0] = m1tag[1] = m1tag[2] = m1tag[3] = -1;
     fence_barrier_init();
@@ -953,12 +935,17 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
   if (warp < NEPI_W) {
     mbar_wait(&bar_tail, 0);
     const int qd = warp & 3, ch = warp >> 2;
-    const int r = qd * 32 + lane, c0 = ch * CWF;
+    const int r = qd * 32 + lane;
+    // Column ownership is K-CHUNK-MAJOR: in trip j a thread works on columns [32 j + 8 ch, + 8), so that after trip j of all
+    // threads the 32 columns of K chunk j are complete and the MMA warp can issue that chunk while the epilogue is in trip j + 1
+    // (with [32 ch, + 32) per thread a block of MMAs could only start when the whole phase was over: 2.8 + 2.2 us of waiting per
+    // step for the dHR and dhg blocks).
+    constexpr int NTRIP = C::NCH;
+    const int cb = 8 * ch;
     const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
     const uint32_t t1c = tl + 2 * HH, t2c = tl + 3 * HH;   // acc1 = dHR (then dHR * R), acc2 = p G Z + dhg
     Row ri;
     const M1Cache mc{m1data, m1tag};
-    WarpStore ws{slots + warp * (BC::NSLOT * BC::SLOT / 4), 0};
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
       const int k = s / a.T, t = s - k * a.T;
@@ -989,8 +976,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
       // transposed tiles).  Unrolled over 16-column chunks the compiler kept up to 16 float4 loads and five 16-column arrays
       // alive at once and spilled (see BCfg).
 #pragma unroll 1
-      for (int j = 0; j < CWF; j += 8) {
-        const int c = c0 + j;
+      for (int j = 0; j < NTRIP; ++j) {
+        const int c = 32 * j + cb;
         float4 zq[2], rq[2], cq[2], gq[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -1033,7 +1020,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
             const float dzv = gg * (hh - hc[e]) * z[e] * (1.0f - z[e]);
             dc[i + e] = gg * (1.0f - z[e]) * (1.0f - hc[e] * hc[e]);
             gz[i + e] = gg * z[e];
-            DZ(j + i + e) = dzv;
+            DZ(8 * j + i + e) = dzv;
             if (!(hh > 0.f)) ng |= 1u << (i + e);
 #if !REGT_XP_SKIP_E0_STORES
             o_h[(i + e) * 32] = hh;                                           // re-read in E1: not streamed
@@ -1049,16 +1036,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
 #endif
           }
         }
-        neg |= ng << j;
+        neg |= ng << (8 * j);
         dp += (double)dpc;
         if (j == 0) { F_TS(1, 10) }
         put_a8<HH>(tl, c, dc);
         st_f32x8(t2c + c, gz);                    // acc2 starts from p G Z: the dhg MMAs accumulate on top of it
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_a[j]);                   // K chunk j of Dc is staged: its dHR MMAs run under the next trip
         if (j == 0) { F_TS(1, 11) }
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bar_a);
       F_TS(1, 1)
       // attention gradient d probs[t] += sum G * H'_t.  The softmax Jacobian takes differences of these nearly equal sums
       // (models/RegionalTemporalGCN.py:134), so everything above 16 terms is summed in fp64: fixed-order warp sum, one
@@ -1066,102 +1053,98 @@ __global__ void __launch_bounds__(NTHR, 1) k_cell_bwd_f(FArgs a) {
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, d);
       if (lane == 0) red[warp][t] += dp;
-      // ---- M1 done (dHR in acc1): Dz -> A, M2z starts ----
+      // ---- M1 done (dHR in acc1): Dz -> A chunk by chunk, M2z follows the chunks ----
       mbar_wait(&bar_1, ph);
       tc_fence_after();
       F_TS(1, 2)
 #pragma unroll
-      for (int j = 0; j < CWF; j += 16) {
-        float v[16];
+      for (int j = 0; j < NTRIP; ++j) {
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = DZ(j + i);
-        put_a16<HH>(tl, c0 + j, v);
+        for (int i = 0; i < 8; ++i) v[i] = DZ(8 * j + i);
+        put_a8<HH>(tl, 32 * j + cb, v);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_az[j]);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bar_az);
       F_TS(1, 3)
-      // ---- E1 (under M2z): Dr = dHR h R (1-R) (registers, reusing dz), t1 = dHR R -> acc1 in place ----
-      ws.drain(lane);     // the h tiles of E0 have landed: they are re-read below with ordinary loads
+      // ---- E1 (under M2z): Dr = dHR h R (1-R), t1 = dHR R -> acc1 in place; as soon as the M2z MMAs of K chunk j have read A,
+      //      Dr of that chunk goes in and its M2r MMAs follow ----
+      __syncwarp();       // the h lines of E0 (this warp's own stores) are re-read below with ordinary loads
+#pragma unroll 1
+      for (int j = 0; j < NTRIP; ++j) {
+        const int c = 32 * j + cb;
+        float v[8], hh[8], dr[8];
+        float4 rq[2];
 #pragma unroll
-      for (int j = 0; j < CWF; j += 16) {
-        float v[16], hh[16], dr[16];
-        float4 rq[4];
-        // h (this warp's own bulk stores of E0) and R of the chunk, all in flight before the first use
+        for (int i = 0; i < 8; ++i) hh[i] = hT[(size_t)(c + i) * 32 + lane];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hh[i] = hT[(size_t)(c0 + j + i) * 32 + lane];
+        for (int i = 0; i < 2; ++i) rq[i] = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c + 4 * i)));
+        tmem_ld8(t1c + c, v);
+        float* o_dr = DT + (size_t)(HH + c) * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rq[i] = __ldg(reinterpret_cast<const float4*>(rt + piece(r, c0 + j + 4 * i)));
-        tmem_ld16(t1c + c0 + j, v);
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
+        for (int i = 0; i < 8; i += 4) {
           const float rg[4] = {rq[i >> 2].x, rq[i >> 2].y, rq[i >> 2].z, rq[i >> 2].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             dr[i + e] = v[i + e] * hh[i + e] * rg[e] * (1.0f - rg[e]);
-            DZ(j + i + e) = dr[i + e];
             v[i + e] *= rg[e];
+#if REGT_F_STCS
+            __stcs(o_dr + (i + e) * 32, dr[i + e]);
+#else
+            o_dr[(i + e) * 32] = dr[i + e];
+#endif
           }
         }
-        st_f32x16(t1c + c0 + j, v);
-        ws.put(lane, DT + (size_t)(HH + c0 + j) * 32, dr);
+        st_f32x8(t1c + c, v);
+        mbar_wait(&bar_2z[j], ph);                // A columns of chunk j are free (Dz of the chunk has been consumed)
+        tc_fence_after();
+        put_a8<HH>(tl, c, dr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_ar[j]);
       }
-      tmem_st_wait();
       F_TS(1, 4)
-      // ---- M2z done (A free): Dr -> A, M2r ----
-      mbar_wait(&bar_2z, ph);
-      tc_fence_after();
       F_TS(1, 5)
-#pragma unroll
-      for (int j = 0; j < CWF; j += 16) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = DZ(j + i);
-        put_a16<HH>(tl, c0 + j, v);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&bar_ar);
       F_TS(1, 6)
       // ---- E2: d h_pre = act'(h) (p G Z + dhg + dHR R) ----
       mbar_wait(&bar_2r, ph);
       tc_fence_after();
       F_TS(1, 7)
+#pragma unroll 1
+      for (int j = 0; j < NTRIP; ++j) {
+        const int c = 32 * j + cb;
+        float v[8], u[8];
+        tmem_ld8(t2c + c, v);
+        tmem_ld8(t1c + c, u);
+        float* o_dh = DT + (size_t)(3 * HH + c) * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < CWF; j += 16) {
-        float v[16], u[16];
-        tmem_ld16(t2c + c0 + j, v);
-        tmem_ld16(t1c + c0 + j, u);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           float d = v[i] + u[i];
-          if (a.mode == REGT_MODE_REGIONAL && ((neg >> (j + i)) & 1u)) d *= 0.01f;
-          v[i] = d;
+          if (a.mode == REGT_MODE_REGIONAL && ((neg >> (8 * j + i)) & 1u)) d *= 0.01f;
+#if REGT_F_STCS
+          __stcs(o_dh + i * 32, d);
+#else
+          o_dh[i * 32] = d;
+#endif
         }
-        ws.put(lane, DT + (size_t)(3 * HH + c0 + j) * 32, v);
       }
       tc_fence_before();
       F_TS(1, 8)
     }
-    ws.drain(lane);
   } else if (warp == W_MMA) {
     const uint32_t ring0 = smem_u32(ring);
     long long gs = 0;
     for (int s = 0; s < S; ++s) {
       const uint32_t ph = s & 1;
-      mbar_wait(&bar_a, ph);       // also: E2 of the previous step has read acc1 / acc2 (program order of the epilogue threads)
-      tc_fence_after();
-      mma_block_n<HH, NS>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, false);     // dHR = Dc . B_h
+      // dHR = Dc . B_h, chunk by chunk behind E0 (bar_a[0] also says: E2 of the previous step has read acc1 / acc2)
+      for (int kc = 0; kc < C::NCH; ++kc) mma_chunk_n<HH, NS>(tmem, 2 * HH, ring0, bar_full, bar_empty, gs, lane, kc, false, &bar_a[kc], ph, nullptr);
       if (lane == 0) umma_commit(&bar_1);
       __syncwarp();
-      mbar_wait(&bar_az, ph);
-      tc_fence_after();
-      mma_block_n<HH, NS>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, true);      // acc2 = p G Z + Dz . B_z
-      if (lane == 0) umma_commit(&bar_2z);
-      __syncwarp();
-      mbar_wait(&bar_ar, ph);
-      tc_fence_after();
-      mma_block_n<HH, NS>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, true);      // acc2 += Dr . B_r
+      // acc2 = p G Z + Dz . B_z; every chunk reports its completion: E1 refills A with Dr of that chunk
+      for (int kc = 0; kc < C::NCH; ++kc) mma_chunk_n<HH, NS>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, kc, true, &bar_az[kc], ph, &bar_2z[kc]);
+      // acc2 += Dr . B_r
+      for (int kc = 0; kc < C::NCH; ++kc) mma_chunk_n<HH, NS>(tmem, 3 * HH, ring0, bar_full, bar_empty, gs, lane, kc, true, &bar_ar[kc], ph, nullptr);
       if (lane == 0) umma_commit(&bar_2r);
       __syncwarp();
     }
