@@ -1,10 +1,13 @@
-"""bring-up check of the fused 3xTF32 cell (csrc/cell_f.cu) against the fp64 oracle: prints every error, asserts nothing."""
+"""bring-up check of the fused 3xTF32 cell (csrc/cell_f.cu) against the fp64 oracle: prints every error; exit code 2 when an output or the
+loss is off by more than 1e-4 (the GPU scripts stop there: a wrong kernel should not go on to be benchmarked)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "regt-gcn_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch
 from parity_util import W, build_cuda, is_dead, oracle_step, relerr, to_dev, twin_limits
+
+WORST = [0.0]
 
 cases = [
     ("RegionalTemporalGCN", dict(N=60, T=3, H=128, O=6, R=3, B=2, seed=8)),
@@ -33,7 +36,14 @@ for ci, (model, kw) in enumerate(cases):
     torch.cuda.synchronize()
     print(f"[{ci}] {w.name}: out {relerr(out, ref['out']):.2e} hid {relerr(hid, ref['hid']):.2e} "
           f"loss {abs(float(loss) - ref['loss']) / abs(ref['loss']):.2e}  ({time.time() - t0:.1f}s)", flush=True)
+    WORST[0] = max(WORST[0], float(relerr(out, ref['out'])), float(relerr(hid, ref['hid'])), abs(float(loss) - ref['loss']) / abs(ref['loss']))
     _, twin = twin_limits(w, B, ref)
     for k, g in ref["grads"].items():
         if not is_dead(w.model, k):
             print(f"      grad {k:45s} {relerr(m.get_parameter(k).grad, g):.2e}   (fp32 twin of the oracle: {twin.get(k, float('nan')):.2e})", flush=True)
+            if not k.endswith("_attention"):
+                WORST[0] = max(WORST[0], float(relerr(m.get_parameter(k).grad, g)) / 10.0)
+
+if WORST[0] > 1e-4:
+    print(f"FUSED CHECK: worst error {WORST[0]:.2e} > 1e-4")
+    sys.exit(2)
