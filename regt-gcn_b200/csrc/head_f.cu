@@ -47,29 +47,61 @@ __global__ void __launch_bounds__(256) k_hf_mid(float* __restrict__ a1, const fl
     w[o][0] = t.x; w[o][1] = t.y; w[o][2] = t.z; w[o][3] = t.w;
   }
   const float4 bb = __ldg(reinterpret_cast<const float4*>(b1) + lane);
-  const float b2v = lane < O ? __ldg(b2 + lane) : 0.f;
   float lsum = 0.f;
   // grid-stride over the rows (a bounded number of blocks: the loss partials are summed by one thread per output)
   for (long long q = blockIdx.x * 8ll + warp; q < BN; q += (long long)gridDim.x * 8) {
     const float4 p = reinterpret_cast<const float4*>(a1 + q * HEAD_HID)[lane];
     const float a[4] = {fmaxf(p.x + bb.x, 0.f), fmaxf(p.y + bb.y, 0.f), fmaxf(p.z + bb.z, 0.f), fmaxf(p.w + bb.w, 0.f)};
     reinterpret_cast<float4*>(a1 + q * HEAD_HID)[lane] = make_float4(a[0], a[1], a[2], a[3]);
-    float mine = 0.f;     // lane o ends up with out[o]
+    // 16 partial dot products per lane -> out[o] on lanes 2o, 2o+1 by a halving exchange: 8 + 4 + 2 + 1 + 1 = 16 shuffles per row
+    // (a full butterfly per output was 80; the kernel is shuffle-bound).  Fixed order: deterministic.
+    float s16[HF_O];
 #pragma unroll
     for (int o = 0; o < HF_O; ++o) {
       float s = a[0] * w[o][0];
       s = fmaf(a[1], w[o][1], s); s = fmaf(a[2], w[o][2], s); s = fmaf(a[3], w[o][3], s);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      if (lane == o) mine = s;
+      s16[o] = s;
     }
-    if (lane < O) {
-      const float v = mine + b2v;
-      out[q * O + lane] = v;
+    float s8[8], s4[4], s2[2];
+    {
+      const bool up = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float keep = up ? s16[i + 8] : s16[i], send = up ? s16[i] : s16[i + 8];
+        s8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    {
+      const bool up = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float keep = up ? s8[i + 4] : s8[i], send = up ? s8[i] : s8[i + 4];
+        s4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    {
+      const bool up = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = up ? s4[i + 2] : s4[i], send = up ? s4[i] : s4[i + 2];
+        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
+    float mine;
+    {
+      const bool up = lane & 2;
+      const float keep = up ? s2[1] : s2[0], send = up ? s2[0] : s2[1];
+      mine = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+    const int o = lane >> 1;     // lanes 2o and 2o+1 hold out[o] (bits 4..1 of the lane picked the halves)
+    if ((lane & 1) == 0 && o < O) {
+      const float v = mine + __ldg(b2 + o);
+      out[q * O + o] = v;
       if (y) {
-        const float diff = v - __ldg(y + q * O + lane);
+        const float diff = v - __ldg(y + q * O + o);
         lsum = fmaf(diff, diff, lsum);
-        d_out[q * O + lane] = 2.0f * diff * scale;
+        d_out[q * O + o] = 2.0f * diff * scale;
       }
     }
   }

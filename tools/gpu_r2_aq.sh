@@ -1,0 +1,14 @@
+# round 2, call AQ: k_hf_mid with the halving exchange (16 shuffles per row instead of 80)
+set -x
+mkdir -p gpurun_out
+timeout 150 python tools/fused_check.py > gpurun_out/r2aq_fused_all.log 2>&1
+rc=$?; echo "fused_check rc=$rc"
+if [ $rc -ne 0 ]; then echo "FUSED CHECK FAILED: stopping"; tail -n 30 gpurun_out/r2aq_fused_all.log; exit 1; fi
+timeout 600 python -m pytest tests/test_gpu_fused.py tests/test_gpu_large_configs.py tests/test_gpu_model_parity.py tests/test_gpu_loop.py -m gpu -q -x > gpurun_out/r2aq_pytest.log 2>&1; tail -n 2 gpurun_out/r2aq_pytest.log
+timeout 400 python bench.py --workload 5 --no-extras --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/r2aq_b5.json 2> gpurun_out/r2aq_b5.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r2aq_b5.json').read().strip().splitlines()[-1])
+k=d['kernels']
+print('cfg5', d['ms_per_step'], {n:k[n]['ms_per_step'] for n in ('k_cell_bwd_f','k_cell_fwd_f','k_gemm_kt','k_hf_mid')}, d['clocks']['sm_mhz'])
+PY
