@@ -273,6 +273,8 @@ int regt_debug_gemm_tn_multi(const float* A, int64_t lda, int64_t M, int32_t H, 
                              float* C0, float* C1, int32_t splits, const float* B2, float* C2, regt_stream_t stream);
 int regt_debug_gemm_kt(const float* AT, int64_t ntile, int32_t H, const float* B0T, const float* B1T, const float* FT,
                        float* C0, float* C1, float* C2, int32_t splits, regt_stream_t stream);
+int regt_debug_spmm_partition_host(const int32_t* rowptr, const int32_t* col, int32_t N, int32_t width, int32_t* blk_ptr,
+                                   int32_t* nblk_out, int32_t* cap_out);   /* regt_spmm_partition's algorithm on HOST arrays; cap_out = {rows, edges} a block may hold */
 int regt_debug_f_timestamps(long long* out);   /* phase clocks of the fused 3xTF32 cell kernels (REGT_F_DEBUG), [3][16][12]: forward epilogue, backward epilogue, forward MMA warp */
 int regt_debug_umma_selftest(int fmt, int variant, const float* A, const float* B, float* D, int N, int K,
                              regt_stream_t stream);

@@ -497,6 +497,19 @@ extern "C" int regt_spmm_partition(const int32_t* rowptr, const int32_t* col, in
   *nblk_out = nblk;
   return 0;
 }
+// TEST HOOK: the partition algorithm on HOST arrays (no device work): what regt_spmm_partition computes after copying the CSR back
+extern "C" int regt_debug_spmm_partition_host(const int32_t* rowptr, const int32_t* col, int32_t N, int32_t width, int32_t* blk_ptr,
+                                              int32_t* nblk_out, int32_t* cap_out) {
+  REGT_CHECK(rowptr && col && blk_ptr && nblk_out && N > 0 && width > 0 && width % 4 == 0, "spmm_partition_host: bad arguments");
+  int nb, emax;
+  regt::spmm_geometry(width, regt::spmm_ctas(), &nb, &emax);
+  REGT_CHECK(nb >= 32, "spmm_partition_host: rows of %d floats do not fit the staged kernel", width);
+  std::vector<int32_t> rp(rowptr, rowptr + N + 1), cj(col, col + rowptr[N]), blk;
+  *nblk_out = regt::spmm_partition_host(rp, cj, N, nb, emax, &blk);
+  for (size_t i = 0; i < blk.size(); ++i) blk_ptr[i] = blk[i];
+  if (cap_out) { cap_out[0] = nb; cap_out[1] = emax; }
+  return 0;
+}
 extern "C" int regt_spmm_f8_blocked(const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
                                     int32_t B, int32_t N, int32_t width, const int32_t* blk_ptr, int32_t nblk,
                                     regt_stream_t stream) {

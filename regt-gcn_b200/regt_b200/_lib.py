@@ -152,6 +152,8 @@ def load() -> C.CDLL:
                                            vp, C.c_int64, vp, vp]
     lib.regt_debug_gemm_tn_multi.restype = C.c_int
     lib.regt_debug_gemm_tn_multi.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp]
+    lib.regt_debug_spmm_partition_host.restype = C.c_int
+    lib.regt_debug_spmm_partition_host.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, c_i32p, vp]
     lib.regt_debug_gemm_kt.restype = C.c_int
     lib.regt_debug_gemm_kt.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp]
     lib.regt_debug_f_timestamps.restype = C.c_int

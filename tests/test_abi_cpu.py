@@ -133,3 +133,46 @@ def test_run_py_keeps_the_reference_flags():
     ns = mod.build_parser().parse_args("--num_timesteps_in 6 --num_timesteps_out 1 --tr 0.2 --tf occrate --dataloading_type 2 "
                                        "--epochs 50 --decomp_type regional --model RegionalTemporalGCN".split())
     assert (ns.num_timesteps_in, ns.num_timesteps_out, ns.tr, ns.tf, ns.epochs, ns.decomp_type) == (6, 1, 0.2, "occrate", 50, "regional")
+
+
+def test_spmm_partition_algorithm_on_host_arrays():
+    """regt_spmm_partition's block-cutting rule, run on host arrays (no GPU): blocks cover the rows, respect the staged kernel's
+    row and edge capacity, and on a graph whose node ids are ordered by region (contiguous regions, a few inter-region edges)
+    the cuts fall on region borders -- far fewer edges leave their block than with uniform blocks of the same count."""
+    import ctypes as C
+    import numpy as np
+    from regt_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    deg, W = 6, 96
+    sizes = rng.integers(250, 421, size=12)                   # regions of unequal size: uniform blocks cannot line up with them
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    N = int(starts[-1])
+    region = np.repeat(np.arange(12), sizes)
+    rows, cols = [], []
+    for i in range(N):
+        r0, r1 = starts[region[i]], starts[region[i] + 1]
+        nb = rng.integers(r0, r1, size=deg)                   # neighbours inside the node's region
+        if rng.random() < 0.02:
+            nb[0] = rng.integers(0, N)                        # a rare inter-region edge
+        rows += [i] * (deg + 1)
+        cols += [i] + list(nb)                                # self loop first, as the gcn_norm CSR has it
+    rowptr = np.zeros(N + 1, dtype=np.int32)
+    np.add.at(rowptr, np.asarray(rows) + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.int32)
+    col = np.asarray(cols, dtype=np.int32)
+    blk = np.zeros(N + 2, dtype=np.int32)
+    nblk = C.c_int32(0)
+    cap = np.zeros(2, dtype=np.int32)
+    rc = lib.regt_debug_spmm_partition_host(rowptr.ctypes.data, col.ctypes.data, N, W, blk.ctypes.data, C.byref(nblk), cap.ctypes.data)
+    _lib.check(rc, "regt_debug_spmm_partition_host")
+    b = blk[: nblk.value + 1]
+    assert b[0] == 0 and b[-1] == N and (np.diff(b) > 0).all()
+    assert np.diff(b).max() <= cap[0] and (rowptr[b[1:]] - rowptr[b[:-1]]).max() <= cap[1]
+    r = np.asarray(rows)
+
+    def crossing(bounds):
+        return int((np.searchsorted(bounds, r, side="right") != np.searchsorted(bounds, col, side="right")).sum())
+    uniform = np.minimum(np.arange(nblk.value + 1) * -(-N // nblk.value), N)
+    assert crossing(b) <= 0.05 * len(col) < crossing(uniform)
+    assert set(b[1:-1].tolist()) <= set(starts[1:-1].tolist())   # every interior cut is a region border
